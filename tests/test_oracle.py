@@ -1,0 +1,294 @@
+"""CPU tests that pin the oracle (oracle/) -- the checker every GPU parity test relies on.
+
+The reference holds no golden vector for this path (PARITY UNPINNED), so the
+oracle is pinned by: an independent NumPy restatement (tests/np_restatement.py), NumPy's FFT, SciPy's
+QUADPACK, the invariants of the scheme and a binary128 build of itself.
+"""
+import math
+
+import numpy as np
+import pytest
+
+from np_restatement import NpModel
+from oracle import oracle as orc
+from oracle.oracle import Oracle, OracleConfig
+
+
+def rel(a, b):
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+def smooth_field(rng, shape, amp, kmax=3):
+    """random smooth field: a few low zonal / meridional harmonics"""
+    nlat, nlon = shape
+    lam = 2 * np.pi * np.arange(nlon) / nlon
+    phi = np.pi * (np.arange(nlat) + 0.5) / nlat
+    f = np.zeros(shape)
+    for k in range(kmax + 1):
+        for l in range(1, kmax + 1):
+            a, b = rng.standard_normal(2)
+            f += np.sin(l * phi)[:, None] * (a * np.cos(k * lam) + b * np.sin(k * lam))[None, :]
+    return amp * f / np.abs(f).max()
+
+
+def generic_state(nlon, nlat, seed=0):
+    """A smooth, symmetry-free state: the filter's s1 = sum(d*w) is then well conditioned."""
+    rng = np.random.default_rng(seed)
+    u = smooth_field(rng, (nlat, nlon), 30.0)
+    u[0] = u[-1] = 0.0
+    v = smooth_field(rng, (nlat - 1, nlon), 20.0)
+    gd = 5.0e4 + smooth_field(rng, (nlat, nlon), 5.0e3)
+    ghs = 2.0e3 + smooth_field(rng, (nlat, nlon), 2.0e3)
+    for f in (gd, ghs):  # a pole is one point: single-valued scalars there
+        f[0] = f[0].mean()
+        f[-1] = f[-1].mean()
+    return u, v, gd, ghs
+
+
+# ------------------------------------------------------------------------------------------- FFTPACK
+@pytest.mark.parametrize("n", [12, 30, 36, 64, 100, 180, 360, 1440, 3600, 7200])
+def test_rfft_matches_numpy(n):
+    x = np.random.default_rng(n).standard_normal(n)
+    X = orc.rfft_forward(x)
+    ref = np.fft.rfft(x) / n
+    exp = np.zeros(n)
+    exp[0] = ref[0].real
+    for k in range(1, (n + 1) // 2):
+        exp[2 * k - 1] = 2 * ref[k].real      # a_k, rfftf1.f:87-107
+        exp[2 * k] = -2 * ref[k].imag         # b_k
+    if n % 2 == 0:
+        exp[n - 1] = ref[n // 2].real
+    assert np.abs(X - exp).max() < 5e-16 * max(1.0, math.log2(n))
+    assert np.abs(orc.rfft_backward(X) - x).max() < 1e-14
+
+
+def test_rfft_factor_order():
+    # rffti1.f:38-58: 4 first, a factor 2 moved to the front
+    assert orc.rfft_factors(360) == [2, 4, 3, 3, 5]
+    assert orc.rfft_factors(180) == [4, 3, 3, 5]
+    assert orc.rfft_factors(3600) == [4, 4, 3, 3, 5, 5]
+    with pytest.raises(orc.OracleError):
+        orc.rfft_factors(14)
+
+
+# ------------------------------------------------------------------------------------------- filter
+def test_filter_row_map_and_projection():
+    cfg = OracleConfig(num_lon=72, num_lat=37, time_step_size=600, zonal_tend_filter_cutoff_wavenumber=[5, 4, 3])
+    o = Oracle(cfg)
+    ff, fc, hf, hc = o.filter_rows()
+    nlat = 37
+    # full rows: south 1+k, north nlat-k (1-based) -> 0-based k and nlat-1-k
+    assert list(np.nonzero(ff)[0]) == [1, 2, 3, nlat - 4, nlat - 3, nlat - 2]
+    assert [fc[j] for j in (1, 2, 3, nlat - 2, nlat - 3, nlat - 4)] == [5, 4, 3, 5, 4, 3]
+    # half rows: south k (mask c_k); north flag nlat-k+1 (k=1 out of bounds) but mask nlat-k  (B2)
+    assert list(np.nonzero(hf)[0]) == [0, 1, 2, nlat - 3, nlat - 2]
+    assert [hc[h] for h in (0, 1, 2)] == [5, 4, 3]
+    assert hc[nlat - 2] == 5 and hc[nlat - 3] == 4 and hc[nlat - 4] == 3 and hf[nlat - 4] == 0
+    x = np.random.default_rng(1).standard_normal(72)
+    y = o.filter_row(False, 1, x)
+    # projection onto wavenumbers 0..c plus Re(c+1)  (B3), idempotent
+    X = np.fft.rfft(x)
+    Y = np.zeros_like(X)
+    Y[:6] = X[:6]
+    Y[6] = X[6].real
+    assert np.abs(y - np.fft.irfft(Y, 72)).max() < 2e-15
+    assert np.abs(o.filter_row(False, 1, y) - y).max() < 2e-15
+
+
+# ------------------------------------------------------------------------------------------- operators
+@pytest.mark.parametrize("adv", ["center_diff", "upwind"])
+@pytest.mark.parametrize("pass_", ["all", "fast", "slow"])
+def test_space_operators_match_numpy(adv, pass_):
+    nlon, nlat = 72, 37
+    u, v, gd, ghs = generic_state(nlon, nlat)
+    cfg = OracleConfig(num_lon=nlon, num_lat=nlat, time_step_size=600, uv_adv_scheme=adv,
+                       uv_adv_upwind_lon_beta=0.3, uv_adv_upwind_lat_beta=0.1,
+                       zonal_tend_filter_cutoff_wavenumber=[4, 3, 2])
+    o = Oracle(cfg)
+    o.set_state(u, v, gd, ghs)
+    o.run_init()
+    npm = NpModel(nlon, nlat, 600, adv=adv, beta_lon=0.3, beta_lat=0.1, cutoff=[4, 3, 2])
+    npm.ghs = ghs
+    a = o.space_operators(pass_)
+    b = npm.tend(npm.make_state(u, v, gd), pass_)
+    for x, y in zip(a, b):
+        assert rel(x, y) < 1e-13 or np.abs(y).max() == 0.0
+
+
+def test_update_state_matches_numpy():
+    nlon, nlat = 60, 31
+    u, v, gd, ghs = generic_state(nlon, nlat, seed=3)
+    o = Oracle(OracleConfig(num_lon=nlon, num_lat=nlat, time_step_size=600, zonal_tend_filter_cutoff_wavenumber=[4, 4]))
+    o.set_state(u, v, gd, ghs)
+    o.run_init()
+    npm = NpModel(nlon, nlat, 600, cutoff=[4, 4])
+    npm.ghs = ghs
+    st = npm.make_state(u, v, gd)
+    td = npm.tend(st, "all")
+    o.space_operators("all")
+    got = o.update_state_preview(123.0)
+    exp = npm.update(123.0, td, st)
+    for x, y in zip(got, exp):
+        assert rel(x, y) < 1e-14
+
+
+@pytest.mark.parametrize("case,adv,diff", [("mountain_zonal_flow", "upwind", False),
+                                           ("jet_zonal_flow", "center_diff", True),
+                                           ("steady_geostrophic_flow", "center_diff", False)])
+def test_step_matches_numpy(case, adv, diff):
+    nlon, nlat = 120, 61
+    cfg = OracleConfig(num_lon=nlon, num_lat=nlat, time_step_size=600, subcycles=6, uv_adv_scheme=adv,
+                       uv_adv_upwind_lat_beta=0.1, zonal_tend_filter_cutoff_wavenumber=[4] * 5,
+                       use_diffusion=diff, diffusion_coef=1.0e5)
+    o = Oracle(cfg)
+    o.set_initial_condition(case)
+    u, v, gd = o.state()
+    ghs = o.ghs()
+    o.run_init()
+    npm = NpModel(nlon, nlat, 600, 6, adv=adv, beta_lat=0.1, cutoff=[4] * 5, use_diffusion=diff, diffusion_coef=1.0e5)
+    npm.ghs = ghs
+    st = npm.make_state(u, v, gd)
+    for _ in range(3):
+        o.step(1)
+        st = npm.step(st)
+    ou, ov, ogd = o.state()
+    assert rel(ou, st[0]) < 1e-12 and rel(ogd, st[2]) < 1e-12
+    assert np.abs(ov - st[1]).max() < 1e-11 * max(1.0, np.abs(ou).max())
+    assert abs(o.diag()[2] - npm.beta) < 1e-12
+
+
+def test_unsplit_step_matches_numpy():
+    nlon, nlat = 72, 37
+    u, v, gd, ghs = generic_state(nlon, nlat, seed=5)
+    cfg = OracleConfig(num_lon=nlon, num_lat=nlat, time_step_size=120, split_scheme="none",
+                       zonal_tend_filter_cutoff_wavenumber=[4, 4, 4])
+    o = Oracle(cfg)
+    o.set_state(u, v, gd, ghs)
+    o.run_init()
+    npm = NpModel(nlon, nlat, 120, split="none", cutoff=[4, 4, 4])
+    npm.ghs = ghs
+    st = npm.make_state(u, v, gd)
+    o.step(2)
+    st = npm.step(npm.step(st))
+    for x, y in zip(o.state(), st[:3]):
+        assert rel(x, y) < 1e-12
+
+
+# ------------------------------------------------------------------------------------------- invariants
+def test_antisymmetry_sums_vanish():
+    """check_antisymmetry, dycore_mod.F90:794-851: the four sums are zero up to rounding."""
+    o = Oracle(OracleConfig(num_lon=120, num_lat=61, time_step_size=600, use_zonal_tend_filter=False))
+    u, v, gd, ghs = generic_state(120, 61, seed=7)
+    o.set_state(u, v, gd, ghs)
+    o.run_init()
+    o.space_operators("all")
+    sums, scale = o.check_antisymmetry()
+    assert np.all(np.abs(sums) < 1e-13 * scale)
+
+
+def test_energy_conservation_and_beta():
+    """centred scheme + qcon_modified conserves total energy to rounding."""
+    cfg = OracleConfig(num_lon=120, num_lat=61, time_step_size=600, subcycles=6,
+                       zonal_tend_filter_cutoff_wavenumber=[4] * 5)
+    o = Oracle(cfg)
+    o.set_initial_condition("rossby_haurwitz_wave")
+    o.run_init()
+    _, e0, _ = o.diag()
+    o.step(24)
+    m1, e1, beta = o.diag()
+    assert abs(e1 - e0) / e0 < 1e-13
+    assert 0 < beta - 1.0 < 1e-3
+    # the same run in binary128 conserves energy to 1e-25
+    oq = Oracle(OracleConfig(num_lon=48, num_lat=25, time_step_size=900, subcycles=4,
+                             zonal_tend_filter_cutoff_wavenumber=[4, 4]), kind="quad")
+    assert oq.lib.orc_real_bytes() == 16
+    oq.set_initial_condition("rossby_haurwitz_wave")
+    oq.run_init()
+    _, q0, _ = oq.diag()
+    oq.step(3)
+    assert oq.diag()[1] == q0
+
+
+def test_steady_geostrophic_flow_is_stationary():
+    cfg = OracleConfig(num_lon=120, num_lat=61, time_step_size=600, subcycles=6,
+                       zonal_tend_filter_cutoff_wavenumber=[4] * 5)
+    o = Oracle(cfg)
+    o.set_initial_condition("steady_geostrophic_flow")
+    u0, v0, gd0 = o.state()
+    o.run_init()
+    o.step(24)
+    u, v, gd = o.state()
+    assert np.abs(gd - gd0).max() / gd0.max() < 1e-3
+    assert np.abs(v).max() < 5e-2 and np.abs(u - u0).max() < 0.2
+
+
+def test_pole_rows():
+    """u = U = 0 on the pole rows for ever; dgd on a pole row is one zonal constant (cap formula)."""
+    cfg = OracleConfig(num_lon=72, num_lat=37, time_step_size=600, subcycles=4,
+                       zonal_tend_filter_cutoff_wavenumber=[4, 4])
+    o = Oracle(cfg)
+    o.set_initial_condition("rossby_haurwitz_wave")
+    o.run_init()
+    du, dv, dgd = o.space_operators("all")
+    assert np.all(du[0] == 0) and np.all(du[-1] == 0)
+    assert np.ptp(dgd[0]) == 0 and np.ptp(dgd[-1]) == 0
+    o.step(3)
+    u, v, gd = o.state()
+    iu, _, _ = o.iap_state()
+    assert np.all(u[0] == 0) and np.all(u[-1] == 0) and np.all(iu[0] == 0) and np.all(iu[-1] == 0)
+
+
+def test_fast_math_build_is_at_the_noise_floor():
+    """The reference is built with -Ofast; our strict and -ffast-math builds of the same source bracket
+    what any build of it can reproduce.  One model step must agree to ~1e-11 on a well conditioned case."""
+    cfg = OracleConfig(num_lon=120, num_lat=61, time_step_size=600, subcycles=6, uv_adv_scheme="upwind",
+                       uv_adv_upwind_lat_beta=0.1, zonal_tend_filter_cutoff_wavenumber=[4] * 3)
+    a, b = Oracle(cfg, "strict"), Oracle(cfg, "fast")
+    for o in (a, b):
+        o.set_initial_condition("mountain_zonal_flow")
+        o.run_init()
+        o.step(2)
+    for x, y in zip(a.state(), b.state()):
+        assert np.abs(x - y).max() < 1e-10 * max(1.0, np.abs(y).max())
+
+
+# ------------------------------------------------------------------------------------------- ICs / golden
+def test_jet_profile_matches_quadpack_golden(golden_dir):
+    d = np.load(golden_dir / "jet_gd_profile_181.npz")
+    got = np.array([orc.jet_gd_profile(float(x)) for x in d["lat"]])
+    assert np.abs(got - d["gd"]).max() / d["gd"].max() < 1e-14
+
+
+def test_jet_profile_matches_scipy_live():
+    scipy_integrate = pytest.importorskip("scipy.integrate")
+    pi = 4 * np.arctan(1.0)
+    omega, radius, g = 2 * pi / 86400.0, 6.37122e6, 9.80616
+    lat0 = pi / 7
+    lat1 = pi / 2 - lat0
+    en = np.exp(-4 / (lat1 - lat0) ** 2)
+
+    def integrand(lat):
+        u = 0.0 if (lat <= lat0 or lat >= lat1) else 80.0 / en * np.exp(1 / (lat - lat0) / (lat - lat1))
+        return radius * u * (2 * omega * np.sin(lat) + np.tan(lat) / radius * u)
+
+    for lat in (0.3, 0.6, 0.8, 1.0, 1.3, 1.5):
+        r, _ = scipy_integrate.quad(integrand, -0.5 * pi, lat, epsabs=1e-10, epsrel=1e-3, limit=500)
+        assert abs(orc.jet_gd_profile(lat) - (g * 1e4 - r)) < 1e-9
+
+
+@pytest.mark.parametrize("name", ["rh_36x19_csp2", "rh_72x37_nosplit", "mz_60x31_upwind", "jz_72x37_diffusion",
+                                  "sg_48x25_isp", "mz_48x25_weno"])
+def test_oracle_reproduces_committed_golden(name, golden_dir):
+    from golden.make_golden import CASES
+    d = np.load(golden_dir / f"case_{name}.npz")
+    kw, tc, n = CASES[name]
+    o = Oracle(OracleConfig(**kw))
+    o.set_initial_condition(tc)
+    for x, k in zip(o.state(), ("u0", "v0", "gd0")):
+        assert np.array_equal(x, d[k])
+    o.run_init()
+    o.step(n)
+    for x, k in zip(o.state(), ("u1", "v1", "gd1")):
+        assert np.abs(x - d[k]).max() <= 1e-12 * max(1.0, np.abs(d[k]).max())
+    m, e, b = o.diag()
+    assert abs(m - d["mass"][-1]) <= 1e-14 * abs(m) and abs(e - d["energy"][-1]) <= 1e-14 * abs(e)
