@@ -1,0 +1,289 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the barotropic shallow-water time step (BASELINE.json metric) on N B200s.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (libgmd.so, C ABI)
+    python bench.py --impl reference --steps K --warmup W    # the reference's serial CPU algorithm (oracle port)
+
+One "step" = one model step (time_integrate + diag_run, src/dycore_mod.F90:131-140) of the whole globe.
+metric = grid-point updates/s = num_lon * num_lat * K / t, whole job.  Workload (BASELINE.json configs[3], the
+configuration the metric is quoted on): steady geostrophic flow on the 0.1 degree grid 3600x1801, predict_correct +
+beta, csp2 with S subcycles, centred advection, zonal filter on 20 rows per pole.  The reference ships no namelist
+for this grid; dt, S and the cutoff vector are builder-chosen and reported in `config`.
+
+  value     inputs resident in HBM when the timed region starts; K steps between CUDA events; max over ranks
+  e2e       through the C ABI with HOST buffers: gmd_set_state (H2D of u,v,gd,ghs) + K x {gmd_step(1) +
+            gmd_get_diag (D2H)} + gmd_get_state (D2H of u,v,gd), wall clock around the calls
+  roofline  the fused stage kernel (S2 variant) timed alone with CUDA events; algorithmic bytes = 13 words/column
+  cpu_baseline  the CPU oracle (-O3 -ffast-math, as the reference's -Ofast), 1 thread (the reference is serial),
+            on a bounded sample: the same configuration on a 900x451 grid
+Multi-GPU (torchrun, one rank per GPU): latitude bands, NCCL halo exchange + allreduce inside libgmd;
+fixed global grid => "strong" scaling.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (test case, kwargs)
+    "sg_0.1deg": ("steady_geostrophic_flow",
+                  dict(num_lon=3600, num_lat=1801, time_step_size=10.0, subcycles=10, split_scheme="csp2",
+                       zonal_tend_filter_cutoff_wavenumber=[4] * 20)),
+    "rh_0.05deg": ("rossby_haurwitz_wave",
+                   dict(num_lon=7200, num_lat=3601, time_step_size=2.0, subcycles=10, split_scheme="csp2",
+                        zonal_tend_filter_cutoff_wavenumber=[4] * 20)),
+    "jz_0.25deg": ("jet_zonal_flow",
+                   dict(num_lon=1440, num_lat=721, time_step_size=30.0, subcycles=6, split_scheme="csp2",
+                        zonal_tend_filter_cutoff_wavenumber=[4] * 20, use_diffusion=True, diffusion_coef=6.0e3)),
+    "rh_1deg": ("rossby_haurwitz_wave",
+                dict(num_lon=360, num_lat=181, time_step_size=240.0, subcycles=6, split_scheme="csp2",
+                     zonal_tend_filter_cutoff_wavenumber=[4] * 5)),
+}
+CPU_SAMPLE_GRID = (900, 451)
+
+
+def initial_condition(test_case, kw):
+    """analytic IC on the host (synthetic input: the reference's test-case formulas, gamil_dycore_b200/ics.py)"""
+    from gamil_dycore_b200 import ics
+    if test_case in ics.CASES:
+        return ics.CASES[test_case](kw["num_lon"], kw["num_lat"])
+    from oracle.oracle import Oracle, OracleConfig   # jet: needs the QAGS quadrature restated in oracle/quadrature.c
+    o = Oracle(OracleConfig(**kw))
+    o.set_initial_condition(test_case)
+    u, v, gd = o.state()
+    ghs = o.ghs()
+    o.close()
+    return u, v, gd, ghs
+
+
+class ClockSampler(threading.Thread):
+    """samples SM clock + throttle reasons of one GPU during the timed region (pynvml; nvidia-smi fallback)"""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.samples, self.reasons, self.max_mhz = index, False, [], set(), None
+        self.nv = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+                 0x80: "hw_power_brake_slowdown"}
+        while not self.stop_flag:
+            try:
+                if self.nv:
+                    self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                    r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(
+                        self.nv, "nvmlDeviceGetCurrentClocksEventReasons") else self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                    for bit, nm in names.items():
+                        if r & bit:
+                            self.reasons.add(nm)
+                else:
+                    import subprocess
+                    out = subprocess.run(["nvidia-smi", f"--id={self.index}", "--query-gpu=clocks.sm,clocks.max.sm",
+                                          "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                    a, b = out.strip().split(",")
+                    self.samples.append(int(a))
+                    self.max_mhz = int(b)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def cpu_oracle_rate(test_case, kw, nsteps, warm=1):
+    """grid-point updates/s of the serial CPU oracle on the bounded sample grid"""
+    from oracle.oracle import Oracle, OracleConfig
+    skw = dict(kw)
+    skw["num_lon"], skw["num_lat"] = CPU_SAMPLE_GRID
+    o = Oracle(OracleConfig(**skw), kind="fast")
+    o.set_initial_condition(test_case)
+    o.run_init()
+    o.step(warm)
+    t0 = time.perf_counter()
+    o.step(nsteps)
+    t = time.perf_counter() - t0
+    o.close()
+    return CPU_SAMPLE_GRID[0] * CPU_SAMPLE_GRID[1] * nsteps / t, t / nsteps
+
+
+def run_reference(args):
+    """the reference's own (serial, CPU) implementation of the path: not buildable here (Fortran), so the oracle port"""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    test_case, kw = WORKLOADS[args.workload]
+    from oracle import oracle as orc
+    orc.build()
+    rate, spp = cpu_oracle_rate(test_case, kw, args.steps, warm=max(args.warmup, 0))
+    cpu = {"value": rate, "unit": "grid-point-updates/s", "cores": 1, "kind": "port",
+           "sample": f"same configuration on a {CPU_SAMPLE_GRID[0]}x{CPU_SAMPLE_GRID[1]} grid, {args.steps} steps, 1 thread "
+                     "(the reference is serial: no OpenMP/MPI in src/), gcc -O3 -ffast-math"}
+    line = {"impl": "reference", "metric": "grid-point-updates/s", "value": rate, "unit": "grid-point-updates/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": spp * 1e3,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config_dict(args.workload, kw, 1), "cpu_baseline": cpu,
+            "e2e": {"value": rate, "unit": "grid-point-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def config_dict(name, kw, ngpu):
+    return {"workload": f"{name}: {WORKLOADS[name][0]} {kw['num_lon']}x{kw['num_lat']}", "dt_s": kw["time_step_size"],
+            "split_scheme": kw["split_scheme"], "subcycles": kw["subcycles"], "uv_adv_scheme": kw.get("uv_adv_scheme", "center_diff"),
+            "filter_rows_per_pole": sum(1 for c in kw["zonal_tend_filter_cutoff_wavenumber"] if c),
+            "filter_cutoff": max(kw["zonal_tend_filter_cutoff_wavenumber"]),
+            "use_diffusion": bool(kw.get("use_diffusion", False)),
+            "decomposition": f"{ngpu} latitude band(s)", "l2_policy": "per-step working set (>= 16 fields x 51.9 MB at 0.1 deg) exceeds the 126 MB L2"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=4)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="sg_0.1deg", choices=list(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import gamil_dycore_b200 as gmd
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    test_case, kw = WORKLOADS[args.workload]
+    W = max(args.warmup, 3)
+    K = args.steps
+    u, v, gd, ghs = initial_condition(test_case, kw)
+    ncol = kw["num_lon"] * kw["num_lat"]
+
+    d = gmd.Dycore(gmd.Config(rank=rank, nranks=world, device=local, **kw))
+    if world > 1:
+        import torch.distributed as dist
+        uid = [gmd.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        d.comm_init(uid[0])
+    if args.no_graph:
+        d.set_graph_mode(False)
+    stream = torch.cuda.current_stream()
+    d.set_stream(stream.cuda_stream)
+    d.set_state(u, v, gd, ghs)
+    d.run_init()
+    m0, e0, _ = d.diag()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput ----------------------------------------------------------------------
+    d.step(W)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = d.kernel_launches()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    d.step_async(K)
+    ev1.record(stream)
+    d.sync()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = d.kernel_launches() - l0
+    sampler.stop_flag = True
+    sampler.join()
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = ncol * K / (ms * 1e-3)
+    m1, e1, beta = d.diag()
+
+    # ---- roofline of the dominant kernel ------------------------------------------------------------------
+    kms, kbytes = d.time_stage_kernel(20)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = kbytes / (kms * 1e-3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "stage_kernel_traffic.json"))).get(args.workload)
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": "k_stage<fast|all, S2>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
+                "ms_per_launch": kms, "algorithmic_bytes_per_launch": kbytes,
+                "step_algorithmic_GBps": d.algorithmic_bytes_per_column_step() * value / 1e9 / max(world, 1),
+                "step_frac_per_gpu": d.algorithmic_bytes_per_column_step() * value / 1e9 / max(world, 1) / peak}
+
+    # ---- end to end through the C ABI with host buffers ----------------------------------------------------
+    barrier()
+    t0 = time.perf_counter()
+    d.set_state(u, v, gd, ghs)
+    for _ in range(K):
+        d.step(1)
+        d.diag()
+    uo, vo, gdo = d.state()
+    barrier()
+    te = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([te], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        te = float(t.item())
+    r0, r1 = d.band()
+    h2d = 4 * (r1 - r0 + 4) * kw["num_lon"] * 8
+    d2h = 3 * (r1 - r0) * kw["num_lon"] * 8 + K * 3 * 4096 * 8
+    e2e = {"value": ncol * K / te, "unit": "grid-point-updates/s", "h2d_bytes_per_step": h2d / K, "d2h_bytes_per_step": d2h / K,
+           "what": f"gmd_set_state + {K} x (gmd_step(1) + gmd_get_diag) + gmd_get_state, host arrays in and out"}
+
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu_baseline and world == 1:
+            rate, spp = cpu_oracle_rate(test_case, kw, 8)
+            cpu = {"value": rate, "unit": "grid-point-updates/s", "cores": 1, "kind": "port",
+                   "sample": f"same configuration on a {CPU_SAMPLE_GRID[0]}x{CPU_SAMPLE_GRID[1]} grid, 8 steps, 1 thread "
+                             "(the reference is serial), oracle built with gcc -O3 -ffast-math"}
+        line = {"metric": "grid-point-updates/s", "value": value, "unit": "grid-point-updates/s", "n_gpus": world,
+                "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_dict(args.workload, kw, world),
+                "sim_days_per_day": kw["time_step_size"] * K / (ms * 1e-3), "clocks": sampler.summary(), "e2e": e2e,
+                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+                "conservation": {"mass_rel_drift": abs(m1 / m0 - 1), "energy_rel_drift": abs(e1 / e0 - 1), "beta": beta}}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

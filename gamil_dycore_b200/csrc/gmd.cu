@@ -1,0 +1,1429 @@
+// gmd.cu -- model object, step driver and C ABI (include/gmd.h) of the B200-native barotropic step.
+//
+// Control flow mirrors src/dycore_mod.F90: time_integrate (:654-669) -> csp2_splitting (:671-687) /
+// isp_splitting (:689-752) / predict_correct (:754-792) -> space_operators + update_state, followed by
+// ordinary_diffusion (src/diffusion_mod.F90:74-217) and diag_run (src/diag_mod.F90:42-89).  Everything
+// between two host calls is stream-ordered on one CUDA stream; beta never leaves the device.
+#include "../../include/gmd.h"
+#include "gmd_kernels.cuh"
+#include "gmd_mesh.h"
+
+#include <dlfcn.h>
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+using namespace gmd;
+
+// ---------------------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+static int fail(int code, const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CK(call)                                                                                         \
+  do {                                                                                                   \
+    cudaError_t e_ = (call);                                                                             \
+    if (e_ != cudaSuccess)                                                                               \
+      return fail(GMD_ERR_CUDA, "CUDA error %s at %s:%d (%s)", cudaGetErrorName(e_), __FILE__, __LINE__, \
+                  cudaGetErrorString(e_));                                                               \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------------------
+// NCCL, bound at run time (only when nranks > 1) so that the library loads on hosts without it
+// ---------------------------------------------------------------------------------------------------------
+struct NcclId128 {  // ncclUniqueId (NCCL_UNIQUE_ID_BYTES = 128), passed by value
+  char b[128];
+};
+struct NcclApi {
+  void *lib = nullptr;
+  int (*GetUniqueId)(void *) = nullptr;
+  int (*CommInitRank)(void **, int, NcclId128, int) = nullptr;
+  int (*CommDestroy)(void *) = nullptr;
+  int (*Send)(const void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+  int (*Recv)(void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+  int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  const char *(*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+static int nccl_load() {
+  if (g_nccl.lib) return 0;
+  void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) return fail(GMD_ERR_COMM, "cannot load libnccl.so.2: %s", dlerror());
+#define SYM(field, name)                                                        \
+  *(void **)(&g_nccl.field) = dlsym(h, name);                                   \
+  if (!g_nccl.field) return fail(GMD_ERR_COMM, "libnccl lacks symbol %s", name)
+  SYM(GetUniqueId, "ncclGetUniqueId");
+  SYM(CommInitRank, "ncclCommInitRank");
+  SYM(CommDestroy, "ncclCommDestroy");
+  SYM(Send, "ncclSend");
+  SYM(Recv, "ncclRecv");
+  SYM(AllReduce, "ncclAllReduce");
+  SYM(GroupStart, "ncclGroupStart");
+  SYM(GroupEnd, "ncclGroupEnd");
+  SYM(GetErrorString, "ncclGetErrorString");
+#undef SYM
+  g_nccl.lib = h;
+  return 0;
+}
+#define NK(call)                                                                                              \
+  do {                                                                                                        \
+    int r_ = (call);                                                                                          \
+    if (r_ != 0) return fail(GMD_ERR_COMM, "NCCL error %d (%s) at %s:%d", r_, g_nccl.GetErrorString(r_), __FILE__, __LINE__); \
+  } while (0)
+enum { NCCL_F64 = 8, NCCL_SUM = 0 };
+
+// ---------------------------------------------------------------------------------------------------------
+// model
+// ---------------------------------------------------------------------------------------------------------
+enum { KIND_U = 0, KIND_V = 1, KIND_G = 2 };
+
+struct State {
+  double *U = nullptr, *V = nullptr, *gd = nullptr;
+};
+struct Tend {
+  double *U = nullptr, *V = nullptr, *gd = nullptr;
+};
+
+struct gmd_model {
+  gmd_config cfg;
+  HostMesh mesh;
+  Geo geo;
+  int nr = 0;            // owned rows
+  size_t fld_elems = 0;  // (nr + 2 GHOST) * nlon
+  int dev = 0;
+  cudaStream_t stream = nullptr, own_stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool run_inited = false, have_state = false;
+  int step = 0;
+  long long launches = 0;
+
+  // device tables
+  std::vector<double *> tab_allocs;
+  unsigned char *d_flags_alloc = nullptr;
+  Tab tab;
+  double *d_basis = nullptr;
+  int ncoef_max = 0;
+
+  // polar items: [0] all/fast pass, [1] slow pass, [2] plain filter (diffusion)
+  PolarItem *d_items[3] = {nullptr, nullptr, nullptr};
+  int n_items[3] = {0, 0, 0};
+
+  // buffers
+  std::vector<double *> free_[3];
+  std::vector<double *> all_allocs;
+  std::map<double *, int> refc;  // base pointer (row r0) -> refcount
+  std::map<double *, int> kind_of;
+
+  State cur;
+  double *ghs = nullptr;
+  Tend tendOld, tendNew, tendA, tendB;  // tendA/B: isp only
+  double *d_partials = nullptr;
+  int n_partials = 0;
+  double *d_ip = nullptr;    // {ip1, ip2}
+  double *d_sums = nullptr;  // {mass, energy}
+  double *d_beta = nullptr;
+  double *d_ring = nullptr;  // [RING][3]
+  int *d_ctr = nullptr;      // device step counter (ring slot = ctr % RING)
+  static const int RING = 4096;
+  // weno / diffusion scratch (lazily acquired, kept)
+  double *w_u = nullptr, *w_v = nullptr;
+  double *w_fpu = nullptr, *w_fnu = nullptr, *w_fpv = nullptr, *w_fnv = nullptr, *w_fu = nullptr, *w_fv = nullptr;
+  double *w_alon_u = nullptr, *w_alat_u = nullptr, *w_alon_v = nullptr, *w_alat_v = nullptr;
+  double *d_ud = nullptr, *d_vd = nullptr, *d_gdd = nullptr, *d_ud2 = nullptr, *d_vd2 = nullptr, *d_gdd2 = nullptr;
+
+  // stage launch geometry
+  int nbx = 0, nchunks = 0, rows_per_cta = 0;
+  int ew_blocks = 0;  // grid of element-wise kernels
+
+  // comm
+  void *comm = nullptr;
+
+  // graphs
+  bool graph_mode = true;
+  struct GraphEntry {
+    std::vector<double *> key;
+    cudaGraphExec_t exec;
+    long long launches;
+    State out;
+  };
+  std::vector<GraphEntry> graphs;
+  bool capturing = false;
+  bool dry = false;  // bookkeeping-only pass of the step logic (graph replay): no launches
+
+  float last_ms = 0.f;
+  bool span_open = false;
+  int pending_steps = 0;
+};
+
+static int set_dev(gmd_model *m) {
+  CK(cudaSetDevice(m->dev));
+  return 0;
+}
+
+// ---- buffer pool --------------------------------------------------------------------------------------
+static int acquire(gmd_model *m, int kind, double **out) {
+  if (!m->free_[kind].empty()) {
+    *out = m->free_[kind].back();
+    m->free_[kind].pop_back();
+  } else {
+    if (m->capturing) return fail(GMD_ERR_STATE, "buffer pool exhausted during graph capture");
+    double *p = nullptr;
+    CK(cudaMalloc(&p, m->fld_elems * sizeof(double)));
+    CK(cudaMemsetAsync(p, 0, m->fld_elems * sizeof(double), m->stream));
+    m->all_allocs.push_back(p);
+    *out = p + (size_t)GHOST * m->geo.nlon;
+    m->kind_of[*out] = kind;
+  }
+  m->refc[*out] = 1;
+  return 0;
+}
+static void retain(gmd_model *m, double *p) { m->refc[p]++; }
+static void release(gmd_model *m, double *p) {
+  if (!p) return;
+  if (--m->refc[p] == 0) m->free_[m->kind_of[p]].push_back(p);
+}
+static int new_state(gmd_model *m, State *s, double *shared_gd) {
+  int r;
+  if ((r = acquire(m, KIND_U, &s->U))) return r;
+  if ((r = acquire(m, KIND_V, &s->V))) return r;
+  if (shared_gd) {
+    s->gd = shared_gd;
+    retain(m, shared_gd);
+  } else if ((r = acquire(m, KIND_G, &s->gd)))
+    return r;
+  return 0;
+}
+static void release_state(gmd_model *m, State *s) {
+  release(m, s->U);
+  release(m, s->V);
+  release(m, s->gd);
+  s->U = s->V = s->gd = nullptr;
+}
+static int new_tend(gmd_model *m, Tend *t) {
+  int r;
+  if ((r = acquire(m, KIND_U, &t->U))) return r;
+  if ((r = acquire(m, KIND_V, &t->V))) return r;
+  if ((r = acquire(m, KIND_G, &t->gd))) return r;
+  return 0;
+}
+
+// ---- tables -------------------------------------------------------------------------------------------
+static int upload_table(gmd_model *m, const std::vector<double> &h, const double **dptr) {
+  double *d = nullptr;
+  CK(cudaMalloc(&d, h.size() * sizeof(double)));
+  CK(cudaMemcpy(d, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice));
+  m->tab_allocs.push_back(d);
+  *dptr = d + TPAD;
+  return 0;
+}
+
+static int build_tables(gmd_model *m) {
+  HostMesh &M = m->mesh;
+  const int nlat = M.nlat;
+  const size_t n = (size_t)nlat + 2 * TPAD;
+  auto mk = [&](double fill) { return std::vector<double>(n, fill); };
+  std::vector<double> q_fdlon = mk(0), q_hdlon = mk(0), q_fdlat = mk(0), q_hdlat = mk(0), cor1 = mk(0), cor2 = mk(0),
+                      r_fdlon = mk(0), hc_hdlat = mk(0), h_fdlon = mk(0), h_fdlat = mk(0);
+  for (int j = 0; j < nlat; j++) {
+    const size_t k = (size_t)(j + TPAD);
+    q_fdlon[k] = 0.25 / M.full_dlon[k];
+    q_fdlat[k] = 0.25 / M.full_dlat[k];
+    r_fdlon[k] = 1.0 / M.full_dlon[k];
+    h_fdlon[k] = 0.5 / M.full_dlon[k];
+    h_fdlat[k] = 0.5 / M.full_dlat[k];
+    cor1[k] = M.half_cos[k - 1] / M.full_cos[k];
+    cor2[k] = M.half_cos[k] / M.full_cos[k];
+    if (j < nlat - 1) {
+      q_hdlon[k] = 0.25 / M.half_dlon[k];
+      q_hdlat[k] = 0.25 / M.half_dlat[k];
+      hc_hdlat[k] = M.half_cos[k] / M.half_dlat[k];
+    }
+  }
+  int r;
+  // padded entries of the divisor tables must not be 0 (they are multiplied by exact zeros, never used)
+  std::vector<double> fdlon = M.full_dlon, hdlon = M.half_dlon, fdlat = M.full_dlat, hdlat = M.half_dlat;
+  for (size_t k = 0; k < n; k++) {
+    if (fdlon[k] == 0.0) fdlon[k] = 1.0;
+    if (hdlon[k] == 0.0) hdlon[k] = 1.0;
+    if (fdlat[k] == 0.0) fdlat[k] = 1.0;
+    if (hdlat[k] == 0.0) hdlat[k] = 1.0;
+  }
+  Tab &t = m->tab;
+  memset(&t, 0, sizeof t);
+  if ((r = upload_table(m, M.full_cos, &t.cosf))) return r;
+  if ((r = upload_table(m, M.half_cos, &t.cosh))) return r;
+  if ((r = upload_table(m, M.full_f, &t.ff))) return r;
+  if ((r = upload_table(m, M.full_c, &t.fc))) return r;
+  if ((r = upload_table(m, fdlon, &t.fdlon))) return r;
+  if ((r = upload_table(m, hdlon, &t.hdlon))) return r;
+  if ((r = upload_table(m, fdlat, &t.fdlat))) return r;
+  if ((r = upload_table(m, hdlat, &t.hdlat))) return r;
+  if ((r = upload_table(m, q_fdlon, &t.q_fdlon))) return r;
+  if ((r = upload_table(m, q_hdlon, &t.q_hdlon))) return r;
+  if ((r = upload_table(m, q_fdlat, &t.q_fdlat))) return r;
+  if ((r = upload_table(m, q_hdlat, &t.q_hdlat))) return r;
+  if ((r = upload_table(m, cor1, &t.cor1))) return r;
+  if ((r = upload_table(m, cor2, &t.cor2))) return r;
+  if ((r = upload_table(m, r_fdlon, &t.r_fdlon))) return r;
+  if ((r = upload_table(m, hc_hdlat, &t.hc_hdlat))) return r;
+  if ((r = upload_table(m, h_fdlon, &t.h_fdlon))) return r;
+  if ((r = upload_table(m, h_fdlat, &t.h_fdlat))) return r;
+
+  // row flags
+  std::vector<unsigned char> fl(n, 0);
+  for (int j = 0; j < nlat; j++) {
+    unsigned char f = 0;
+    if (j >= 1 && j <= nlat - 2 && M.flag_full[(size_t)j]) f |= FL_DU | FL_DGD;
+    if (j <= nlat - 2 && M.flag_half[(size_t)j]) f |= FL_DV;
+    if (j == 0 || j == nlat - 1) f |= FL_POLE;
+    fl[(size_t)(j + TPAD)] = f;
+  }
+  CK(cudaMalloc(&m->d_flags_alloc, n));
+  CK(cudaMemcpy(m->d_flags_alloc, fl.data(), n, cudaMemcpyHostToDevice));
+  t.flags = m->d_flags_alloc + TPAD;
+
+  // filter basis: row 0 = 1, row 2k-1 = cos(k x_i), row 2k = sin(k x_i), x_i = 2 pi i / nlon
+  const int nlon = M.nlon;
+  const int cmax = std::max(M.cutoff_max, 0);
+  m->ncoef_max = 2 * (cmax + 1);
+  {
+    std::vector<double> B((size_t)m->ncoef_max * nlon);
+    const long double twopi = 8.0L * atanl(1.0L);
+    for (int mm = 0; mm < m->ncoef_max; mm++) {
+      const int k = (mm + 1) / 2;
+      for (int i = 0; i < nlon; i++) {
+        const long long rr = ((long long)k * i) % nlon;  // exact argument reduction
+        const long double ang = twopi * (long double)rr / (long double)nlon;
+        B[(size_t)mm * nlon + i] = (mm == 0) ? 1.0 : ((mm & 1) ? (double)cosl(ang) : (double)sinl(ang));
+      }
+    }
+    CK(cudaMalloc(&m->d_basis, B.size() * sizeof(double)));
+    CK(cudaMemcpy(m->d_basis, B.data(), B.size() * sizeof(double), cudaMemcpyHostToDevice));
+  }
+
+  // polar items for this band
+  const int r0 = m->geo.r0, r1 = m->geo.r1;
+  std::vector<PolarItem> it[3];
+  for (int j = r0; j < r1; j++) {
+    const bool fullrow = (j >= 1 && j <= nlat - 2);
+    if (fullrow && M.flag_full[(size_t)j]) {
+      PolarItem a = {IT_DU, j, M.cut_full[(size_t)j], 0};
+      PolarItem g = {IT_DGD, j, M.cut_full[(size_t)j], 0};
+      it[0].push_back(a);
+      it[0].push_back(g);
+      it[1].push_back(a);
+      it[2].push_back(a);
+      it[2].push_back(g);
+    }
+    if (j <= nlat - 2 && M.flag_half[(size_t)j]) {
+      PolarItem v = {IT_DV, j, M.cut_half[(size_t)j], 0};
+      it[0].push_back(v);
+      it[1].push_back(v);
+      it[2].push_back(v);
+    }
+    if (j == 0) it[0].push_back(PolarItem{IT_POLE_S, j, -1, 0});
+    if (j == nlat - 1) it[0].push_back(PolarItem{IT_POLE_N, j, -1, 0});
+  }
+  for (int k = 0; k < 3; k++) {
+    m->n_items[k] = (int)it[k].size();
+    if (m->n_items[k]) {
+      CK(cudaMalloc(&m->d_items[k], it[k].size() * sizeof(PolarItem)));
+      CK(cudaMemcpy(m->d_items[k], it[k].data(), it[k].size() * sizeof(PolarItem), cudaMemcpyHostToDevice));
+    }
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------------------------
+typedef void (*stage_fn)(const StageArgs);
+template <int MODE>
+static stage_fn pick_stage_mode(int pass, int adv) {
+  if (pass == PASS_FAST) return k_stage<PASS_FAST, ADV_CENTER, MODE>;
+  if (pass == PASS_ALL) {
+    if (adv == ADV_CENTER) return k_stage<PASS_ALL, ADV_CENTER, MODE>;
+    if (adv == ADV_UPWIND) return k_stage<PASS_ALL, ADV_UPWIND, MODE>;
+    return k_stage<PASS_ALL, ADV_WENO, MODE>;
+  }
+  if (adv == ADV_CENTER) return k_stage<PASS_SLOW, ADV_CENTER, MODE>;
+  if (adv == ADV_UPWIND) return k_stage<PASS_SLOW, ADV_UPWIND, MODE>;
+  return k_stage<PASS_SLOW, ADV_WENO, MODE>;
+}
+static stage_fn pick_stage(int pass, int adv, int mode) {
+  switch (mode) {
+    case MODE_S1: return pick_stage_mode<MODE_S1>(pass, adv);
+    case MODE_S2: return pick_stage_mode<MODE_S2>(pass, adv);
+    case MODE_S3A: return pick_stage_mode<MODE_S3A>(pass, adv);
+    default: return pick_stage_mode<MODE_EVAL>(pass, adv);
+  }
+}
+
+static int post_launch(gmd_model *m) {
+  m->launches++;
+  if (m->dry) return 0;
+  cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) return fail(GMD_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+// halo rows of one field: send my top `ns` rows north / bottom `nn` rows south, receive the matching ghosts
+static int exchange_field(gmd_model *m, double *f, int ns, int nn) {
+  const int nlon = m->geo.nlon, nr = m->nr;
+  const int rank = m->cfg.rank, np = m->cfg.nranks;
+  if (rank + 1 < np) {
+    NK(g_nccl.Send(f + (size_t)(nr - ns) * nlon, (size_t)ns * nlon, NCCL_F64, rank + 1, m->comm, m->stream));
+    NK(g_nccl.Recv(f + (size_t)nr * nlon, (size_t)nn * nlon, NCCL_F64, rank + 1, m->comm, m->stream));
+  }
+  if (rank > 0) {
+    NK(g_nccl.Send(f, (size_t)nn * nlon, NCCL_F64, rank - 1, m->comm, m->stream));
+    NK(g_nccl.Recv(f - (ptrdiff_t)ns * nlon, (size_t)ns * nlon, NCCL_F64, rank - 1, m->comm, m->stream));
+  }
+  return 0;
+}
+// ghosts the stage kernel needs: south U,V,gd row r0-1; north U,V row r1, gd rows r1, r1+1
+static int exchange_state(gmd_model *m, const State &s, bool with_gd) {
+  if (m->cfg.nranks == 1 || m->dry) return 0;
+  if (!m->comm) return fail(GMD_ERR_COMM, "gmd_comm_init has not been called on this rank");
+  NK(g_nccl.GroupStart());
+  int r;
+  if ((r = exchange_field(m, s.U, 1, 1))) return r;
+  if ((r = exchange_field(m, s.V, 1, 1))) return r;
+  if (with_gd && (r = exchange_field(m, s.gd, 1, 2))) return r;
+  NK(g_nccl.GroupEnd());
+  return 0;
+}
+static int exchange_tend3(gmd_model *m, double *a, double *b, double *c, int ns, int nn) {
+  if (m->cfg.nranks == 1 || m->dry) return 0;
+  if (!m->comm) return fail(GMD_ERR_COMM, "gmd_comm_init has not been called on this rank");
+  NK(g_nccl.GroupStart());
+  int r;
+  if (a && (r = exchange_field(m, a, ns, nn))) return r;
+  if (b && (r = exchange_field(m, b, ns, nn))) return r;
+  if (c && (r = exchange_field(m, c, ns, nn))) return r;
+  NK(g_nccl.GroupEnd());
+  return 0;
+}
+static int allreduce2(gmd_model *m, double *d) {
+  if (m->cfg.nranks == 1 || m->dry) return 0;
+  if (!m->comm) return fail(GMD_ERR_COMM, "gmd_comm_init has not been called on this rank");
+  NK(g_nccl.AllReduce(d, d, 2, NCCL_F64, NCCL_SUM, m->comm, m->stream));
+  return 0;
+}
+
+static int ensure_weno(gmd_model *m) {
+  if (m->w_fpu) return 0;
+  int r;
+  double **us[] = {&m->w_fpu, &m->w_fnu, &m->w_fu, &m->w_alon_u, &m->w_alat_u};
+  double **vs[] = {&m->w_fpv, &m->w_fnv, &m->w_fv, &m->w_alon_v, &m->w_alat_v};
+  for (auto p : us)
+    if ((r = acquire(m, KIND_U, p))) return r;
+  for (auto p : vs)
+    if ((r = acquire(m, KIND_V, p))) return r;
+  return 0;
+}
+static int ensure_uv(gmd_model *m) {
+  if (m->w_u) return 0;
+  int r;
+  if ((r = acquire(m, KIND_U, &m->w_u))) return r;
+  if ((r = acquire(m, KIND_V, &m->w_v))) return r;
+  return 0;
+}
+
+// derived u, v of state s on rows [max(r0-1,0), min(r1+1,nlat))
+static int derive_uv(gmd_model *m, const State &s) {
+  int r;
+  if ((r = ensure_uv(m))) return r;
+  const int ja = std::max(m->geo.r0 - 1, 0), jb = std::min(m->geo.r1 + 1, m->geo.nlat);
+  if (!m->dry) k_derive<<<m->ew_blocks, 256, 0, m->stream>>>(m->geo, ja, jb, s.U, s.V, s.gd, m->w_u, m->w_v, nullptr);
+  return post_launch(m);
+}
+
+// WENO advection terms of state E into w_alon_u .. (src/weno_mod.F90:69-233)
+static int weno_terms(gmd_model *m, const State &E) {
+  int r;
+  if (m->cfg.nranks > 1) return fail(GMD_ERR_ARG, "uv_adv_scheme='weno' is single-GPU only in this build");
+  if ((r = ensure_weno(m))) return r;
+  if ((r = derive_uv(m, E))) return r;
+  WenoArgs a;
+  a.g = m->geo;
+  a.t = m->tab;
+  a.u = m->w_u; a.v = m->w_v; a.U = E.U; a.V = E.V;
+  a.fpu = m->w_fpu; a.fnu = m->w_fnu; a.fpv = m->w_fpv; a.fnv = m->w_fnv;
+  a.fu = m->w_fu; a.fv = m->w_fv;
+  a.alon_u = m->w_alon_u; a.alat_u = m->w_alat_u; a.alon_v = m->w_alon_v; a.alat_v = m->w_alat_v;
+  for (int dir = 0; dir < 2; dir++) {
+    a.dir = dir;
+    if (!m->dry) k_weno_split<<<m->ew_blocks, 256, 0, m->stream>>>(a);
+    if ((r = post_launch(m))) return r;
+    if (!m->dry) k_weno_flux<<<m->ew_blocks, 256, 0, m->stream>>>(a);
+    if ((r = post_launch(m))) return r;
+    if (!m->dry) k_weno_adv<<<m->ew_blocks, 256, 0, m->stream>>>(a);
+    if ((r = post_launch(m))) return r;
+  }
+  return 0;
+}
+
+// one fused operator evaluation (+ update / store / dots) of state E
+static int stage(gmd_model *m, int pass, int mode, const State &E, const State *O, double dt, State *N, Tend *T,
+                 const Tend *P) {
+  int r;
+  const int adv = m->cfg.uv_adv_scheme;
+  if (pass != PASS_FAST && adv == ADV_WENO && (r = weno_terms(m, E))) return r;
+  StageArgs a;
+  memset(&a, 0, sizeof a);
+  a.g = m->geo;
+  a.t = m->tab;
+  a.EU = E.U; a.EV = E.V; a.Egd = E.gd; a.ghs = m->ghs;
+  if (O) { a.OU = O->U; a.OV = O->V; a.Ogd = O->gd; }
+  if (N) { a.NU = N->U; a.NV = N->V; a.Ngd = N->gd; }
+  if (T) { a.TU = T->U; a.TV = T->V; a.Tgd = T->gd; }
+  if (P) { a.PU = P->U; a.PV = P->V; a.Pgd = P->gd; }
+  a.AUlon = m->w_alon_u; a.AUlat = m->w_alat_u; a.AVlon = m->w_alon_v; a.AVlat = m->w_alat_v;
+  a.dt = dt;
+  a.beta_lon = m->cfg.uv_adv_upwind_lon_beta;
+  a.beta_lat = m->cfg.uv_adv_upwind_lat_beta;
+  a.partials = m->d_partials;
+  a.rows_per_cta = m->rows_per_cta;
+  dim3 grid((unsigned)m->nbx, (unsigned)m->nchunks);
+  if (!m->dry) pick_stage(pass, adv, mode)<<<grid, BX, 0, m->stream>>>(a);
+  if ((r = post_launch(m))) return r;
+
+  const int li = (pass == PASS_SLOW) ? 1 : 0;
+  const int nst = m->nbx * m->nchunks;
+  if (m->n_items[li]) {
+    PolarArgs p;
+    memset(&p, 0, sizeof p);
+    p.g = m->geo;
+    p.t = m->tab;
+    p.items = m->d_items[li];
+    p.basis = m->d_basis;
+    p.EU = a.EU; p.EV = a.EV; p.Egd = a.Egd; p.ghs = a.ghs;
+    p.OU = a.OU; p.OV = a.OV; p.Ogd = a.Ogd;
+    p.NU = a.NU; p.NV = a.NV; p.Ngd = a.Ngd;
+    p.TU = a.TU; p.TV = a.TV; p.Tgd = a.Tgd;
+    p.PU = a.PU; p.PV = a.PV; p.Pgd = a.Pgd;
+    p.dt = dt;
+    p.partials = m->d_partials + 2 * (size_t)nst;
+    p.rescale = 1;
+    p.radius = m->mesh.radius;
+    p.dlat = m->mesh.dlat;
+    const size_t sh = (size_t)m->geo.nlon * sizeof(double);
+    switch (mode) {
+      case MODE_S1: if (!m->dry) k_polar<MODE_S1><<<m->n_items[li], PT, sh, m->stream>>>(p); break;
+      case MODE_S2: if (!m->dry) k_polar<MODE_S2><<<m->n_items[li], PT, sh, m->stream>>>(p); break;
+      case MODE_S3A: if (!m->dry) k_polar<MODE_S3A><<<m->n_items[li], PT, sh, m->stream>>>(p); break;
+      default: if (!m->dry) k_polar<MODE_EVAL><<<m->n_items[li], PT, sh, m->stream>>>(p); break;
+    }
+    if ((r = post_launch(m))) return r;
+  }
+  if (mode == MODE_S3A) {
+    if (!m->dry) k_reduce_pairs<<<1, 256, 0, m->stream>>>(m->d_partials, nst + m->n_items[li], m->d_ip);
+    if ((r = post_launch(m))) return r;
+    if ((r = allreduce2(m, m->d_ip))) return r;
+  }
+  return 0;
+}
+
+static int update(gmd_model *m, const State &O, const Tend &T, double dt, int beta_mode, double dt0, bool with_gd,
+                  State *N) {
+  UpdateArgs a;
+  memset(&a, 0, sizeof a);
+  a.g = m->geo;
+  a.OU = O.U; a.OV = O.V; a.Ogd = O.gd;
+  a.TU = T.U; a.TV = T.V; a.Tgd = T.gd;
+  a.NU = N->U; a.NV = N->V; a.Ngd = N->gd;
+  a.dt = dt;
+  a.ip = m->d_ip;
+  a.qcon = m->cfg.qcon_modified;
+  a.beta_mode = beta_mode;
+  a.dt0 = dt0;
+  a.beta_out = m->d_beta;
+  a.with_gd = with_gd ? 1 : 0;
+  if (!m->dry) k_update<<<m->ew_blocks, 256, 0, m->stream>>>(a);
+  return post_launch(m);
+}
+
+// predict_correct(dt, O -> *out, pass), src/dycore_mod.F90:754-792.  *out is a fresh state; O is kept.
+static int predict_correct(gmd_model *m, double dts, const State &O, int pass, State *out) {
+  int r;
+  const bool slow = (pass == PASS_SLOW);
+  const double dt = dts * 0.5;
+  State A, B;
+  if ((r = new_state(m, &A, slow ? O.gd : nullptr))) return r;
+  if ((r = new_state(m, &B, slow ? O.gd : nullptr))) return r;
+  // tend(old) = L(old); new = old + dt/2 tend(old)
+  if ((r = stage(m, pass, MODE_S1, O, &O, dt, &A, &m->tendOld, nullptr))) return r;
+  if ((r = exchange_state(m, A, !slow))) return r;
+  // tend(old) = L(new); new = old + dt/2 tend(old)
+  if ((r = stage(m, pass, MODE_S2, A, &O, dt, &B, &m->tendOld, nullptr))) return r;
+  if ((r = exchange_state(m, B, !slow))) return r;
+  // tend(new) = L(new); ip1 = <tend(old), tend(new)>, ip2 = <tend(new), tend(new)>
+  if ((r = stage(m, pass, MODE_S3A, B, nullptr, 0.0, nullptr, &m->tendNew, &m->tendOld))) return r;
+  // new = old + dt beta tend(new)
+  if ((r = update(m, O, m->tendNew, dts, 1, 0.0, !slow, &A))) return r;
+  if ((r = exchange_state(m, A, !slow))) return r;
+  release_state(m, &B);
+  *out = A;
+  return 0;
+}
+
+// csp2_splitting, src/dycore_mod.F90:671-687
+static int csp2(gmd_model *m, const State &in, State *out) {
+  int r;
+  const double dtm = m->cfg.time_step_size;
+  const double fast_dt = dtm / m->cfg.subcycles;
+  State s0, s1;
+  if ((r = predict_correct(m, 0.5 * dtm, in, PASS_SLOW, &s0))) return r;
+  for (int k = 0; k < m->cfg.subcycles; k++) {
+    if ((r = predict_correct(m, fast_dt, s0, PASS_FAST, &s1))) return r;
+    release_state(m, &s0);
+    s0 = s1;
+  }
+  if ((r = predict_correct(m, 0.5 * dtm, s0, PASS_SLOW, &s1))) return r;
+  release_state(m, &s0);
+  *out = s1;
+  return 0;
+}
+
+static int axpby(gmd_model *m, double alpha, const Tend &x, double beta, Tend &y) {
+  const size_t total = (size_t)m->nr * m->geo.nlon;
+  if (!m->dry) k_axpby3<<<m->ew_blocks, 256, 0, m->stream>>>(total, alpha, x.U, x.V, x.gd, beta, y.U, y.V, y.gd);
+  return post_launch(m);
+}
+static int dot(gmd_model *m, const double *aU, const double *aV, const double *aG, const double *bU, const double *bV,
+               const double *bG, int slot) {
+  if (!m->dry) k_dot<<<m->ew_blocks, 256, 0, m->stream>>>(m->geo, m->tab, aU, aV, aG, bU, bV, bG, 1, m->d_partials, slot);
+  return post_launch(m);
+}
+
+// isp_splitting, src/dycore_mod.F90:689-752 (tend algebra on du, dv, dgd only)
+static int isp(gmd_model *m, const State &F, State *out) {
+  int r;
+  const double dtm = m->cfg.time_step_size;
+  const int S = m->cfg.subcycles;
+  const double fast_dt = dtm / S, half_dt = dtm * 0.5;
+  if (!m->tendA.U) {
+    if ((r = new_tend(m, &m->tendA))) return r;
+    if ((r = new_tend(m, &m->tendB))) return r;
+  }
+  Tend &slow = m->tendA, &acc = m->tendB, &T = m->tendOld, &T2 = m->tendNew;
+  const size_t bytes = (size_t)m->nr * m->geo.nlon * sizeof(double);
+  // space_operators(slow) leaves dgd = 0 (:297)
+  if (!m->dry) CK(cudaMemsetAsync(slow.gd, 0, bytes, m->stream));
+  if ((r = stage(m, PASS_SLOW, MODE_EVAL, F, nullptr, 0, nullptr, &slow, nullptr))) return r;
+  if ((r = axpby(m, 0.0, slow, 0.0, acc))) return r;  // acc = 0
+  State P = F, P1, P2;
+  bool ownP = false;
+  for (int k = 0; k < S; k++) {
+    if ((r = new_state(m, &P1, nullptr))) return r;
+    if ((r = new_state(m, &P2, nullptr))) return r;
+    if ((r = stage(m, PASS_FAST, MODE_EVAL, P, nullptr, 0, nullptr, &T, nullptr))) return r;
+    if ((r = axpby(m, 1.0, slow, 1.0, T))) return r;
+    if ((r = update(m, P, T, fast_dt * 0.5, 0, 0, true, &P1))) return r;
+    if ((r = exchange_state(m, P1, true))) return r;
+    if ((r = stage(m, PASS_FAST, MODE_EVAL, P1, nullptr, 0, nullptr, &T, nullptr))) return r;
+    if ((r = axpby(m, 1.0, slow, 1.0, T))) return r;
+    if ((r = update(m, P, T, fast_dt * 0.5, 0, 0, true, &P2))) return r;
+    if ((r = exchange_state(m, P2, true))) return r;
+    if ((r = stage(m, PASS_FAST, MODE_EVAL, P2, nullptr, 0, nullptr, &T2, nullptr))) return r;
+    if ((r = axpby(m, 1.0, T2, 1.0, acc))) return r;
+    if ((r = axpby(m, 1.0, slow, 1.0, T2))) return r;
+    if ((r = update(m, P, T2, fast_dt, 0, 0, true, &P1))) return r;
+    if ((r = exchange_state(m, P1, true))) return r;
+    release_state(m, &P2);
+    if (ownP) release_state(m, &P);
+    P = P1;
+    ownP = true;
+  }
+  if ((r = axpby(m, 0.0, slow, 2.0 / S, acc))) return r;  // acc *= 2/S
+  State Q1, Q2;
+  if ((r = new_state(m, &Q1, nullptr))) return r;
+  if ((r = new_state(m, &Q2, nullptr))) return r;
+  if (!m->dry) CK(cudaMemsetAsync(T.gd, 0, bytes, m->stream));
+  if ((r = stage(m, PASS_SLOW, MODE_EVAL, P, nullptr, 0, nullptr, &T, nullptr))) return r;
+  if ((r = axpby(m, -1.0, slow, 1.0, T))) return r;
+  if ((r = update(m, P, T, half_dt, 0, 0, true, &Q1))) return r;
+  if ((r = exchange_state(m, Q1, true))) return r;
+  if (!m->dry) CK(cudaMemsetAsync(T.gd, 0, bytes, m->stream));
+  if ((r = stage(m, PASS_SLOW, MODE_EVAL, Q1, nullptr, 0, nullptr, &T, nullptr))) return r;
+  if ((r = axpby(m, -1.0, slow, 1.0, T))) return r;
+  if ((r = update(m, P, T, half_dt, 0, 0, true, &Q2))) return r;
+  if ((r = exchange_state(m, Q2, true))) return r;
+  if (!m->dry) CK(cudaMemsetAsync(T2.gd, 0, bytes, m->stream));
+  if ((r = stage(m, PASS_SLOW, MODE_EVAL, Q2, nullptr, 0, nullptr, &T2, nullptr))) return r;
+  if ((r = axpby(m, 1.0, slow, 1.0, T2))) return r;
+  if ((r = axpby(m, 1.0, acc, 1.0, T2))) return r;
+  // ip1 = <R, F> (tend-state product, src/types_mod.F90:373-397), ip2 = <R, R>
+  if ((r = dot(m, T2.U, T2.V, T2.gd, F.U, F.V, F.gd, 0))) return r;
+  if ((r = dot(m, T2.U, T2.V, T2.gd, T2.U, T2.V, T2.gd, 1))) return r;
+  if (!m->dry) k_reduce_pairs<<<1, 256, 0, m->stream>>>(m->d_partials, m->ew_blocks, m->d_ip);
+  if ((r = post_launch(m))) return r;
+  if ((r = allreduce2(m, m->d_ip))) return r;
+  if ((r = update(m, F, T2, half_dt, 2, dtm, true, &Q1))) return r;
+  if ((r = exchange_state(m, Q1, true))) return r;
+  release_state(m, &Q2);
+  if (ownP) release_state(m, &P);
+  *out = Q1;
+  return 0;
+}
+
+static int polar_filter_only(gmd_model *m, double *ud, double *vd, double *gdd) {
+  if (!m->n_items[2]) return 0;
+  PolarArgs p;
+  memset(&p, 0, sizeof p);
+  p.g = m->geo;
+  p.t = m->tab;
+  p.items = m->d_items[2];
+  p.basis = m->d_basis;
+  p.TU = ud; p.TV = vd; p.Tgd = gdd;
+  p.rescale = 0;
+  p.partials = m->d_partials;
+  const size_t sh = (size_t)m->geo.nlon * sizeof(double);
+  if (!m->dry) k_polar<MODE_EVAL><<<m->n_items[2], PT, sh, m->stream>>>(p);
+  return post_launch(m);
+}
+
+// ordinary_diffusion(dt, state), src/diffusion_mod.F90:74-217.  *out is a fresh state.
+static int diffusion(gmd_model *m, double dt, const State &in, State *out) {
+  int r;
+  const int norder = m->cfg.diffusion_order / 2;
+  if (!m->d_ud) {
+    if ((r = acquire(m, KIND_U, &m->d_ud))) return r;
+    if ((r = acquire(m, KIND_V, &m->d_vd))) return r;
+    if ((r = acquire(m, KIND_G, &m->d_gdd))) return r;
+    if ((r = acquire(m, KIND_U, &m->d_ud2))) return r;
+    if ((r = acquire(m, KIND_V, &m->d_vd2))) return r;
+    if ((r = acquire(m, KIND_G, &m->d_gdd2))) return r;
+  }
+  if ((r = derive_uv(m, in))) return r;
+  const bool south = (m->geo.r0 == 0), north = (m->geo.r1 == m->geo.nlat);
+  const double *qu = m->w_u, *qv = m->w_v, *qg = in.gd;
+  double *ou = m->d_ud, *ov = m->d_vd, *og = m->d_gdd;
+  for (int order = 1; order <= norder; order++) {
+    if (!m->dry) k_laplace<<<m->ew_blocks, 256, 0, m->stream>>>(m->geo, m->tab, qu, qv, qg, ou, ov, og);
+    if ((r = post_launch(m))) return r;
+    if (south || north) {
+      if (!m->dry) k_lap_pole<<<2, PT, 0, m->stream>>>(m->geo, m->tab, qg, og, south ? 1 : 0, north ? 1 : 0);
+      if ((r = post_launch(m))) return r;
+    }
+    if (order != norder) {
+      if ((r = exchange_tend3(m, ou, ov, og, 1, 1))) return r;
+      qu = ou; qv = ov; qg = og;
+      ou = m->d_ud2; ov = m->d_vd2; og = m->d_gdd2;
+    }
+  }
+  if ((r = polar_filter_only(m, ou, ov, og))) return r;
+  if ((r = exchange_tend3(m, nullptr, nullptr, og, 1, 1))) return r;  // gdd(j+1) enters sqrt(gd') of row j+1
+  const double sign = ((norder + 1) % 2 == 0) ? 1.0 : -1.0;
+  const double sdc = sign * dt * m->cfg.diffusion_coef;
+  State N;
+  if ((r = new_state(m, &N, nullptr))) return r;
+  if (!m->dry) k_diff_update<<<m->ew_blocks, 256, 0, m->stream>>>(m->geo, m->w_u, m->w_v, in.gd, ou, ov, og, sdc, N.U, N.V, N.gd);
+  if ((r = post_launch(m))) return r;
+  if ((r = exchange_state(m, N, true))) return r;
+  *out = N;
+  return 0;
+}
+
+// diag_run totals of state s into the ring slot of the device step counter (advanced first if `advance`)
+static int diag(gmd_model *m, const State &s, int advance) {
+  int r;
+  if (!m->dry) k_diag<<<m->ew_blocks, 256, 0, m->stream>>>(m->geo, m->tab, s.U, s.V, s.gd, m->ghs, m->mesh.dlon, m->mesh.dlat,
+                                             m->d_partials);
+  if ((r = post_launch(m))) return r;
+  if (!m->dry) k_reduce_pairs<<<1, 256, 0, m->stream>>>(m->d_partials, m->ew_blocks, m->d_sums);
+  if ((r = post_launch(m))) return r;
+  if ((r = allreduce2(m, m->d_sums))) return r;
+  if (!m->dry) k_diag_store<<<1, 32, 0, m->stream>>>(m->d_sums, m->d_beta, m->mesh.radius, m->d_ring, m->d_ctr, advance, gmd_model::RING);
+  return post_launch(m);
+}
+
+// time_integrate (src/dycore_mod.F90:654-669) + time_advance + diag_run for ONE step; consumes m->cur
+static int one_step(gmd_model *m) {
+  int r;
+  State next;
+  switch (m->cfg.split_scheme) {
+    case GMD_SPLIT_CSP2: r = csp2(m, m->cur, &next); break;
+    case GMD_SPLIT_ISP: r = isp(m, m->cur, &next); break;
+    default: r = predict_correct(m, m->cfg.time_step_size, m->cur, PASS_ALL, &next);
+  }
+  if (r) return r;
+  release_state(m, &m->cur);
+  m->cur = next;
+  if (m->cfg.use_diffusion) {
+    State d;
+    if ((r = diffusion(m, m->cfg.time_step_size, m->cur, &d))) return r;
+    release_state(m, &m->cur);
+    m->cur = d;
+  }
+  m->step++;
+  // canonical pool order: the next step's buffer choice depends on `cur` only (graph keys stay few)
+  for (int q = 0; q < 3; q++) std::sort(m->free_[q].begin(), m->free_[q].end());
+  return diag(m, m->cur, 1);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host <-> device field transfer
+// ---------------------------------------------------------------------------------------------------------
+// global host array (layout) -> band staging incl. ghost rows; nrows_valid = rows of the field on the globe
+static void pack_band(const gmd_model *m, const double *src, int layout, int nrows_valid, std::vector<double> &st) {
+  const int nlon = m->geo.nlon, r0 = m->geo.r0;
+  st.assign(m->fld_elems, 0.0);
+  for (int l = 0; l < m->nr + 2 * GHOST; l++) {
+    const int j = r0 - GHOST + l;
+    if (j < 0 || j >= nrows_valid) continue;
+    const double *row = (layout == GMD_LAYOUT_REFERENCE) ? src + (size_t)(j + 2) * (nlon + 4) + 2 : src + (size_t)j * nlon;
+    memcpy(&st[(size_t)l * nlon], row, (size_t)nlon * sizeof(double));
+  }
+}
+static int upload_field(gmd_model *m, const double *src, int layout, int nrows_valid, double *dst) {
+  std::vector<double> st;
+  if (src) pack_band(m, src, layout, nrows_valid, st);
+  else st.assign(m->fld_elems, 0.0);
+  CK(cudaMemcpyAsync(dst - (size_t)GHOST * m->geo.nlon, st.data(), m->fld_elems * sizeof(double), cudaMemcpyHostToDevice,
+                     m->stream));
+  CK(cudaStreamSynchronize(m->stream));
+  return 0;
+}
+// owned rows of a band field -> global host array
+static int download_field(gmd_model *m, const double *src, int layout, int nrows_valid, double *dst, bool zero_poles) {
+  if (!dst) return 0;
+  const int nlon = m->geo.nlon, r0 = m->geo.r0;
+  std::vector<double> st((size_t)m->nr * nlon);
+  CK(cudaMemcpyAsync(st.data(), src, st.size() * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+  CK(cudaStreamSynchronize(m->stream));
+  for (int l = 0; l < m->nr; l++) {
+    const int j = r0 + l;
+    if (j >= nrows_valid) continue;
+    const double *row = &st[(size_t)l * nlon];
+    const bool zero = zero_poles && (j == 0 || j == m->geo.nlat - 1);
+    if (layout == GMD_LAYOUT_REFERENCE) {
+      double *d = dst + (size_t)(j + 2) * (nlon + 4);
+      for (int i = 0; i < nlon; i++) d[i + 2] = zero ? 0.0 : row[i];
+      d[0] = d[nlon];      // parallel_fill_halo, src/parallel_mod.F90:466-524
+      d[1] = d[nlon + 1];
+      d[nlon + 2] = d[2];
+      d[nlon + 3] = d[3];
+    } else {
+      double *d = dst + (size_t)j * nlon;
+      for (int i = 0; i < nlon; i++) d[i] = zero ? 0.0 : row[i];
+    }
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char *gmd_last_error(void) { return g_err; }
+int gmd_version(void) { return GMD_VERSION; }
+
+void gmd_config_defaults(gmd_config *c) {
+  memset(c, 0, sizeof *c);
+  c->subcycles = 4;
+  c->uv_adv_upwind_lon_beta = 0.0;
+  c->uv_adv_upwind_lat_beta = 0.5;
+  c->use_zonal_tend_filter = 1;
+  c->diffusion_order = 2;
+  c->split_scheme = GMD_SPLIT_CSP2;
+  c->rank = 0;
+  c->nranks = 1;
+  c->device = -1;
+}
+
+void gmd_destroy(gmd_model *m) {
+  if (!m) return;
+  cudaSetDevice(m->dev);
+  if (m->stream) cudaStreamSynchronize(m->stream);
+  for (auto &g : m->graphs) cudaGraphExecDestroy(g.exec);
+  if (m->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(m->comm);
+  for (double *p : m->all_allocs) cudaFree(p);
+  for (double *p : m->tab_allocs) cudaFree(p);
+  cudaFree(m->d_flags_alloc);
+  cudaFree(m->d_basis);
+  for (int k = 0; k < 3; k++) cudaFree(m->d_items[k]);
+  cudaFree(m->d_partials);
+  cudaFree(m->d_ip);
+  cudaFree(m->d_ring);
+  if (m->ev0) cudaEventDestroy(m->ev0);
+  if (m->ev1) cudaEventDestroy(m->ev1);
+  if (m->own_stream) cudaStreamDestroy(m->own_stream);
+  delete m;
+}
+
+int gmd_create(const gmd_config *cfg, gmd_model **out) {
+  if (!cfg || !out) return fail(GMD_ERR_ARG, "null argument");
+  *out = nullptr;
+  if (cfg->num_lon < 4 || cfg->num_lat < 5) return fail(GMD_ERR_ARG, "grid too small: %d x %d", cfg->num_lon, cfg->num_lat);
+  if (cfg->nranks < 1 || cfg->rank < 0 || cfg->rank >= cfg->nranks) return fail(GMD_ERR_ARG, "bad rank %d of %d", cfg->rank, cfg->nranks);
+  if (cfg->uv_adv_scheme < 0 || cfg->uv_adv_scheme > 2)
+    return fail(GMD_ERR_ARG, "Unknown uv_adv_scheme %d!", cfg->uv_adv_scheme);  // dycore_mod.F90:104-106
+  if (cfg->subcycles < 1) return fail(GMD_ERR_ARG, "subcycles must be >= 1");
+  if (cfg->use_diffusion && cfg->diffusion_order != 2 && cfg->diffusion_order != 4)
+    return fail(GMD_ERR_ARG, "diffusion_order must be 2 or 4");
+  {  // FFTPACK accepts any n, but the reference's grids are 2^a 3^b 5^c; the projector needs no factorisation
+    for (int k = 0; k < 20; k++) {
+      const int c = cfg->zonal_tend_filter_cutoff_wavenumber[k];
+      if (c < 0 || c > 254) return fail(GMD_ERR_ARG, "zonal_tend_filter_cutoff_wavenumber(%d)=%d outside 0..254", k + 1, c);
+    }
+  }
+  if (cfg->num_lat / cfg->nranks < 4) return fail(GMD_ERR_ARG, "fewer than 4 latitude rows per rank");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(GMD_ERR_CUDA, "no CUDA device available (%s); this library has no CPU fallback",
+                e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+  gmd_model *m = new gmd_model();
+  m->cfg = *cfg;
+  if (cfg->device >= 0) m->dev = cfg->device;
+  else cudaGetDevice(&m->dev);
+#define CKD(call)                                                                                         \
+  do {                                                                                                    \
+    cudaError_t e_ = (call);                                                                              \
+    if (e_ != cudaSuccess) {                                                                              \
+      fail(GMD_ERR_CUDA, "CUDA error %s at %s:%d (%s)", cudaGetErrorName(e_), __FILE__, __LINE__,         \
+           cudaGetErrorString(e_));                                                                       \
+      gmd_destroy(m);                                                                                     \
+      return GMD_ERR_CUDA;                                                                                \
+    }                                                                                                     \
+  } while (0)
+  CKD(cudaSetDevice(m->dev));
+  CKD(cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking));
+  m->stream = m->own_stream;
+  CKD(cudaEventCreate(&m->ev0));
+  CKD(cudaEventCreate(&m->ev1));
+  const int nlon = cfg->num_lon, nlat = cfg->num_lat;
+  m->mesh.init(nlon, nlat, /*reset_poles=*/true);
+  m->mesh.filter_init(cfg->use_zonal_tend_filter != 0, cfg->zonal_tend_filter_cutoff_wavenumber);
+  // latitude bands: rows split as evenly as possible
+  const int base = nlat / cfg->nranks, rem = nlat % cfg->nranks;
+  m->geo.nlon = nlon;
+  m->geo.nlat = nlat;
+  m->geo.r0 = cfg->rank * base + std::min(cfg->rank, rem);
+  m->geo.r1 = m->geo.r0 + base + (cfg->rank < rem ? 1 : 0);
+  m->nr = m->geo.r1 - m->geo.r0;
+  m->fld_elems = (size_t)(m->nr + 2 * GHOST) * nlon;
+  int r = build_tables(m);
+  if (r) { gmd_destroy(m); return r; }
+  // stage grid: ~6 CTAs per SM
+  int nsm = 148;
+  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, m->dev);
+  m->nbx = (nlon + NOUT - 1) / NOUT;
+  int want = std::max(1, (nsm * 6) / m->nbx);
+  m->rows_per_cta = std::max(4, (m->nr + want - 1) / want);
+  if (const char *ev = getenv("GMD_ROWS_PER_CTA")) m->rows_per_cta = std::max(1, atoi(ev));
+  m->nchunks = (m->nr + m->rows_per_cta - 1) / m->rows_per_cta;
+  const size_t total = (size_t)m->nr * nlon;
+  m->ew_blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)nsm * 8);
+  m->n_partials = std::max(m->nbx * m->nchunks + m->n_items[0] + m->n_items[1], m->ew_blocks) + 16;
+  CKD(cudaMalloc(&m->d_partials, (size_t)m->n_partials * 2 * sizeof(double)));
+  CKD(cudaMalloc(&m->d_ip, 8 * sizeof(double)));
+  CKD(cudaMemset(m->d_ip, 0, 8 * sizeof(double)));
+  m->d_sums = m->d_ip + 2;
+  m->d_beta = m->d_ip + 4;
+  m->d_ctr = (int *)(m->d_ip + 6);
+  {
+    const double one = 1.0;
+    CKD(cudaMemcpy(m->d_beta, &one, sizeof one, cudaMemcpyHostToDevice));
+  }
+  CKD(cudaMalloc(&m->d_ring, (size_t)gmd_model::RING * 3 * sizeof(double)));
+  CKD(cudaMemset(m->d_ring, 0, (size_t)gmd_model::RING * 3 * sizeof(double)));
+  CKD(cudaFuncSetAttribute(k_polar<MODE_S1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CKD(cudaFuncSetAttribute(k_polar<MODE_S2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CKD(cudaFuncSetAttribute(k_polar<MODE_S3A>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CKD(cudaFuncSetAttribute(k_polar<MODE_EVAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  if ((size_t)nlon * sizeof(double) > 200 * 1024) { fail(GMD_ERR_ARG, "num_lon too large for the polar-row kernel"); gmd_destroy(m); return GMD_ERR_ARG; }
+  // persistent buffers
+  if ((r = new_state(m, &m->cur, nullptr)) || (r = acquire(m, KIND_G, &m->ghs)) || (r = new_tend(m, &m->tendOld)) ||
+      (r = new_tend(m, &m->tendNew))) {
+    gmd_destroy(m);
+    return r;
+  }
+  CKD(cudaStreamSynchronize(m->stream));
+#undef CKD
+  *out = m;
+  return 0;
+}
+
+int gmd_comm_unique_id(void *id128) {
+  int r = nccl_load();
+  if (r) return r;
+  NK(g_nccl.GetUniqueId(id128));
+  return 0;
+}
+
+int gmd_comm_init(gmd_model *m, const void *id128) {
+  if (!m || !id128) return fail(GMD_ERR_ARG, "null argument");
+  if (m->cfg.nranks == 1) return 0;
+  int r = nccl_load();
+  if (r) return r;
+  if ((r = set_dev(m))) return r;
+  NcclId128 id;
+  memcpy(id.b, id128, 128);
+  NK(g_nccl.CommInitRank(&m->comm, m->cfg.nranks, id, m->cfg.rank));
+  return 0;
+}
+
+int gmd_get_band(const gmd_model *m, int *b, int *e) {
+  if (!m) return fail(GMD_ERR_ARG, "null model");
+  if (b) *b = m->geo.r0;
+  if (e) *e = m->geo.r1;
+  return 0;
+}
+
+int gmd_set_stream(gmd_model *m, void *s) {
+  if (!m) return fail(GMD_ERR_ARG, "null model");
+  int r = set_dev(m);
+  if (r) return r;
+  CK(cudaStreamSynchronize(m->stream));
+  m->stream = s ? (cudaStream_t)s : m->own_stream;
+  for (auto &g : m->graphs) cudaGraphExecDestroy(g.exec);
+  m->graphs.clear();
+  return 0;
+}
+
+int gmd_set_graph_mode(gmd_model *m, int on) {
+  if (!m) return fail(GMD_ERR_ARG, "null model");
+  m->graph_mode = on != 0;
+  return 0;
+}
+
+static int diag_now(gmd_model *m) { return diag(m, m->cur, 0); }
+
+static int check_nan_last(gmd_model *m, int n) {
+  // diag_run NaN abort, src/diag_mod.F90:79-87
+  n = std::min(n, (int)gmd_model::RING);
+  std::vector<double> h((size_t)3 * gmd_model::RING);
+  CK(cudaMemcpyAsync(h.data(), m->d_ring, h.size() * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+  CK(cudaStreamSynchronize(m->stream));
+  for (int k = 0; k < n; k++) {
+    const int slot = (m->step - k) % gmd_model::RING;
+    if (slot < 0) break;
+    if (std::isnan(h[3 * (size_t)slot])) return fail(GMD_ERR_NAN, "Total mass is NaN!");
+    if (std::isnan(h[3 * (size_t)slot + 1])) return fail(GMD_ERR_NAN, "Total energy is NaN!");
+  }
+  return 0;
+}
+
+int gmd_set_state(gmd_model *m, const double *u, const double *v, const double *gd, const double *ghs, int layout) {
+  if (!m || !u || !v || !gd) return fail(GMD_ERR_ARG, "null argument");
+  if (layout != GMD_LAYOUT_COMPACT && layout != GMD_LAYOUT_REFERENCE) return fail(GMD_ERR_ARG, "bad layout %d", layout);
+  int r = set_dev(m);
+  if (r) return r;
+  const int nlon = m->geo.nlon, nlat = m->geo.nlat;
+  // pole rows of u must be zero (du is never written there, so U(pole) = 0 is an invariant of every reference IC)
+  for (int pj = 0; pj < 2; pj++) {
+    const int j = pj ? nlat - 1 : 0;
+    const double *row = (layout == GMD_LAYOUT_REFERENCE) ? u + (size_t)(j + 2) * (nlon + 4) + 2 : u + (size_t)j * nlon;
+    for (int i = 0; i < nlon; i++)
+      if (row[i] != 0.0) return fail(GMD_ERR_ARG, "u must be 0 on the pole rows (row %d, column %d is %g)", j, i, row[i]);
+  }
+  if ((r = ensure_uv(m))) return r;
+  if ((r = upload_field(m, u, layout, nlat, m->w_u))) return r;
+  if ((r = upload_field(m, v, layout, nlat - 1, m->w_v))) return r;
+  if ((r = upload_field(m, gd, layout, nlat, m->cur.gd))) return r;
+  if ((r = upload_field(m, ghs, layout, nlat, m->ghs))) return r;
+  // iap_transform on owned + ghost rows inside the globe (src/types_mod.F90:399-426)
+  Geo g = m->geo;
+  g.r0 = std::max(m->geo.r0 - 1, 0);
+  g.r1 = std::min(m->geo.r1 + 1, nlat);
+  const ptrdiff_t sh = (ptrdiff_t)(g.r0 - m->geo.r0) * nlon;
+  if (!m->dry) k_iap<<<m->ew_blocks, 256, 0, m->stream>>>(g, m->w_u + sh, m->w_v + sh, m->cur.gd + sh, m->cur.U + sh, m->cur.V + sh);
+  if ((r = post_launch(m))) return r;
+  m->have_state = true;
+  if (m->run_inited) {
+    if ((r = diag_now(m))) return r;
+    return check_nan_last(m, 1);
+  }
+  CK(cudaStreamSynchronize(m->stream));
+  return 0;
+}
+
+int gmd_run_init(gmd_model *m) {
+  if (!m) return fail(GMD_ERR_ARG, "null model");
+  if (!m->have_state) return fail(GMD_ERR_STATE, "gmd_set_state has not been called");
+  int r = set_dev(m);
+  if (r) return r;
+  m->run_inited = true;
+  if ((r = diag_now(m))) return r;
+  return check_nan_last(m, 1);
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------
+// step execution: direct launches for the first steps (warms the buffer pool), then one CUDA graph per
+// distinct `cur` buffer triple.  A replay advances the host-side pool bookkeeping with a dry pass of the
+// same step logic (no launches), so direct and replayed steps can be mixed freely.
+// ---------------------------------------------------------------------------------------------------------
+static int enqueue_steps(gmd_model *m, int nsteps) {
+  int r;
+  for (int n = 0; n < nsteps; n++) {
+    const bool use_graph = m->graph_mode && m->cfg.nranks == 1 && m->step >= 2;
+    if (!use_graph) {
+      if ((r = one_step(m))) return r;
+      continue;
+    }
+    const std::vector<double *> key = {m->cur.U, m->cur.V, m->cur.gd};
+    gmd_model::GraphEntry *hit = nullptr;
+    for (auto &g : m->graphs)
+      if (g.key == key) { hit = &g; break; }
+    if (hit) {
+      CK(cudaGraphLaunch(hit->exec, m->stream));
+      m->dry = true;
+      r = one_step(m);
+      m->dry = false;
+      if (r) return r;
+      continue;
+    }
+    if (m->graphs.size() >= 16) {  // unexpected: pool state does not cycle; stay correct, lose the graph
+      if ((r = one_step(m))) return r;
+      continue;
+    }
+    CK(cudaStreamBeginCapture(m->stream, cudaStreamCaptureModeThreadLocal));
+    m->capturing = true;
+    const long long l0 = m->launches;
+    r = one_step(m);
+    m->capturing = false;
+    cudaGraph_t graph = nullptr;
+    cudaError_t ce = cudaStreamEndCapture(m->stream, &graph);
+    if (r) {
+      if (graph) cudaGraphDestroy(graph);
+      return r;
+    }
+    if (ce != cudaSuccess) return fail(GMD_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
+    gmd_model::GraphEntry ge;
+    ge.key = key;
+    ge.launches = m->launches - l0;
+    CK(cudaGraphInstantiate(&ge.exec, graph, 0));
+    cudaGraphDestroy(graph);
+    m->graphs.push_back(ge);
+    CK(cudaGraphLaunch(ge.exec, m->stream));  // capture executed nothing
+  }
+  return 0;
+}
+
+extern "C" {
+
+int gmd_step_async(gmd_model *m, int nsteps) {
+  if (!m) return fail(GMD_ERR_ARG, "null model");
+  if (!m->run_inited) return fail(GMD_ERR_STATE, "gmd_run_init has not been called");
+  if (nsteps < 0) return fail(GMD_ERR_ARG, "nsteps < 0");
+  int r = set_dev(m);
+  if (r) return r;
+  if (!m->span_open) {
+    CK(cudaEventRecord(m->ev0, m->stream));
+    m->span_open = true;
+    m->pending_steps = 0;
+  }
+  if ((r = enqueue_steps(m, nsteps))) return r;
+  m->pending_steps += nsteps;
+  return 0;
+}
+
+int gmd_sync(gmd_model *m) {
+  if (!m) return fail(GMD_ERR_ARG, "null model");
+  int r = set_dev(m);
+  if (r) return r;
+  if (m->span_open) {
+    CK(cudaEventRecord(m->ev1, m->stream));
+    CK(cudaEventSynchronize(m->ev1));
+    CK(cudaEventElapsedTime(&m->last_ms, m->ev0, m->ev1));
+    m->span_open = false;
+  } else {
+    CK(cudaStreamSynchronize(m->stream));
+  }
+  const int n = m->pending_steps;
+  m->pending_steps = 0;
+  return check_nan_last(m, std::max(n, 1));
+}
+
+int gmd_step(gmd_model *m, int nsteps) {
+  int r = gmd_step_async(m, nsteps);
+  if (r) return r;
+  return gmd_sync(m);
+}
+
+int gmd_last_step_ms(gmd_model *m, float *ms) {
+  if (!m || !ms) return fail(GMD_ERR_ARG, "null argument");
+  *ms = m->last_ms;
+  return 0;
+}
+
+long long gmd_kernel_launches(const gmd_model *m) { return m ? m->launches : 0; }
+int gmd_get_step_count(const gmd_model *m) { return m ? m->step : 0; }
+
+double gmd_algorithmic_bytes_per_column_step(const gmd_model *m) {
+  if (!m) return 0.0;
+  double b;
+  const int S = m->cfg.subcycles;
+  switch (m->cfg.split_scheme) {
+    case GMD_SPLIT_CSP2: b = 312.0 * S + 216.0 * 2; break;
+    case GMD_SPLIT_ISP: b = 312.0 * S + 216.0 * 2; break;  // same operator-evaluation count as csp2 (3S fast + 6 slow)
+    default: b = 312.0;
+  }
+  if (m->cfg.use_diffusion) b += 48.0 * (m->cfg.diffusion_order / 2);
+  return b;
+}
+
+int gmd_get_diag_series(gmd_model *m, int n, double *mass, double *energy, double *beta) {
+  if (!m) return fail(GMD_ERR_ARG, "null model");
+  if (n < 0 || n > gmd_model::RING || n > m->step + 1) return fail(GMD_ERR_ARG, "bad series length %d", n);
+  int r = set_dev(m);
+  if (r) return r;
+  std::vector<double> h((size_t)3 * gmd_model::RING);
+  CK(cudaMemcpyAsync(h.data(), m->d_ring, h.size() * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+  CK(cudaStreamSynchronize(m->stream));
+  for (int k = 0; k < n; k++) {
+    const int slot = (m->step - (n - 1 - k)) % gmd_model::RING;
+    if (mass) mass[k] = h[3 * (size_t)slot];
+    if (energy) energy[k] = h[3 * (size_t)slot + 1];
+    if (beta) beta[k] = h[3 * (size_t)slot + 2];
+  }
+  return 0;
+}
+
+int gmd_get_diag(gmd_model *m, double *mass, double *energy, double *beta) {
+  if (!m) return fail(GMD_ERR_ARG, "null model");
+  if (!m->run_inited) return fail(GMD_ERR_STATE, "gmd_run_init has not been called");
+  return gmd_get_diag_series(m, 1, mass, energy, beta);
+}
+
+int gmd_get_state(gmd_model *m, double *u, double *v, double *gd, int layout) {
+  if (!m) return fail(GMD_ERR_ARG, "null model");
+  if (!m->have_state) return fail(GMD_ERR_STATE, "gmd_set_state has not been called");
+  int r = set_dev(m);
+  if (r) return r;
+  if ((r = derive_uv(m, m->cur))) return r;
+  const int nlat = m->geo.nlat;
+  if ((r = download_field(m, m->w_u, layout, nlat, u, false))) return r;
+  if ((r = download_field(m, m->w_v, layout, nlat - 1, v, false))) return r;
+  return download_field(m, m->cur.gd, layout, nlat, gd, false);
+}
+
+int gmd_get_iap_state(gmd_model *m, double *iu, double *iv, double *igd, int layout) {
+  if (!m) return fail(GMD_ERR_ARG, "null model");
+  if (!m->have_state) return fail(GMD_ERR_STATE, "gmd_set_state has not been called");
+  int r = set_dev(m);
+  if (r) return r;
+  const int nlat = m->geo.nlat;
+  if ((r = download_field(m, m->cur.U, layout, nlat, iu, false))) return r;
+  if ((r = download_field(m, m->cur.V, layout, nlat - 1, iv, false))) return r;
+  if (igd) {
+    double *tmp = nullptr;
+    if ((r = acquire(m, KIND_G, &tmp))) return r;
+    k_derive<<<m->ew_blocks, 256, 0, m->stream>>>(m->geo, m->geo.r0, m->geo.r1, m->cur.U, m->cur.V, m->cur.gd, nullptr,
+                                                 nullptr, tmp);
+    if ((r = post_launch(m))) return r;
+    r = download_field(m, tmp, layout, nlat, igd, false);
+    release(m, tmp);
+    if (r) return r;
+  }
+  return 0;
+}
+
+int gmd_get_vor_div(gmd_model *m, double *vor, double *div, int layout) {
+  if (!m) return fail(GMD_ERR_ARG, "null model");
+  if (!m->run_inited) return fail(GMD_ERR_STATE, "gmd_run_init has not been called");
+  int r = set_dev(m);
+  if (r) return r;
+  if ((r = derive_uv(m, m->cur))) return r;
+  double *dv = nullptr, *dd = nullptr;
+  if ((r = acquire(m, KIND_V, &dv))) return r;
+  if ((r = acquire(m, KIND_G, &dd))) return r;
+  k_vor_div<<<m->ew_blocks, 256, 0, m->stream>>>(m->geo, m->tab, m->w_u, m->w_v, dv, dd);
+  if ((r = post_launch(m))) return r;
+  const int nlat = m->geo.nlat;
+  r = download_field(m, dv, layout, nlat - 1, vor, false);
+  if (!r) r = download_field(m, dd, layout, nlat, div, false);
+  release(m, dv);
+  release(m, dd);
+  return r;
+}
+
+int gmd_space_operators(gmd_model *m, int pass, double *du, double *dv, double *dgd, int layout) {
+  if (!m) return fail(GMD_ERR_ARG, "null model");
+  if (!m->run_inited) return fail(GMD_ERR_STATE, "gmd_run_init has not been called");
+  if (pass < 0 || pass > 2) return fail(GMD_ERR_ARG, "bad pass %d", pass);
+  int r = set_dev(m);
+  if (r) return r;
+  const size_t bytes = (size_t)m->nr * m->geo.nlon * sizeof(double);
+  if (pass == PASS_SLOW) CK(cudaMemsetAsync(m->tendNew.gd, 0, bytes, m->stream));  // dgd = 0, :297
+  if ((r = stage(m, pass, MODE_EVAL, m->cur, nullptr, 0.0, nullptr, &m->tendNew, nullptr))) return r;
+  const int nlat = m->geo.nlat;
+  if ((r = download_field(m, m->tendNew.U, layout, nlat, du, true))) return r;
+  if ((r = download_field(m, m->tendNew.V, layout, nlat - 1, dv, false))) return r;
+  return download_field(m, m->tendNew.gd, layout, nlat, dgd, false);
+}
+
+int gmd_predict_correct(gmd_model *m, double dt, int pass) {
+  if (!m) return fail(GMD_ERR_ARG, "null model");
+  if (!m->run_inited) return fail(GMD_ERR_STATE, "gmd_run_init has not been called");
+  if (pass < 0 || pass > 2) return fail(GMD_ERR_ARG, "bad pass %d", pass);
+  int r = set_dev(m);
+  if (r) return r;
+  State out;
+  if ((r = predict_correct(m, dt, m->cur, pass, &out))) return r;
+  release_state(m, &m->cur);
+  m->cur = out;
+  CK(cudaStreamSynchronize(m->stream));
+  return 0;
+}
+
+int gmd_ordinary_diffusion(gmd_model *m, double dt) {
+  if (!m) return fail(GMD_ERR_ARG, "null model");
+  if (!m->run_inited) return fail(GMD_ERR_STATE, "gmd_run_init has not been called");
+  int r = set_dev(m);
+  if (r) return r;
+  State out;
+  if ((r = diffusion(m, dt, m->cur, &out))) return r;
+  release_state(m, &m->cur);
+  m->cur = out;
+  CK(cudaStreamSynchronize(m->stream));
+  return 0;
+}
+
+int gmd_filter_row(gmd_model *m, int half, int row0, double *x) {
+  if (!m || !x) return fail(GMD_ERR_ARG, "null argument");
+  const int nlat = m->geo.nlat, nlon = m->geo.nlon;
+  if (row0 < 0 || row0 >= (half ? nlat - 1 : nlat)) return fail(GMD_ERR_ARG, "row %d out of range", row0);
+  int r = set_dev(m);
+  if (r) return r;
+  double *buf = nullptr;
+  if ((r = acquire(m, KIND_G, &buf))) return r;
+  PolarItem it = {IT_DGD, m->geo.r0, half ? m->mesh.cut_half[(size_t)row0] : m->mesh.cut_full[(size_t)row0], 0};
+  PolarItem *dit = nullptr;
+  CK(cudaMalloc(&dit, sizeof it));
+  CK(cudaMemcpyAsync(dit, &it, sizeof it, cudaMemcpyHostToDevice, m->stream));
+  CK(cudaMemcpyAsync(buf, x, (size_t)nlon * sizeof(double), cudaMemcpyHostToDevice, m->stream));
+  PolarArgs p;
+  memset(&p, 0, sizeof p);
+  p.g = m->geo;
+  p.t = m->tab;
+  p.items = dit;
+  p.basis = m->d_basis;
+  p.Tgd = buf;
+  p.rescale = 0;
+  p.partials = m->d_partials;
+  if (2 * (it.cutoff + 1) > m->ncoef_max && it.cutoff >= 0) {
+    cudaFree(dit);
+    release(m, buf);
+    return fail(GMD_ERR_STATE, "internal: basis too small");
+  }
+  k_polar<MODE_EVAL><<<1, PT, (size_t)nlon * sizeof(double), m->stream>>>(p);
+  if ((r = post_launch(m))) return r;
+  CK(cudaMemcpyAsync(x, buf, (size_t)nlon * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+  CK(cudaStreamSynchronize(m->stream));
+  // restore the buffer's zero rows invariant is not needed: row r0 of a G buffer is ordinary data
+  cudaFree(dit);
+  release(m, buf);
+  return 0;
+}
+
+int gmd_get_filter_rows(const gmd_model *m, int *ff, int *fc, int *hf, int *hc) {
+  if (!m) return fail(GMD_ERR_ARG, "null model");
+  const int nlat = m->geo.nlat;
+  for (int j = 0; j < nlat; j++) {
+    if (ff) ff[j] = m->mesh.flag_full[(size_t)j];
+    if (fc) fc[j] = m->mesh.cut_full[(size_t)j];
+  }
+  for (int j = 0; j < nlat - 1; j++) {
+    if (hf) hf[j] = m->mesh.flag_half[(size_t)j];
+    if (hc) hc[j] = m->mesh.cut_half[(size_t)j];
+  }
+  return 0;
+}
+
+int gmd_get_table(const gmd_model *m, int which, double *out) {
+  if (!m || !out) return fail(GMD_ERR_ARG, "null argument");
+  const HostMesh &M = m->mesh;
+  const std::vector<double> *t;
+  int n = M.nlat;
+  switch (which) {
+    case 0: t = &M.full_cos; break;
+    case 1: t = &M.half_cos; n--; break;
+    case 2: t = &M.full_f; break;
+    case 3: t = &M.full_c; break;
+    case 4: t = &M.full_dlon; break;
+    case 5: t = &M.half_dlon; n--; break;
+    case 6: t = &M.full_dlat; break;
+    case 7: t = &M.half_dlat; n--; break;
+    case 8: t = &M.full_lat; break;
+    case 9: t = &M.half_lat; n--; break;
+    default: return fail(GMD_ERR_ARG, "bad table %d", which);
+  }
+  for (int j = 0; j < n; j++) out[j] = (*t)[(size_t)(j + TPAD)];
+  return 0;
+}
+
+int gmd_time_stage_kernel(gmd_model *m, int reps, float *ms_per_launch, double *alg_bytes) {
+  if (!m || !ms_per_launch) return fail(GMD_ERR_ARG, "null argument");
+  if (!m->run_inited) return fail(GMD_ERR_STATE, "gmd_run_init has not been called");
+  if (reps < 1) return fail(GMD_ERR_ARG, "reps < 1");
+  int r = set_dev(m);
+  if (r) return r;
+  const int pass = (m->cfg.split_scheme == GMD_SPLIT_CSP2 || m->cfg.split_scheme == GMD_SPLIT_ISP) ? PASS_FAST : PASS_ALL;
+  State A, B;
+  if ((r = new_state(m, &A, nullptr))) return r;
+  if ((r = new_state(m, &B, nullptr))) return r;
+  const double dt = 0.5 * m->cfg.time_step_size / std::max(1, m->cfg.subcycles);
+  // warm-up: A = cur + dt L(cur)
+  if ((r = stage(m, pass, MODE_S1, m->cur, &m->cur, dt, &A, &m->tendOld, nullptr))) return r;
+  if ((r = stage(m, pass, MODE_S2, A, &m->cur, dt, &B, &m->tendOld, nullptr))) return r;
+  // time the stage kernel only (not k_polar): launch it directly
+  StageArgs a;
+  memset(&a, 0, sizeof a);
+  a.g = m->geo; a.t = m->tab;
+  a.EU = A.U; a.EV = A.V; a.Egd = A.gd; a.ghs = m->ghs;
+  a.OU = m->cur.U; a.OV = m->cur.V; a.Ogd = m->cur.gd;
+  a.NU = B.U; a.NV = B.V; a.Ngd = B.gd;
+  a.TU = m->tendOld.U; a.TV = m->tendOld.V; a.Tgd = m->tendOld.gd;
+  a.dt = dt;
+  a.beta_lon = m->cfg.uv_adv_upwind_lon_beta; a.beta_lat = m->cfg.uv_adv_upwind_lat_beta;
+  a.AUlon = m->w_alon_u; a.AUlat = m->w_alat_u; a.AVlon = m->w_alon_v; a.AVlat = m->w_alat_v;
+  a.partials = m->d_partials;
+  a.rows_per_cta = m->rows_per_cta;
+  dim3 grid((unsigned)m->nbx, (unsigned)m->nchunks);
+  stage_fn fn = pick_stage(pass, m->cfg.uv_adv_scheme, MODE_S2);
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  CK(cudaEventRecord(e0, m->stream));
+  for (int k = 0; k < reps; k++) {
+    fn<<<grid, BX, 0, m->stream>>>(a);
+    m->launches++;
+  }
+  CK(cudaEventRecord(e1, m->stream));
+  CK(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  CK(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  CK(cudaGetLastError());
+  *ms_per_launch = ms / reps;
+  // S2 of the all/fast pass: reads U,V,gd,ghs of the evaluated state + U,V,gd of the base state, writes the
+  // new U,V,gd and the three tendencies: 13 words per column
+  if (alg_bytes) *alg_bytes = 13.0 * 8.0 * (double)m->nr * (double)m->geo.nlon;
+  release_state(m, &A);
+  release_state(m, &B);
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,982 @@
+// gmd_kernels.cuh -- sm_100a kernels of the barotropic shallow-water step (fp64, HBM-bound stencils).
+//
+// Persistent device state is the MINIMAL one: U = sqrt(gd)-weighted u, V likewise, gd (the IAP variables of
+// src/types_mod.F90:25-46) per time level, plus ghs.  u, v and sqrt(gd) are recomputed on chip inside the
+// fused stage kernel; the reference's 13 tendency arrays (src/types_mod.F90:58-72) never exist in HBM.
+//
+// Field addressing: a field pointer p addresses the rank's band, p[(j - r0) * nlon + i] for global row j
+// and column i (0-based); rows r0-GHOST .. r1-1+GHOST are allocated.  Rows outside the globe are zeros
+// that are never written (the reference's permanent zero latitude halos).
+//
+// GMD_STRICT=1 (libgmd_strict.so, built with -fmad=false) keeps every division and the exact operand
+// order of the reference so that element-wise results are bit-identical to the oracle away from the
+// reduction rows; GMD_STRICT=0 (libgmd.so, the product) multiplies by host-precomputed reciprocals and
+// lets ptxas contract a*b+c into DFMA.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#ifndef GMD_STRICT
+#define GMD_STRICT 0
+#endif
+
+namespace gmd {
+
+constexpr int GHOST = 2;      // ghost rows on each side of a band
+constexpr int BX = 128;       // threads per CTA of the stage kernel = columns held on chip
+constexpr int NOUT = BX - 3;  // output columns per CTA (1 west + 2 east columns are halo)
+
+enum { PASS_ALL = 0, PASS_FAST = 1, PASS_SLOW = 2 };
+enum { ADV_CENTER = 0, ADV_UPWIND = 1, ADV_WENO = 2 };
+// what the stage kernel does with the tendency it has just computed
+enum { MODE_S1 = 0,    // new = base + dt * tend               (tend stored only on filtered rows)
+       MODE_S2 = 1,    // new = base + dt * tend, tend stored
+       MODE_S3A = 2,   // tend stored, <tend,prev> and <tend,tend> accumulated
+       MODE_EVAL = 3 };// tend stored
+
+// row flags (global row index)
+enum { FL_DU = 1, FL_DGD = 2, FL_POLE = 4, FL_DV = 8 };
+
+struct Tab {  // device pointers, already offset by TPAD: valid for j in [-TPAD, nlat+TPAD)
+  const double *cosf, *cosh, *ff, *fc;
+  const double *fdlon, *hdlon, *fdlat, *hdlat;
+  const double *q_fdlon, *q_hdlon, *q_fdlat, *q_hdlat;  // 0.25 / d
+  const double *cor1, *cor2;                            // cosh[j-1]/cosf[j], cosh[j]/cosf[j]
+  const double *r_fdlon, *hc_hdlat, *h_fdlon, *h_fdlat; // 1/fdlon, cosh/hdlat, 0.5/fdlon, 0.5/fdlat
+  const double *r_fdlon2, *r_hdlon2, *r_fdlat2, *r_hdlat2; // unused in strict mode (diffusion)
+  const unsigned char *flags;                           // FL_* per row
+};
+
+struct Geo {
+  int nlon, nlat;
+  int r0, r1;  // this rank owns full rows [r0, r1)
+};
+
+struct StageArgs {
+  Geo g;
+  Tab t;
+  const double *EU, *EV, *Egd, *ghs;  // state the operators are evaluated on
+  const double *OU, *OV, *Ogd;        // base state of the update
+  double *NU, *NV, *Ngd;              // new state
+  double *TU, *TV, *Tgd;              // tendency out
+  const double *PU, *PV, *Pgd;        // previous tendency for <tend, prev>
+  const double *AUlon, *AUlat, *AVlon, *AVlat;  // WENO advection terms, precomputed
+  double dt, beta_lon, beta_lat;
+  double *partials;  // [gridDim.x * gridDim.y][2]
+  int rows_per_cta;
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// deterministic block sum (fixed tree); result valid in thread 0; red must hold >= 32 doubles
+template <int NT>
+__device__ __forceinline__ double block_sum(double v, double *red) {
+  v = warp_sum(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) red[w] = v;
+  __syncthreads();
+  double r = 0.0;
+  if (w == 0) {
+    r = (l < NT / 32) ? red[l] : 0.0;
+    r = warp_sum(r);
+  }
+  return r;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Fused stage kernel: one operator evaluation (space_operators, src/dycore_mod.F90:184-365, with the seven
+// operators :367-598 fused) + update_state (:600-652) + inner_product (src/types_mod.F90:347-371) in ONE
+// sweep.  A CTA owns NOUT columns and marches south -> north over `rows_per_cta` rows, keeping rolling row
+// windows of sqrt(gd), u, v, U, V, gd+ghs in shared memory, so every field element is read from HBM once
+// (plus 3 halo columns per 128 and 3 prologue rows per chunk).
+// ---------------------------------------------------------------------------------------------------------
+#define S_(j, c) sS[(((j)&7) * BX) + (c)]
+#define U_(j, c) sU[(((j)&3) * BX) + (c)]
+#define V_(j, c) sV[(((j)&3) * BX) + (c)]
+#define u_(j, c) su[(((j)&3) * BX) + (c)]
+#define v_(j, c) sv[(((j)&3) * BX) + (c)]
+#if GMD_STRICT
+#define GD_(j, c) sG[(((j)&3) * BX) + (c)]
+#define GS_(j, c) sH[(((j)&3) * BX) + (c)]
+// gd(a) + ghs(a) - gd(b) - ghs(b), left to right (src/dycore_mod.F90:516-517,532-533)
+#define GHDIFF(ja, ca, jb, cb) (((GD_(ja, ca) + GS_(ja, ca)) - GD_(jb, cb)) - GS_(jb, cb))
+constexpr int STAGE_SMEM_ROWS = 8 + 4 * 6;
+#else
+#define G_(j, c) sG[(((j)&3) * BX) + (c)]
+#define GHDIFF(ja, ca, jb, cb) (G_(ja, ca) - G_(jb, cb))
+constexpr int STAGE_SMEM_ROWS = 8 + 4 * 5;
+#endif
+constexpr int STAGE_SMEM_BYTES = STAGE_SMEM_ROWS * BX * 8;
+
+template <int PASS, int ADV, int MODE>
+__global__ void __launch_bounds__(BX) k_stage(const StageArgs a) {
+  __shared__ double sm[STAGE_SMEM_ROWS * BX];
+  __shared__ double red[32];
+  double *sS = sm;
+  double *sU = sS + 8 * BX;
+  double *sV = sU + 4 * BX;
+  double *su = sV + 4 * BX;
+  double *sv = su + 4 * BX;
+  double *sG = sv + 4 * BX;
+#if GMD_STRICT
+  double *sH = sG + 4 * BX;
+#endif
+  const int nlon = a.g.nlon, nlat = a.g.nlat, r0 = a.g.r0;
+  const int c = threadIdx.x;
+  const int col0 = blockIdx.x * NOUT;
+  int i = col0 + c - 1;
+  i %= nlon;
+  if (i < 0) i += nlon;
+  const bool out_col = (c >= 1) && (c <= NOUT) && (col0 + c - 1 < nlon);
+  const int ja = r0 + blockIdx.y * a.rows_per_cta;
+  const int jb = min(ja + a.rows_per_cta, a.g.r1);
+  const bool need_gh = (PASS != PASS_SLOW);
+  const Tab &t = a.t;
+
+  // address of column i on global row j of a band field
+#define AT(p, j) ((p)[(ptrdiff_t)((j)-r0) * (ptrdiff_t)nlon + (ptrdiff_t)i])
+
+  double ip1 = 0.0, ip2 = 0.0;
+
+  // ---- prologue: rows ja-1, ja, ja+1 of sqrt(gd); rows ja-1, ja of U, V; gh row ja -----------------------
+  {
+    S_(ja - 1, c) = sqrt(AT(a.Egd, ja - 1));
+    S_(ja, c) = sqrt(AT(a.Egd, ja));
+    S_(ja + 1, c) = sqrt(AT(a.Egd, ja + 1));
+    U_(ja - 1, c) = AT(a.EU, ja - 1);
+    U_(ja, c) = AT(a.EU, ja);
+    V_(ja - 1, c) = AT(a.EV, ja - 1);
+    V_(ja, c) = AT(a.EV, ja);
+    if (need_gh) {
+#if GMD_STRICT
+      GD_(ja, c) = AT(a.Egd, ja);
+      GS_(ja, c) = AT(a.ghs, ja);
+#else
+      G_(ja, c) = AT(a.Egd, ja) + AT(a.ghs, ja);
+#endif
+    }
+  }
+  __syncthreads();
+  {
+    // u(ja), v(ja-1), v(ja): update_state :636-645 (u = 2U/(s_i + s_i+1), v = 2V/(s_j + s_j+1))
+    const int cc = (c < BX - 1) ? c + 1 : c;
+    const bool uok = (ja >= 0 && ja < nlat);
+    u_(ja, c) = uok ? U_(ja, c) * 2.0 / (S_(ja, c) + S_(ja, cc)) : 0.0;
+    const bool v0 = (ja - 1 >= 0 && ja - 1 < nlat - 1), v1 = (ja >= 0 && ja < nlat - 1);
+    v_(ja - 1, c) = v0 ? V_(ja - 1, c) * 2.0 / (S_(ja - 1, c) + S_(ja, c)) : 0.0;
+    v_(ja, c) = v1 ? V_(ja, c) * 2.0 / (S_(ja, c) + S_(ja + 1, c)) : 0.0;
+  }
+  // first prefetch: gd(ja+2), U(ja+1), V(ja+1), ghs(ja+1)
+  double n_gd2 = AT(a.Egd, ja + 2);
+  double n_U = AT(a.EU, ja + 1);
+  double n_V = AT(a.EV, ja + 1);
+  double n_gd1 = 0.0, n_hs = 0.0;
+  if (need_gh) {
+    n_gd1 = AT(a.Egd, ja + 1);
+    n_hs = AT(a.ghs, ja + 1);
+  }
+
+  for (int j = ja; j < jb; j++) {
+    // ---- advance the window: s(j+2), U(j+1), V(j+1), gh(j+1), u(j+1), v(j+1) ----------------------------
+    {
+      const double s2 = sqrt(n_gd2);
+      S_(j + 2, c) = s2;
+      U_(j + 1, c) = n_U;
+      V_(j + 1, c) = n_V;
+      if (need_gh) {
+#if GMD_STRICT
+        GD_(j + 1, c) = n_gd1;
+        GS_(j + 1, c) = n_hs;
+#else
+        G_(j + 1, c) = n_gd1 + n_hs;
+#endif
+      }
+      const int cc = (c < BX - 1) ? c + 1 : c;
+      const double s1c = S_(j + 1, c), s1e = S_(j + 1, cc);  // written one iteration ago (or prologue)
+      const bool uok = (j + 1 < nlat);
+      const bool vok = (j + 1 < nlat - 1);
+      u_(j + 1, c) = uok ? n_U * 2.0 / (s1c + s1e) : 0.0;
+      v_(j + 1, c) = vok ? n_V * 2.0 / (s1c + s2) : 0.0;
+    }
+    // ---- prefetch the next row and the operands of this row's update ------------------------------------
+    if (j + 1 < jb) {
+      n_gd2 = AT(a.Egd, j + 3);
+      n_U = AT(a.EU, j + 2);
+      n_V = AT(a.EV, j + 2);
+      if (need_gh) {
+        n_gd1 = AT(a.Egd, j + 2);
+        n_hs = AT(a.ghs, j + 2);
+      }
+    }
+    const unsigned fl = t.flags[j];
+    const bool rowU = (j >= 1 && j <= nlat - 2);
+    const bool rowV = (j <= nlat - 2);
+    const bool rowG = rowU && (PASS != PASS_SLOW);
+    double oU = 0.0, oV = 0.0, oG = 0.0, pU = 0.0, pV = 0.0, pG = 0.0;
+    if (out_col) {
+      if (MODE == MODE_S1 || MODE == MODE_S2) {
+        oU = AT(a.OU, j);
+        if (rowV) oV = AT(a.OV, j);
+        if (rowG) oG = AT(a.Ogd, j);
+      }
+      if (MODE == MODE_S3A) {
+        if (rowU) pU = AT(a.PU, j);
+        if (rowV) pV = AT(a.PV, j);
+        if (rowG) pG = AT(a.Pgd, j);
+      }
+    }
+    __syncthreads();
+
+    if (out_col) {
+      const double hc0 = t.cosh[j - 1], hc1 = t.cosh[j], hc2 = t.cosh[j + 1];
+      // ===================== du, full rows 1..nlat-2 (src/dycore_mod.F90:207-210) =======================
+      if (rowU) {
+        const double uc = u_(j, c), Uc = U_(j, c);
+        double dU = 0.0;
+        if (PASS != PASS_FAST) {
+          double alon, alat;
+          if (ADV == ADV_WENO) {
+            alon = AT(a.AUlon, j);
+            alat = AT(a.AUlat, j);
+          } else {
+            const double uw = u_(j, c - 1), ue = u_(j, c + 1);
+            const double Uw = U_(j, c - 1), Ue = U_(j, c + 1);
+            const double Us = U_(j - 1, c), Un = U_(j + 1, c);
+            const double u1 = uc + uw, u2 = uc + ue;
+            const double v1 = (v_(j - 1, c) + v_(j - 1, c + 1)) * hc0;
+            const double v2 = (v_(j, c) + v_(j, c + 1)) * hc1;
+            if (ADV == ADV_CENTER) {
+              alon = t.q_fdlon[j] * (u2 * Ue - u1 * Uw);   // :378-384
+              alat = t.q_fdlat[j] * (v2 * Un - v1 * Us);   // :433-439
+            } else {
+              const double bl = a.beta_lon, bt = a.beta_lat;
+              alon = t.q_fdlon[j] * (u2 * (Uc + Ue) - bl * fabs(u2) * (Ue - Uc) - u1 * (Uc + Uw) +
+                                     bl * fabs(u1) * (Uc - Uw) - (u2 - u1) * Uc);   // :395-404
+              alat = t.q_fdlat[j] * (v2 * (Uc + Un) - bt * fabs(v2) * (Un - Uc) - v1 * (Uc + Us) +
+                                     bt * fabs(v1) * (Uc - Us) - (v2 - v1) * Uc);   // :450-459
+            }
+          }
+          dU = -alon - alat;
+        }
+        if (PASS != PASS_SLOW) {
+          const double fv = 0.25 * (t.ff[j] + t.fc[j] * uc) *
+                            (t.cor1[j] * (V_(j - 1, c) + V_(j - 1, c + 1)) +
+                             t.cor2[j] * (V_(j, c) + V_(j, c + 1)));                // :485-493
+#if GMD_STRICT
+          const double pgf = 0.5 * (S_(j, c) + S_(j, c + 1)) / t.fdlon[j] * GHDIFF(j, c + 1, j, c);  // :514-519
+#else
+          const double pgf = 0.5 * (S_(j, c) + S_(j, c + 1)) * t.r_fdlon[j] * GHDIFF(j, c + 1, j, c);
+#endif
+          dU = (PASS == PASS_ALL) ? (dU + fv - pgf) : (fv - pgf);
+        }
+        if (fl & FL_DU) {
+          AT(a.TU, j) = dU;  // filtered + applied by k_polar
+        } else {
+          if (MODE == MODE_S1 || MODE == MODE_S2) AT(a.NU, j) = oU + a.dt * dU;
+          if (MODE != MODE_S1) AT(a.TU, j) = dU;
+          if (MODE == MODE_S3A) {
+            ip1 = ip1 + dU * pU * t.cosf[j];
+            ip2 = ip2 + dU * dU * t.cosf[j];
+          }
+        }
+      } else {
+        // pole rows: du is never written there (stays 0), so U' = U (src/dycore_mod.F90:623-627)
+        if (MODE == MODE_S1 || MODE == MODE_S2) AT(a.NU, j) = oU;
+      }
+      // ===================== dv, half rows 0..nlat-2 =====================================================
+      if (rowV) {
+        double dV = 0.0;
+        const double Vc = V_(j, c);
+        if (PASS != PASS_FAST) {
+          double alon, alat;
+          if (ADV == ADV_WENO) {
+            alon = AT(a.AVlon, j);
+            alat = AT(a.AVlat, j);
+          } else {
+            const double Vw = V_(j, c - 1), Ve = V_(j, c + 1);
+            const double Vs = V_(j - 1, c), Vn = V_(j + 1, c);
+            const double u1 = u_(j, c - 1) + u_(j + 1, c - 1);
+            const double u2 = u_(j, c) + u_(j + 1, c);
+            const double vh = v_(j, c) * hc1;
+            const double v1 = vh + v_(j - 1, c) * hc0;
+            const double v2 = vh + v_(j + 1, c) * hc2;
+            if (ADV == ADV_CENTER) {
+              alon = t.q_hdlon[j] * (u2 * Ve - u1 * Vw);   // :386-392
+              alat = t.q_hdlat[j] * (v2 * Vn - v1 * Vs);   // :441-447
+            } else {
+              const double bl = a.beta_lon, bt = a.beta_lat;
+              alon = t.q_hdlon[j] * (u2 * (Vc + Ve) - bl * fabs(u2) * (Ve - Vc) - u1 * (Vc + Vw) +
+                                     bl * fabs(u1) * (Vc - Vw) - (u2 - u1) * Vc);   // :406-415
+              alat = t.q_hdlat[j] * (v2 * (Vc + Vn) - bt * fabs(v2) * (Vn - Vc) - v1 * (Vc + Vs) +
+                                     bt * fabs(v1) * (Vc - Vs) - (v2 - v1) * Vc);   // :461-470
+            }
+          }
+          dV = -alon - alat;
+        }
+        if (PASS != PASS_SLOW) {
+          const double f0 = t.ff[j], c0 = t.fc[j], f1 = t.ff[j + 1], c1 = t.fc[j + 1];
+          const double fu = 0.25 * ((f0 + c0 * u_(j, c)) * U_(j, c) + (f0 + c0 * u_(j, c - 1)) * U_(j, c - 1) +
+                                    (f1 + c1 * u_(j + 1, c)) * U_(j + 1, c) +
+                                    (f1 + c1 * u_(j + 1, c - 1)) * U_(j + 1, c - 1));   // :495-503
+#if GMD_STRICT
+          const double pgf = 0.5 * (S_(j, c) + S_(j + 1, c)) / t.hdlat[j] * hc1 * GHDIFF(j + 1, c, j, c);  // :530-535
+#else
+          const double pgf = 0.5 * (S_(j, c) + S_(j + 1, c)) * t.hc_hdlat[j] * GHDIFF(j + 1, c, j, c);
+#endif
+          dV = (PASS == PASS_ALL) ? (dV - fu - pgf) : (-fu - pgf);
+        }
+        if (fl & FL_DV) {
+          AT(a.TV, j) = dV;
+        } else {
+          if (MODE == MODE_S1 || MODE == MODE_S2) AT(a.NV, j) = oV + a.dt * dV;
+          if (MODE != MODE_S1) AT(a.TV, j) = dV;
+          if (MODE == MODE_S3A) {
+            ip1 = ip1 + dV * pV * hc1;
+            ip2 = ip2 + dV * dV * hc1;
+          }
+        }
+      }
+      // ===================== dgd, full rows 1..nlat-2 (pole rows: k_polar) ===============================
+      if (rowG) {
+        const double sc = S_(j, c);
+#if GMD_STRICT
+        const double mlon = ((sc + S_(j, c + 1)) * U_(j, c) - (sc + S_(j, c - 1)) * U_(j, c - 1)) * 0.5 / t.fdlon[j];  // :546-552
+        const double mlat = ((sc + S_(j + 1, c)) * V_(j, c) * hc1 - (sc + S_(j - 1, c)) * V_(j - 1, c) * hc0) * 0.5 /
+                            t.fdlat[j];                                                                              // :564-570
+#else
+        const double mlon = ((sc + S_(j, c + 1)) * U_(j, c) - (sc + S_(j, c - 1)) * U_(j, c - 1)) * t.h_fdlon[j];
+        const double mlat =
+            ((sc + S_(j + 1, c)) * V_(j, c) * hc1 - (sc + S_(j - 1, c)) * V_(j - 1, c) * hc0) * t.h_fdlat[j];
+#endif
+        const double dG = -mlon - mlat;
+        if (fl & FL_DGD) {
+          AT(a.Tgd, j) = dG;
+        } else {
+          if (MODE == MODE_S1 || MODE == MODE_S2) AT(a.Ngd, j) = oG + a.dt * dG;
+          if (MODE != MODE_S1) AT(a.Tgd, j) = dG;
+          if (MODE == MODE_S3A) {
+            ip1 = ip1 + dG * pG * t.cosf[j];
+            ip2 = ip2 + dG * dG * t.cosf[j];
+          }
+        }
+      }
+    }
+  }
+  if (MODE == MODE_S3A) {
+    const double r1 = block_sum<BX>(ip1, red);
+    const double r2 = block_sum<BX>(ip2, red);
+    if (threadIdx.x == 0) {
+      const size_t b = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
+      a.partials[2 * b] = r1;
+      a.partials[2 * b + 1] = r2;
+    }
+  }
+#undef AT
+}
+#undef S_
+#undef U_
+#undef V_
+#undef u_
+#undef v_
+
+// ---------------------------------------------------------------------------------------------------------
+// Polar rows: the SMOOTHING blocks of space_operators (src/dycore_mod.F90:212-219,228-235,244-251) with
+// filter_array_at_{full,half}_lat (src/filter_mod.F90:105-167), and the pole caps of
+// meridional_mass_divergence_operator (src/dycore_mod.F90:572-596).  One CTA per (row, field) item.
+//
+// The FFTPACK forward -> 0/1 mask -> backward round trip keeps halfcomplex entries 1..2(c+1), i.e. it is the
+// orthogonal projector onto {1, cos k x, sin k x (k<=c), cos (c+1) x}.  The projector is applied directly
+// (2c+2 dot products with a host-precomputed basis + reconstruction): same result to rounding, no
+// butterflies, and the row never leaves shared memory.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int PT = 256;
+enum { IT_DU = 0, IT_DV = 1, IT_DGD = 2, IT_POLE_S = 3, IT_POLE_N = 4 };
+
+struct PolarItem {
+  int kind, row, cutoff, pad;
+};
+
+struct PolarArgs {
+  Geo g;
+  Tab t;
+  const PolarItem *items;
+  const double *basis;  // [2*cmax+2][nlon]: row 0 = 1, 2k-1 = cos(k x_i), 2k = sin(k x_i)
+  const double *EU, *EV, *Egd, *ghs;
+  const double *OU, *OV, *Ogd;
+  double *NU, *NV, *Ngd;
+  double *TU, *TV, *Tgd;
+  const double *PU, *PV, *Pgd;
+  double dt, pole_scale;  // pole_scale = 2 / nlon / radius / dlat applied as in :578,591
+  double *partials;       // [nitems][2]
+  int rescale;            // 1: tendency filter with inner-product rescale; 0: plain filter (diffusion)
+  int radius_dlat_div;    // unused
+  double radius, dlat;
+};
+
+// project x[0..n) (shared) onto the kept modes; coef/red are shared scratch; result overwrites x
+__device__ inline void project_row(double *x, int n, int cutoff, const double *__restrict__ basis, double *coef,
+                                   double *red) {
+  int K = cutoff + 1;  // highest (cosine-only) wavenumber kept
+  if (cutoff < 0) {    // all-zero mask
+    for (int i = threadIdx.x; i < n; i += PT) x[i] = 0.0;
+    __syncthreads();
+    return;
+  }
+  if (2 * K >= n) return;  // mask keeps every entry: the FFT round trip is the identity
+  const int ncoef = 2 * K;  // entries 0 .. 2c+1
+  const bool nyq = ((n & 1) == 0) && (K == n / 2);
+  for (int m0 = 0; m0 < ncoef; m0 += 4) {
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int i = threadIdx.x; i < n; i += PT) {
+      const double xi = x[i];
+#pragma unroll
+      for (int q = 0; q < 4; q++)
+        if (m0 + q < ncoef) acc[q] += xi * basis[(size_t)(m0 + q) * n + i];
+    }
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const double r = block_sum<PT>(acc[q], red);
+      if (threadIdx.x == 0 && m0 + q < ncoef) {
+        const int m = m0 + q;
+        double sc = (m == 0) ? 1.0 / n : 2.0 / n;
+        if (nyq && m == ncoef - 1) sc = 1.0 / n;
+        coef[m] = r * sc;
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += PT) {
+    double y = 0.0;
+    for (int m = 0; m < ncoef; m++) y += coef[m] * basis[(size_t)m * n + i];
+    x[i] = y;
+  }
+  __syncthreads();
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(PT) k_polar(const PolarArgs a) {
+  extern __shared__ double psm[];
+  __shared__ double red[32];
+  __shared__ double coef[512];
+  __shared__ double bc[2];
+  const PolarItem it = a.items[blockIdx.x];
+  const int n = a.g.nlon, r0 = a.g.r0;
+  double *x = psm;
+  const int j = it.row;
+  const ptrdiff_t off = (ptrdiff_t)(j - r0) * (ptrdiff_t)n;
+  double ip1 = 0.0, ip2 = 0.0;
+
+  if (it.kind == IT_POLE_S || it.kind == IT_POLE_N) {
+    // src/dycore_mod.F90:572-596: zonal sum of the single adjacent flux, broadcast along the pole row
+    double acc = 0.0;
+    if (it.kind == IT_POLE_S) {
+      for (int i = threadIdx.x; i < n; i += PT)
+        acc = acc + (sqrt(a.Egd[off + i]) + sqrt(a.Egd[off + n + i])) * a.EV[off + i];
+    } else {
+      for (int i = threadIdx.x; i < n; i += PT)
+        acc = acc - (sqrt(a.Egd[off + i]) + sqrt(a.Egd[off - n + i])) * a.EV[off - n + i];
+    }
+    const double r = block_sum<PT>(acc, red);
+    if (threadIdx.x == 0) bc[0] = -(r * 2.0 / n / a.radius / a.dlat);  // dgd = -mass_div_lon(=0) - mass_div_lat
+    __syncthreads();
+    const double dG = bc[0];
+    const double cw = a.t.cosf[j];
+    for (int i = threadIdx.x; i < n; i += PT) {
+      if (MODE == MODE_S1 || MODE == MODE_S2) a.Ngd[off + i] = a.Ogd[off + i] + a.dt * dG;
+      if (MODE != MODE_S1) a.Tgd[off + i] = dG;
+      if (MODE == MODE_S3A) {
+        ip1 = ip1 + dG * a.Pgd[off + i] * cw;
+        ip2 = ip2 + dG * dG * cw;
+      }
+    }
+  } else {
+    double *T = (it.kind == IT_DU) ? a.TU : (it.kind == IT_DV) ? a.TV : a.Tgd;
+    const double *W = (it.kind == IT_DU) ? a.EU : (it.kind == IT_DV) ? a.EV : a.Egd;
+    double s1p = 0.0;
+    for (int i = threadIdx.x; i < n; i += PT) {
+      const double xi = T[off + i];
+      x[i] = xi;
+      if (a.rescale) {
+        const double w = (it.kind == IT_DGD) ? (W[off + i] + a.ghs[off + i]) : W[off + i];
+        s1p = s1p + xi * w;
+      }
+    }
+    bool do_filter = true;
+    double s1 = 0.0;
+    if (a.rescale) {
+      const double r = block_sum<PT>(s1p, red);
+      if (threadIdx.x == 0) bc[0] = r;
+      __syncthreads();
+      s1 = bc[0];
+      do_filter = fabs(s1) > 1.0e-16;  // filter_inner_product_threshold, src/filter_mod.F90:31
+    } else {
+      __syncthreads();
+    }
+    if (do_filter) {
+      project_row(x, n, it.cutoff, a.basis, coef, red);
+      if (a.rescale) {
+        double s2p = 0.0;
+        for (int i = threadIdx.x; i < n; i += PT) {
+          const double w = (it.kind == IT_DGD) ? (W[off + i] + a.ghs[off + i]) : W[off + i];
+          s2p = s2p + x[i] * w;
+        }
+        const double r = block_sum<PT>(s2p, red);
+        if (threadIdx.x == 0) bc[1] = r;
+        __syncthreads();
+        const double s2 = bc[1];
+        for (int i = threadIdx.x; i < n; i += PT) x[i] = x[i] * s1 / s2;  // :218
+      }
+    }
+    const double *O = (it.kind == IT_DU) ? a.OU : (it.kind == IT_DV) ? a.OV : a.Ogd;
+    double *N = (it.kind == IT_DU) ? a.NU : (it.kind == IT_DV) ? a.NV : a.Ngd;
+    const double *P = (it.kind == IT_DU) ? a.PU : (it.kind == IT_DV) ? a.PV : a.Pgd;
+    const double cw = (it.kind == IT_DV) ? a.t.cosh[j] : a.t.cosf[j];
+    for (int i = threadIdx.x; i < n; i += PT) {
+      const double d = x[i];
+      if (MODE == MODE_S1 || MODE == MODE_S2) N[off + i] = O[off + i] + a.dt * d;
+      if (MODE != MODE_S1) T[off + i] = d;
+      if (MODE == MODE_S3A) {
+        ip1 = ip1 + d * P[off + i] * cw;
+        ip2 = ip2 + d * d * cw;
+      }
+    }
+  }
+  if (MODE == MODE_S3A) {
+    const double r1 = block_sum<PT>(ip1, red);
+    const double r2 = block_sum<PT>(ip2, red);
+    if (threadIdx.x == 0) {
+      a.partials[2 * blockIdx.x] = r1;
+      a.partials[2 * blockIdx.x + 1] = r2;
+    }
+  }
+}
+
+// sum `n` pairs of partials in index order (deterministic) -> out[0], out[1]
+__global__ void __launch_bounds__(256) k_reduce_pairs(const double *__restrict__ partials, int n, double *out) {
+  __shared__ double red[32];
+  double a0 = 0.0, a1 = 0.0;
+  for (int k = threadIdx.x; k < n; k += 256) {
+    a0 += partials[2 * k];
+    a1 += partials[2 * k + 1];
+  }
+  const double r0 = block_sum<256>(a0, red);
+  const double r1 = block_sum<256>(a1, red);
+  if (threadIdx.x == 0) {
+    out[0] = r0;
+    out[1] = r1;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Element-wise kernels
+// ---------------------------------------------------------------------------------------------------------
+struct UpdateArgs {
+  Geo g;
+  const double *OU, *OV, *Ogd;
+  const double *TU, *TV, *Tgd;
+  double *NU, *NV, *Ngd;
+  double dt;
+  const double *ip;   // device {ip1, ip2} or NULL
+  int qcon, beta_mode;  // beta_mode 0: dt ; 1: dt*beta (predict_correct :786-790) ; 2: dt * (beta*4/dt0) (isp :745-750)
+  double dt0;
+  double *beta_out;   // device scalar, written by one thread
+  int with_gd;        // 0: slow pass, gd is shared
+};
+
+__device__ __forceinline__ double beta_from_ip(const double *ip, int qcon) {
+  const double ip1 = ip[0], ip2 = ip[1];
+  return (qcon && ip1 != 0.0 && ip2 != 0.0) ? ip1 / ip2 : 1.0;
+}
+
+// update_state on stored tendencies (src/dycore_mod.F90:600-652), U/V/gd only: new = old + dt' * tend
+__global__ void __launch_bounds__(256) k_update(const UpdateArgs a) {
+  double dt = a.dt;
+  if (a.beta_mode) {
+    double beta = beta_from_ip(a.ip, a.qcon);
+    if (a.beta_mode == 2) beta = beta * 4.0 / a.dt0;
+    dt = a.dt * beta;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && a.beta_out) *a.beta_out = beta;
+  }
+  const int nlon = a.g.nlon, nlat = a.g.nlat;
+  const size_t nrow = (size_t)(a.g.r1 - a.g.r0);
+  const size_t total = nrow * (size_t)nlon;
+  for (ptrdiff_t k = (ptrdiff_t)blockIdx.x * 256 + threadIdx.x; k < (ptrdiff_t)total; k += (ptrdiff_t)gridDim.x * 256) {
+    const int j = a.g.r0 + (int)(k / (ptrdiff_t)nlon);
+    if (j >= 1 && j <= nlat - 2) a.NU[k] = a.OU[k] + dt * a.TU[k];
+    else a.NU[k] = a.OU[k];
+    if (j <= nlat - 2) a.NV[k] = a.OV[k] + dt * a.TV[k];
+    if (a.with_gd) a.Ngd[k] = a.Ogd[k] + dt * a.Tgd[k];
+  }
+}
+
+// iap_transform (src/types_mod.F90:399-426): U = 0.5 (s_i + s_i+1) u ; V = 0.5 (s_j + s_j+1) v
+__global__ void __launch_bounds__(256) k_iap(Geo g, const double *u, const double *v, const double *gd, double *U,
+                                             double *V) {
+  const int nlon = g.nlon;
+  const size_t total = (size_t)(g.r1 - g.r0) * (size_t)nlon;
+  for (ptrdiff_t k = (ptrdiff_t)blockIdx.x * 256 + threadIdx.x; k < (ptrdiff_t)total; k += (ptrdiff_t)gridDim.x * 256) {
+    const int lj = (int)(k / (ptrdiff_t)nlon), i = (int)(k - (ptrdiff_t)lj * nlon), j = g.r0 + lj;
+    const int ie = (i + 1 == nlon) ? 0 : i + 1;
+    const double s = sqrt(gd[k]);
+    const double se = sqrt(gd[(ptrdiff_t)lj * nlon + ie]);
+    U[k] = 0.5 * (s + se) * u[k];
+    if (j <= g.nlat - 2) {
+      const double sn = sqrt(gd[k + nlon]);
+      V[k] = 0.5 * (s + sn) * v[k];
+    }
+  }
+}
+
+// inverse: u = 2U/(s_i+s_i+1), v = 2V/(s_j+s_j+1) on rows [ja, jb) (may include ghost rows inside the globe)
+__global__ void __launch_bounds__(256) k_derive(Geo g, int ja, int jb, const double *U, const double *V,
+                                                const double *gd, double *u, double *v, double *s_out) {
+  const int nlon = g.nlon;
+  const size_t total = (size_t)(jb - ja) * (size_t)nlon;
+  for (ptrdiff_t k = (ptrdiff_t)blockIdx.x * 256 + threadIdx.x; k < (ptrdiff_t)total; k += (ptrdiff_t)gridDim.x * 256) {
+    const int lj = (int)(k / (ptrdiff_t)nlon), i = (int)(k - (ptrdiff_t)lj * nlon), j = ja + lj;
+    const ptrdiff_t o = (ptrdiff_t)(j - g.r0) * nlon + i;
+    const int ie = (i + 1 == nlon) ? 0 : i + 1;
+    const double s = sqrt(gd[o]);
+    const double se = sqrt(gd[(ptrdiff_t)(j - g.r0) * nlon + ie]);
+    if (u) u[o] = U[o] * 2.0 / (s + se);
+    if (v && j <= g.nlat - 2) v[o] = V[o] * 2.0 / (s + sqrt(gd[o + nlon]));
+    if (s_out) s_out[o] = s;
+  }
+}
+
+// diag_run totals (src/diag_mod.F90:71-77,98-121): per-CTA partials {sum cos dlon dlat gd, energy}
+__global__ void __launch_bounds__(256) k_diag(Geo g, Tab t, const double *U, const double *V, const double *gd,
+                                              const double *ghs, double dlon, double dlat, double *partials) {
+  __shared__ double red[32];
+  const int nlon = g.nlon;
+  const size_t total = (size_t)(g.r1 - g.r0) * (size_t)nlon;
+  double m = 0.0, e = 0.0;
+  for (ptrdiff_t k = (ptrdiff_t)blockIdx.x * 256 + threadIdx.x; k < (ptrdiff_t)total; k += (ptrdiff_t)gridDim.x * 256) {
+    const int j = g.r0 + (int)(k / (ptrdiff_t)nlon);
+    const double cf = t.cosf[j];
+    const double gdv = gd[k], gh = gdv + ghs[k];
+    m = m + cf * dlon * dlat * gdv;
+    if (j >= 1 && j <= g.nlat - 2) {
+      const double Uv = U[k];
+      e = e + Uv * Uv * cf;
+    }
+    if (j <= g.nlat - 2) {
+      const double Vv = V[k];
+      e = e + Vv * Vv * t.cosh[j];
+    }
+    e = e + gh * gh * cf;
+  }
+  const double rm = block_sum<256>(m, red);
+  const double re = block_sum<256>(e, red);
+  if (threadIdx.x == 0) {
+    partials[2 * blockIdx.x] = rm;
+    partials[2 * blockIdx.x + 1] = re;
+  }
+}
+
+// ring[ctr % nring] = {mass * radius^2, energy, beta}; the step counter lives on the device so that a
+// captured graph of one model step is replayable for any step number
+__global__ void k_diag_store(const double *sums, const double *beta, double radius, double *ring, int *ctr,
+                             int advance, int nring) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    int c = *ctr;
+    if (advance) {
+      c += 1;
+      *ctr = c;
+    }
+    const int slot = c % nring;
+    ring[3 * slot] = sums[0] * (radius * radius);
+    ring[3 * slot + 1] = sums[1];
+    ring[3 * slot + 2] = *beta;
+  }
+}
+
+// <a, b> with the inner-product weights (src/types_mod.F90:347-397); out partials pairs {dot, 0}
+__global__ void __launch_bounds__(256) k_dot(Geo g, Tab t, const double *aU, const double *aV, const double *aG,
+                                             const double *bU, const double *bV, const double *bG, int with_gd,
+                                             double *partials, int slot) {
+  __shared__ double red[32];
+  const int nlon = g.nlon;
+  const size_t total = (size_t)(g.r1 - g.r0) * (size_t)nlon;
+  double s = 0.0;
+  for (ptrdiff_t k = (ptrdiff_t)blockIdx.x * 256 + threadIdx.x; k < (ptrdiff_t)total; k += (ptrdiff_t)gridDim.x * 256) {
+    const int j = g.r0 + (int)(k / (ptrdiff_t)nlon);
+    if (j >= 1 && j <= g.nlat - 2) s = s + aU[k] * bU[k] * t.cosf[j];
+    if (j <= g.nlat - 2) s = s + aV[k] * bV[k] * t.cosh[j];
+    if (with_gd) s = s + aG[k] * bG[k] * t.cosf[j];
+  }
+  const double r = block_sum<256>(s, red);
+  if (threadIdx.x == 0) {
+    partials[2 * blockIdx.x + slot] = r;
+    if (slot == 0) partials[2 * blockIdx.x + 1] = 0.0;
+  }
+}
+
+// y = alpha * x + beta * y on the three tendency arrays (tend algebra, src/types_mod.F90:229-345)
+__global__ void __launch_bounds__(256) k_axpby3(size_t total, double alpha, const double *xU, const double *xV,
+                                                const double *xG, double beta, double *yU, double *yV, double *yG) {
+  for (ptrdiff_t k = (ptrdiff_t)blockIdx.x * 256 + threadIdx.x; k < (ptrdiff_t)total; k += (ptrdiff_t)gridDim.x * 256) {
+    yU[k] = (beta == 0.0 ? 0.0 : beta * yU[k]) + (alpha == 0.0 ? 0.0 : alpha * xU[k]);
+    yV[k] = (beta == 0.0 ? 0.0 : beta * yV[k]) + (alpha == 0.0 ? 0.0 : alpha * xV[k]);
+    yG[k] = (beta == 0.0 ? 0.0 : beta * yG[k]) + (alpha == 0.0 ? 0.0 : alpha * xG[k]);
+  }
+}
+
+// diag vor/div (src/diag_mod.F90:47-69) from derived u, v
+__global__ void __launch_bounds__(256) k_vor_div(Geo g, Tab t, const double *u, const double *v, double *vor,
+                                                 double *div) {
+  const int nlon = g.nlon, nlat = g.nlat;
+  const size_t total = (size_t)(g.r1 - g.r0) * (size_t)nlon;
+  for (ptrdiff_t k = (ptrdiff_t)blockIdx.x * 256 + threadIdx.x; k < (ptrdiff_t)total; k += (ptrdiff_t)gridDim.x * 256) {
+    const int lj = (int)(k / (ptrdiff_t)nlon), i = (int)(k - (ptrdiff_t)lj * nlon), j = g.r0 + lj;
+    const int iw = (i == 0) ? nlon - 1 : i - 1, ie = (i + 1 == nlon) ? 0 : i + 1;
+    const ptrdiff_t row = (ptrdiff_t)lj * nlon;
+    if (j >= 1 && j <= nlat - 2) {
+      const double um1 = u[row + iw], up1 = u[k];
+      const double vm1 = v[k - nlon] * t.cosh[j - 1], vp1 = v[k] * t.cosh[j];
+      div[k] = (up1 - um1) / t.fdlon[j] + (vp1 - vm1) / t.fdlat[j];
+    } else {
+      div[k] = 0.0;
+    }
+    if (j <= nlat - 2) {
+      const double um1 = u[k], up1 = u[k + nlon];
+      const double vm1 = v[k], vp1 = v[row + ie];
+      vor[k] = (vp1 - vm1) / t.hdlon[j] - (up1 - um1) / t.hdlat[j];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// ordinary_diffusion (src/diffusion_mod.F90:74-217)
+// ---------------------------------------------------------------------------------------------------------
+// one scalar-Laplacian pass on (u, v, gd) -> (ud, vd, gdd), rows [r0, r1); gd pole rows by k_lap_pole
+__global__ void __launch_bounds__(256) k_laplace(Geo g, Tab t, const double *u, const double *v, const double *gd,
+                                                 double *ud, double *vd, double *gdd) {
+  const int nlon = g.nlon, nlat = g.nlat;
+  const size_t total = (size_t)(g.r1 - g.r0) * (size_t)nlon;
+  for (ptrdiff_t k = (ptrdiff_t)blockIdx.x * 256 + threadIdx.x; k < (ptrdiff_t)total; k += (ptrdiff_t)gridDim.x * 256) {
+    const int lj = (int)(k / (ptrdiff_t)nlon), i = (int)(k - (ptrdiff_t)lj * nlon), j = g.r0 + lj;
+    const int iw = (i == 0) ? nlon - 1 : i - 1, ie = (i + 1 == nlon) ? 0 : i + 1;
+    const ptrdiff_t row = (ptrdiff_t)lj * nlon;
+    if (j >= 1 && j <= nlat - 2) {
+      const double dl2 = t.fdlon[j] * t.fdlon[j], dt2 = t.fdlat[j] * t.fdlat[j];
+      const double hc1 = t.cosh[j], hc0 = t.cosh[j - 1], fc = t.cosf[j];
+      {
+        const double q = gd[k];
+        gdd[k] = (gd[row + ie] - 2 * q + gd[row + iw]) / dl2 +
+                 ((gd[k + nlon] - q) * hc1 - (q - gd[k - nlon]) * hc0) / dt2 * fc;   // :109-114
+      }
+      {
+        const double q = u[k];
+        ud[k] = (u[row + ie] - 2 * q + u[row + iw]) / dl2 +
+                ((u[k + nlon] - q) * hc1 - (q - u[k - nlon]) * hc0) / dt2 * fc;      // :135-138
+      }
+    } else {
+      ud[k] = 0.0;  // pole rows of ud are never written in the reference (stay 0)
+    }
+    if (j <= nlat - 2) {
+      const double q = v[k];
+      const double hl2 = t.hdlon[j] * t.hdlon[j], ht2 = t.hdlat[j] * t.hdlat[j];
+      double r = (v[row + ie] - 2 * q + v[row + iw]) / hl2;                          // :145-147
+      if (j >= 1 && j <= nlat - 3)
+        r = r + ((v[k + nlon] - q) * t.cosf[j + 1] - (q - v[k - nlon]) * t.cosf[j]) / ht2 * t.cosh[j];  // :148-157
+      else if (j == 0)
+        r = r + (v[k + nlon] - q) * t.cosf[j + 1] / ht2 * t.cosh[j];                 // :158-163
+      else
+        r = r - (q - v[k - nlon]) * t.cosf[j] / ht2 * t.cosh[j];                     // :164-170
+      vd[k] = r;
+    }
+  }
+}
+
+// gd pole caps of the Laplacian (src/diffusion_mod.F90:116-133); blockIdx.x: 0 south, 1 north
+__global__ void __launch_bounds__(PT) k_lap_pole(Geo g, Tab t, const double *gd, double *gdd, int do_south,
+                                                 int do_north) {
+  __shared__ double red[32];
+  __shared__ double bc;
+  const int n = g.nlon, nlat = g.nlat;
+  const bool south = (blockIdx.x == 0);
+  if ((south && !do_south) || (!south && !do_north)) return;
+  const int j = south ? 0 : nlat - 1;
+  const ptrdiff_t off = (ptrdiff_t)(j - g.r0) * n;
+  double acc = 0.0;
+  if (south) {
+    for (int i = threadIdx.x; i < n; i += PT) acc = acc + gd[off + n + i] - gd[off + i];
+  } else {
+    for (int i = threadIdx.x; i < n; i += PT) acc = acc - (gd[off + i] - gd[off - n + i]);
+  }
+  const double r = block_sum<PT>(acc, red);
+  if (threadIdx.x == 0) {
+    const double hc = south ? t.cosh[0] : t.cosh[nlat - 2];
+    bc = r * hc / (t.fdlat[j] * t.fdlat[j]) * t.cosf[j] / n;
+  }
+  __syncthreads();
+  const double vv = bc;
+  for (int i = threadIdx.x; i < n; i += PT) gdd[off + i] = vv;
+}
+
+// q += sign dt coef lap(q) for gd,u,v, then iap_transform (src/diffusion_mod.F90:195-215)
+__global__ void __launch_bounds__(256) k_diff_update(Geo g, const double *u, const double *v, const double *gd,
+                                                     const double *ud, const double *vd, const double *gdd,
+                                                     double sdc, double *NU, double *NV, double *Ngd) {
+  const int nlon = g.nlon, nlat = g.nlat;
+  const size_t total = (size_t)(g.r1 - g.r0) * (size_t)nlon;
+  for (ptrdiff_t k = (ptrdiff_t)blockIdx.x * 256 + threadIdx.x; k < (ptrdiff_t)total; k += (ptrdiff_t)gridDim.x * 256) {
+    const int lj = (int)(k / (ptrdiff_t)nlon), i = (int)(k - (ptrdiff_t)lj * nlon), j = g.r0 + lj;
+    const int ie = (i + 1 == nlon) ? 0 : i + 1;
+    const ptrdiff_t ke = (ptrdiff_t)lj * nlon + ie;
+    const double g0 = gd[k] + sdc * gdd[k];
+    const double ge = gd[ke] + sdc * gdd[ke];
+    const double s0 = sqrt(g0), se = sqrt(ge);
+    Ngd[k] = g0;
+    const double un = u[k] + sdc * ud[k];
+    NU[k] = 0.5 * (s0 + se) * un;
+    if (j <= nlat - 2) {
+      const double gn = gd[k + nlon] + sdc * gdd[k + nlon];
+      const double vn = v[k] + sdc * vd[k];
+      NV[k] = 0.5 * (s0 + sqrt(gn)) * vn;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// WENO advection (src/weno_mod.F90:69-300), order 2 -- unfused sweeps on derived u, v (a "next" row of the
+// scope table: correct first, fused later).  All arrays are band fields.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double weno2(double fp1, double fp2, double fp3, double fn2, double fn3, double fn4) {
+  const double eps = 1.0e-6;
+  const double c11 = -1.0 / 2.0, c21 = 3.0 / 2.0, c12 = 1.0 / 2.0, c22 = 1.0 / 2.0;
+  const double wo1 = 1.0 / 3.0, wo2 = 2.0 / 3.0;
+  double fs1 = c11 * fp1 + c21 * fp2;
+  double fs2 = c12 * fp2 + c22 * fp3;
+  double b1 = (fp2 - fp1) * (fp2 - fp1);
+  double b2 = (fp3 - fp2) * (fp3 - fp2);
+  double w1 = wo1 / ((eps + b1) * (eps + b1));
+  double w2 = wo2 / ((eps + b2) * (eps + b2));
+  double sw = w1 + w2;
+  w1 = w1 / sw;
+  w2 = w2 / sw;
+  double f = w1 * fs1 + w2 * fs2;
+  fs1 = c11 * fn4 + c21 * fn3;
+  fs2 = c12 * fn3 + c22 * fn2;
+  b1 = (fn3 - fn4) * (fn3 - fn4);
+  b2 = (fn2 - fn3) * (fn2 - fn3);
+  w1 = wo1 / ((eps + b1) * (eps + b1));
+  w2 = wo2 / ((eps + b2) * (eps + b2));
+  sw = w1 + w2;
+  w1 = w1 / sw;
+  w2 = w2 / sw;
+  f = f + (w1 * fs1 + w2 * fs2);
+  return f;
+}
+
+struct WenoArgs {
+  Geo g;
+  Tab t;
+  const double *u, *v, *U, *V;    // derived u, v and IAP U, V
+  double *fpu, *fnu, *fpv, *fnv;  // split fluxes
+  double *fu, *fv;                // reconstructed fluxes
+  double *alon_u, *alat_u, *alon_v, *alat_v;
+  int dir;                        // 0 zonal, 1 meridional
+};
+
+// Lax-Friedrichs split fluxes; rows outside their definition range are written as 0 (the reference's
+// never-written zero rows of the work arrays)
+__global__ void __launch_bounds__(256) k_weno_split(const WenoArgs a) {
+  const int nlon = a.g.nlon, nlat = a.g.nlat;
+  const size_t total = (size_t)(a.g.r1 - a.g.r0) * (size_t)nlon;
+  const double amax = 20.0;
+  for (ptrdiff_t k = (ptrdiff_t)blockIdx.x * 256 + threadIdx.x; k < (ptrdiff_t)total; k += (ptrdiff_t)gridDim.x * 256) {
+    const int lj = (int)(k / (ptrdiff_t)nlon), i = (int)(k - (ptrdiff_t)lj * nlon), j = a.g.r0 + lj;
+    const int iw = (i == 0) ? nlon - 1 : i - 1, ie = (i + 1 == nlon) ? 0 : i + 1;
+    const ptrdiff_t row = (ptrdiff_t)lj * nlon;
+    if (j >= 1 && j <= nlat - 2) {
+      double w;
+      if (a.dir == 0) w = a.u[k];
+      else w = 0.25 * (a.v[k - nlon] + a.v[k] + a.v[row - nlon + ie] + a.v[row + ie]);
+      a.fpu[k] = 0.5 * (w + amax) * a.U[k];
+      a.fnu[k] = 0.5 * (w - amax) * a.U[k];
+    } else {
+      a.fpu[k] = 0.0;
+      a.fnu[k] = 0.0;
+    }
+    if (j <= nlat - 2) {
+      double w;
+      if (a.dir == 0) w = 0.25 * (a.u[row + iw] + a.u[row + nlon + iw] + a.u[k] + a.u[k + nlon]);
+      else w = a.v[k];
+      a.fpv[k] = 0.5 * (w + amax) * a.V[k];
+      a.fnv[k] = 0.5 * (w - amax) * a.V[k];
+    } else {
+      a.fpv[k] = 0.0;
+      a.fnv[k] = 0.0;
+    }
+  }
+}
+
+// reads a band work array with zero outside the globe rows [lo, hi]
+__device__ __forceinline__ double rd(const double *p, const Geo &g, int j, int i, int lo, int hi) {
+  return (j < lo || j > hi) ? 0.0 : p[(ptrdiff_t)(j - g.r0) * g.nlon + i];
+}
+
+__global__ void __launch_bounds__(256) k_weno_flux(const WenoArgs a) {
+  const int nlon = a.g.nlon, nlat = a.g.nlat;
+  const size_t total = (size_t)(a.g.r1 - a.g.r0) * (size_t)nlon;
+  for (ptrdiff_t k = (ptrdiff_t)blockIdx.x * 256 + threadIdx.x; k < (ptrdiff_t)total; k += (ptrdiff_t)gridDim.x * 256) {
+    const int lj = (int)(k / (ptrdiff_t)nlon), i = (int)(k - (ptrdiff_t)lj * nlon), j = a.g.r0 + lj;
+    const int iw = (i == 0) ? nlon - 1 : i - 1, ie = (i + 1 == nlon) ? 0 : i + 1;
+    const int ie2 = (ie + 1 == nlon) ? 0 : ie + 1;
+    const ptrdiff_t row = (ptrdiff_t)lj * nlon;
+    if (a.dir == 0) {
+      if (j >= 1 && j <= nlat - 2)
+        a.fu[k] = weno2(a.fpu[row + iw], a.fpu[k], a.fpu[row + ie], a.fnu[k], a.fnu[row + ie], a.fnu[row + ie2]);
+      else a.fu[k] = 0.0;
+      if (j <= nlat - 2)
+        a.fv[k] = weno2(a.fpv[row + iw], a.fpv[k], a.fpv[row + ie], a.fnv[k], a.fnv[row + ie], a.fnv[row + ie2]);
+      else a.fv[k] = 0.0;
+    } else {
+      // rows beyond the work arrays' range read as 0 (zero lat halos / never-written rows)
+      if (j >= 1 && j <= nlat - 2)
+        a.fu[k] = weno2(rd(a.fpu, a.g, j - 1, i, 1, nlat - 2), a.fpu[k], rd(a.fpu, a.g, j + 1, i, 1, nlat - 2),
+                        a.fnu[k], rd(a.fnu, a.g, j + 1, i, 1, nlat - 2), rd(a.fnu, a.g, j + 2, i, 1, nlat - 2));
+      else a.fu[k] = 0.0;
+      if (j <= nlat - 2)
+        a.fv[k] = weno2(rd(a.fpv, a.g, j - 1, i, 0, nlat - 2), a.fpv[k], rd(a.fpv, a.g, j + 1, i, 0, nlat - 2),
+                        a.fnv[k], rd(a.fnv, a.g, j + 1, i, 0, nlat - 2), rd(a.fnv, a.g, j + 2, i, 0, nlat - 2));
+      else a.fv[k] = 0.0;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_weno_adv(const WenoArgs a) {
+  const int nlon = a.g.nlon, nlat = a.g.nlat;
+  const size_t total = (size_t)(a.g.r1 - a.g.r0) * (size_t)nlon;
+  for (ptrdiff_t k = (ptrdiff_t)blockIdx.x * 256 + threadIdx.x; k < (ptrdiff_t)total; k += (ptrdiff_t)gridDim.x * 256) {
+    const int lj = (int)(k / (ptrdiff_t)nlon), i = (int)(k - (ptrdiff_t)lj * nlon), j = a.g.r0 + lj;
+    const int iw = (i == 0) ? nlon - 1 : i - 1, ie = (i + 1 == nlon) ? 0 : i + 1;
+    const ptrdiff_t row = (ptrdiff_t)lj * nlon;
+    if (a.dir == 0) {
+      if (j >= 1 && j <= nlat - 2)   // B8: half_dlon(j) on a full row, src/weno_mod.F90:151-155
+        a.alon_u[k] = (a.fu[k] - a.fu[row + iw] - (a.u[row + ie] - a.u[row + iw]) * a.U[k] * 0.25) / a.t.hdlon[j];
+      if (j <= nlat - 2)
+        a.alon_v[k] = (a.fv[k] - a.fv[row + iw] -
+                       (a.u[k] + a.u[k + nlon] - a.u[row + iw] - a.u[row + nlon + iw]) * a.V[k] * 0.25) /
+                      a.t.hdlon[j];
+    } else {
+      if (j >= 1 && j <= nlat - 2)
+        a.alat_u[k] = (a.fu[k] - rd(a.fu, a.g, j - 1, i, 1, nlat - 2) -
+                       (a.v[row + iw] + a.v[k] - a.v[row - nlon + iw] - a.v[k - nlon]) * a.U[k] * 0.25) /
+                      a.t.fdlat[j];
+      if (j <= nlat - 2)
+        a.alat_v[k] = (a.fv[k] - rd(a.fv, a.g, j - 1, i, 0, nlat - 2) -
+                       (rd(a.v, a.g, j + 1, i, 0, nlat - 2) - rd(a.v, a.g, j - 1, i, 0, nlat - 2)) * a.V[k] * 0.25) /
+                      a.t.hdlat[j];
+    }
+  }
+}
+
+}  // namespace gmd

@@ -1,0 +1,321 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (include/gmd.h via ctypes), against the CPU oracle.
+
+Tolerances (all fp64; `rel` = relative L2, `relmax` = max-norm relative to the field's max):
+  * libgmd_strict.so (divisions and operand order of the reference, no FMA contraction) must agree with the
+    oracle to a few ulp on a single operator evaluation: relmax <= 2e-15 away from the reduction rows
+    (zonal sums / filter rows use a tree instead of the serial sum) and rel <= 1e-13 on them.
+  * libgmd.so (the product; reciprocal tables + DFMA) single evaluation rel <= 5e-14, one model step rel <= 1e-12
+    and mass/energy series <= 1e-13 relative, the tolerances BASELINE.json's north_star states.
+Longer runs are compared beside the algorithm's own rounding-noise floor (oracle vs oracle with a 1e-16 relative
+perturbation of the initial gd), SURVEY.md F8.
+"""
+import ast
+
+import numpy as np
+import pytest
+
+import gamil_dycore_b200 as gmd
+from oracle.oracle import Oracle, OracleConfig
+from test_oracle import generic_state, rel
+
+pytestmark = pytest.mark.gpu
+
+
+def relmax(a, b):
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+def cfg_pair(**kw):
+    return OracleConfig(**kw), gmd.Config(**kw)
+
+
+def make_pair(kind="fast", state=None, test_case=None, **kw):
+    oc, gc = cfg_pair(**kw)
+    o = Oracle(oc)
+    d = gmd.Dycore(gc, kind=kind)
+    if test_case is not None:
+        o.set_initial_condition(test_case)
+        u, v, gd = o.state()
+        ghs = o.ghs()
+    else:
+        u, v, gd, ghs = state
+        o.set_state(u, v, gd, ghs)
+    d.set_state(u, v, gd, ghs)
+    o.run_init()
+    d.run_init()
+    return o, d
+
+
+def test_library_is_the_cuda_path():
+    lib = gmd.load("fast")
+    assert lib.gmd_version() == 100
+    import torch
+    assert torch.cuda.is_available()
+
+
+def test_tables_and_filter_rows_bit_identical():
+    kw = dict(num_lon=72, num_lat=37, time_step_size=600.0, zonal_tend_filter_cutoff_wavenumber=[5, 4, 3])
+    o, d = make_pair(test_case="rossby_haurwitz_wave", **kw)
+    for which in range(10):
+        assert np.array_equal(o.table(which), d.table(which)), which
+    for a, b in zip(o.filter_rows(), d.filter_rows()):
+        assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("n,cut", [(36, [4, 4]), (72, [5, 4, 3]), (360, [4] * 5), (3600, [8, 6, 4])])
+def test_filter_row_matches_fftpack_round_trip(n, cut):
+    nlat = 19
+    kw = dict(num_lon=n, num_lat=nlat, time_step_size=600.0, zonal_tend_filter_cutoff_wavenumber=cut)
+    o, d = make_pair(test_case="rossby_haurwitz_wave", **kw)
+    rng = np.random.default_rng(n)
+    for half, row in [(False, 1), (False, 2), (True, 0), (True, nlat - 3), (False, nlat - 2), (False, 9)]:
+        x = rng.standard_normal(n)
+        yo = o.filter_row(half, row, x)
+        yd = d.filter_row(half, row, x)
+        assert np.abs(yo - yd).max() <= 2e-15 * np.abs(x).max() * max(1.0, np.log2(n) / 4), (half, row)
+
+
+@pytest.mark.parametrize("adv", ["center_diff", "upwind", "weno"])
+@pytest.mark.parametrize("pass_", ["all", "fast", "slow"])
+def test_single_evaluation_strict(adv, pass_):
+    kw = dict(num_lon=72, num_lat=37, time_step_size=600.0, uv_adv_scheme=adv, uv_adv_upwind_lon_beta=0.2,
+              uv_adv_upwind_lat_beta=0.1, zonal_tend_filter_cutoff_wavenumber=[5, 4, 3])
+    o, d = make_pair("strict", state=generic_state(72, 37, seed=3), **kw)
+    ref = o.space_operators(pass_)
+    got = d.space_operators(pass_)
+    ff, _, hf, _ = o.filter_rows()
+    for name, a, b, flags in zip(("du", "dv", "dgd"), got, ref, (ff, hf, ff)):
+        plain = np.ones(b.shape[0], bool)
+        plain[np.nonzero(flags[: b.shape[0]])[0]] = False
+        if name == "dgd":
+            plain[0] = plain[-1] = False
+        scale = max(np.abs(b).max(), 1e-300)
+        if np.abs(b).max() == 0.0:
+            assert np.abs(a).max() == 0.0
+            continue
+        # the minimal state recomputes u = 2U/(s+s): 1-2 ulp on u, amplified by the advective cancellation
+        assert np.abs(a[plain] - b[plain]).max() / scale <= 4e-15, (name, "plain rows")
+        assert rel(a, b) <= 1e-13, name
+
+
+@pytest.mark.parametrize("adv", ["center_diff", "upwind", "weno"])
+def test_single_evaluation_fast(adv):
+    kw = dict(num_lon=72, num_lat=37, time_step_size=600.0, uv_adv_scheme=adv, uv_adv_upwind_lat_beta=0.1,
+              zonal_tend_filter_cutoff_wavenumber=[5, 4, 3])
+    o, d = make_pair("fast", state=generic_state(72, 37, seed=4), **kw)
+    for pass_ in ("all", "fast", "slow"):
+        ref = o.space_operators(pass_)
+        got = d.space_operators(pass_)
+        for name, a, b in zip(("du", "dv", "dgd"), got, ref):
+            if np.abs(b).max() == 0.0:
+                assert np.abs(a).max() == 0.0
+            else:
+                assert rel(a, b) <= 5e-14, (pass_, name, rel(a, b))
+
+
+@pytest.mark.parametrize("kind,tol", [("strict", 2e-14), ("fast", 1e-13)])
+@pytest.mark.parametrize("pass_", ["all", "fast", "slow"])
+def test_predict_correct(kind, tol, pass_):
+    kw = dict(num_lon=72, num_lat=37, time_step_size=300.0, zonal_tend_filter_cutoff_wavenumber=[5, 4, 3])
+    o, d = make_pair(kind, state=generic_state(72, 37, seed=5), **kw)
+    o.predict_correct(300.0, pass_)
+    d.predict_correct(300.0, pass_)
+    for name, a, b in zip("u v gd".split(), d.state(), o.state()):
+        assert rel(a, b) <= tol, (name, rel(a, b))
+    for name, a, b in zip("U V s".split(), d.iap_state(), o.iap_state()):
+        assert rel(a, b) <= tol, (name, rel(a, b))
+
+
+def test_pole_rows_and_reference_layout():
+    kw = dict(num_lon=48, num_lat=25, time_step_size=600.0, split_scheme="none",
+              zonal_tend_filter_cutoff_wavenumber=[3, 3])
+    u, v, gd, ghs = generic_state(48, 25, seed=6)
+    o, d = make_pair("fast", state=(u, v, gd, ghs), **kw)
+    o.step(2)
+    d.step(2)
+    ur, vr, gdr = d.state_reference_layout()
+    uc, vc, gdc = d.state()
+    assert np.array_equal(ur[2:-2, 2:-2], uc) and np.array_equal(gdr[2:-2, 2:-2], gdc)
+    assert np.array_equal(vr[2:-3, 2:-2], vc)
+    # periodic lon halos (parallel_fill_halo), zero lat halos
+    assert np.array_equal(gdr[2:-2, :2], gdc[:, -2:]) and np.array_equal(gdr[2:-2, -2:], gdc[:, :2])
+    assert not gdr[:2].any() and not gdr[-2:].any()
+    # u = U = 0 on the pole rows, gd constant along them
+    assert not uc[0].any() and not uc[-1].any()
+    assert np.ptp(gdc[0]) == 0.0 and np.ptp(gdc[-1]) == 0.0
+    assert rel(gdc, o.state()[2]) < 1e-13
+    # non-zero u on a pole row is rejected loudly
+    ub = u.copy()
+    ub[0, 3] = 1.0
+    with pytest.raises(gmd.GmdError):
+        d.set_state(ub, v, gd, ghs)
+    # reference-layout upload gives the same state as the compact one
+    d2 = gmd.Dycore(gmd.Config(**kw))
+    pad = lambda a, rows: np.pad(a, ((2, 2 + (25 - rows)), (2, 2)))
+    d2.set_state(pad(u, 25), pad(v, 24), pad(gd, 25), pad(ghs, 25), layout=gmd.LAYOUT_REFERENCE)
+    d3 = gmd.Dycore(gmd.Config(**kw))
+    d3.set_state(u, v, gd, ghs)
+    for a, b in zip(d2.iap_state(), d3.iap_state()):
+        assert np.array_equal(a, b)
+
+
+GOLDEN = ["rh_36x19_csp2", "rh_72x37_nosplit", "mz_60x31_upwind", "jz_72x37_diffusion", "sg_48x25_isp", "mz_48x25_weno"]
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+@pytest.mark.parametrize("graph", [False, True])
+def test_golden_cases(golden_dir, name, graph):
+    """committed oracle fixtures (tests/golden/make_golden.py): state after nsteps and the diag series"""
+    g = np.load(golden_dir / f"case_{name}.npz", allow_pickle=True)
+    kw = ast.literal_eval(str(g["config"]))
+    d = gmd.Dycore(gmd.Config(**kw))
+    d.set_graph_mode(graph)
+    d.set_state(g["u0"], g["v0"], g["gd0"], g["ghs"])
+    d.run_init()
+    n = int(g["nsteps"])
+    series = [d.diag()]
+    for _ in range(n):
+        d.step(1)
+        series.append(d.diag())
+    series = np.array(series)
+    assert np.abs(series[:, 0] / g["mass"] - 1).max() <= 1e-13
+    assert np.abs(series[:, 1] / g["energy"] - 1).max() <= 1e-13
+    assert np.abs(series[1:, 2] - g["beta"][1:]).max() <= 1e-11
+    u, v, gd = d.state()
+    # after 3-4 steps the filter's s1/s2 rescale has amplified rounding differences
+    tol = {"jz_72x37_diffusion": 5e-9, "sg_48x25_isp": 1e-10}.get(name, 1e-11)
+    assert rel(gd, g["gd1"]) <= tol, rel(gd, g["gd1"])
+    assert rel(u, g["u1"]) <= tol * 10, rel(u, g["u1"])
+    if np.abs(g["v1"]).max() > 1e-6:
+        assert rel(v, g["v1"]) <= tol * 100, rel(v, g["v1"])
+    # the batched series agrees with the per-step reads
+    m, e, b = d.diag_series(n + 1)
+    assert np.array_equal(m, series[:, 0]) and np.array_equal(e, series[:, 1])
+
+
+def noise_floor(kw, test_case, nsteps):
+    """rel-L2 between two oracle runs whose initial gd differs by 1e-16 relative white noise"""
+    o1 = Oracle(OracleConfig(**kw))
+    o1.set_initial_condition(test_case)
+    u, v, gd = o1.state()
+    ghs = o1.ghs()
+    o1.run_init()
+    o2 = Oracle(OracleConfig(**kw))
+    rng = np.random.default_rng(0)
+    o2.set_state(u, v, gd * (1 + 1e-16 * rng.standard_normal(gd.shape)), ghs)
+    o2.run_init()
+    o1.step(nsteps)
+    o2.step(nsteps)
+    return [rel(a, b) for a, b in zip(o2.state(), o1.state())], o1
+
+
+def test_rossby_haurwitz_one_day_parity_C1():
+    """BASELINE config C1: RH wave 360x181, dt=240, csp2 x6, centred, filter 4 on 5 rows, one model day.
+    north_star: prognostic fields within 1e-12 rel-L2, mass/energy series within 1e-13 relative."""
+    kw = dict(num_lon=360, num_lat=181, time_step_size=240.0, subcycles=6, split_scheme="csp2",
+              zonal_tend_filter_cutoff_wavenumber=[4] * 5)
+    nsteps = 360
+    floor, o = noise_floor(kw, "rossby_haurwitz_wave", nsteps)
+    d = gmd.Dycore(gmd.Config(**kw))
+    o0 = Oracle(OracleConfig(**kw))
+    o0.set_initial_condition("rossby_haurwitz_wave")
+    u, v, gd = o0.state()
+    d.set_state(u, v, gd, o0.ghs())
+    d.run_init()
+    m0, e0, _ = d.diag()
+    d.step(nsteps)
+    errs = [rel(a, b) for a, b in zip(d.state(), o.state())]
+    print("C1 one-day rel-L2 (u,v,gd):", errs, "noise floor:", floor)
+    for err, fl in zip(errs, floor):
+        assert err <= max(1e-12, 20 * fl)
+    m, e, b = d.diag_series(nsteps + 1)
+    assert np.abs(m / m0 - 1).max() <= 1e-13 and np.abs(e / e0 - 1).max() <= 1e-13
+    mo, eo, _ = o.diag()
+    assert abs(m[-1] / mo - 1) <= 1e-13 and abs(e[-1] / eo - 1) <= 1e-13
+    assert np.all(np.abs(b[1:] - 1) < 1e-3)
+
+
+def test_mountain_zonal_flow_C2():
+    """BASELINE config C2 (as shipped, run/namelist.mz_test): 180x90, dt=720, upwind 0.1, csp2 x8, filter 4,4,4"""
+    kw = dict(num_lon=180, num_lat=90, time_step_size=720.0, subcycles=8, split_scheme="csp2", uv_adv_scheme="upwind",
+              uv_adv_upwind_lat_beta=0.1, zonal_tend_filter_cutoff_wavenumber=[4, 4, 4])
+    nsteps = 60  # half a model day
+    floor, o = noise_floor(kw, "mountain_zonal_flow", nsteps)
+    d = gmd.Dycore(gmd.Config(**kw))
+    o0 = Oracle(OracleConfig(**kw))
+    o0.set_initial_condition("mountain_zonal_flow")
+    u, v, gd = o0.state()
+    d.set_state(u, v, gd, o0.ghs())
+    d.run_init()
+    d.step(nsteps)
+    errs = [rel(a, b) for a, b in zip(d.state(), o.state())]
+    print("C2 rel-L2 (u,v,gd):", errs, "noise floor:", floor)
+    for err, fl in zip(errs, floor):
+        assert err <= max(1e-12, 20 * fl)
+    mo, eo, _ = o.diag()
+    m, e, _ = d.diag()
+    assert abs(m / mo - 1) <= 1e-13 and abs(e / eo - 1) <= 1e-13
+
+
+def test_conservation_and_launch_accounting_at_quarter_degree():
+    """C3-sized grid (1440x721): size-independent properties -- mass to round-off, energy to round-off with
+    qcon_modified + centred differences, u(pole) = 0, finite fields; graph replay == direct launches bitwise."""
+    kw = dict(num_lon=1440, num_lat=721, time_step_size=30.0, subcycles=6, split_scheme="csp2",
+              zonal_tend_filter_cutoff_wavenumber=[4] * 20)
+    o = Oracle(OracleConfig(**kw))
+    o.set_initial_condition("rossby_haurwitz_wave")
+    u, v, gd = o.state()
+    res = []
+    for graph in (False, True):
+        d = gmd.Dycore(gmd.Config(**kw))
+        d.set_graph_mode(graph)
+        d.set_state(u, v, gd)
+        d.run_init()
+        l0 = d.kernel_launches()
+        d.step(6)
+        assert d.kernel_launches() > l0
+        m, e, b = d.diag_series(7)
+        assert np.abs(m / m[0] - 1).max() < 5e-15 and np.abs(e / e[0] - 1).max() < 5e-15
+        res.append(d.state() + (m, e))
+        assert not res[-1][0][0].any() and np.isfinite(res[-1][2]).all()
+    for a, b in zip(*res):
+        assert np.array_equal(a, b)
+    # and against the oracle after those 6 steps
+    o.run_init()
+    o.step(6)
+    for a, b in zip(res[0][:3], o.state()):
+        assert rel(a, b) < 1e-11
+
+
+def test_vor_div_and_diag():
+    kw = dict(num_lon=72, num_lat=37, time_step_size=600.0, zonal_tend_filter_cutoff_wavenumber=[4, 4])
+    o, d = make_pair("fast", state=generic_state(72, 37, seed=8), **kw)
+    vo, do = o.vor_div()
+    vd, dd = d.vor_div()
+    assert rel(vd, vo) < 1e-13 and rel(dd, do) < 1e-13
+    mo, eo, _ = o.diag()
+    m, e, _ = d.diag()
+    assert abs(m / mo - 1) < 1e-14 and abs(e / eo - 1) < 1e-14
+
+
+def test_nan_is_reported():
+    kw = dict(num_lon=36, num_lat=19, time_step_size=1.0e6, split_scheme="none", use_zonal_tend_filter=False)
+    o = Oracle(OracleConfig(**kw))
+    o.set_initial_condition("rossby_haurwitz_wave")
+    u, v, gd = o.state()
+    d = gmd.Dycore(gmd.Config(**kw))
+    d.set_state(u, v, gd)
+    d.run_init()
+    with pytest.raises(gmd.GmdError) as ei:
+        d.step(20)
+    assert ei.value.code == gmd.ERR_NAN
+
+
+def test_error_behaviour():
+    with pytest.raises(gmd.GmdError):
+        gmd.Dycore(gmd.Config(num_lon=2, num_lat=3, time_step_size=1.0))
+    d = gmd.Dycore(gmd.Config(num_lon=36, num_lat=19, time_step_size=600.0))
+    with pytest.raises(gmd.GmdError):
+        d.step(1)  # before set_state / run_init
+    with pytest.raises(gmd.GmdError):
+        d.run_init()
