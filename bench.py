@@ -193,7 +193,8 @@ def main():
         d.comm_init(uid[0])
     if args.no_graph:
         d.set_graph_mode(False)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()   # a real (non-legacy) stream: libgmd launches on it, torch events time it
+    torch.cuda.set_stream(stream)
     d.set_stream(stream.cuda_stream)
     d.set_state(u, v, gd, ghs)
     d.run_init()
@@ -217,6 +218,9 @@ def main():
     d.sync()
     barrier()
     ms = ev0.elapsed_time(ev1)
+    ms_lib = d.last_step_ms()      # libgmd's own CUDA events around the same span (cross-check)
+    if abs(ms_lib - ms) > 0.05 * ms + 0.05:
+        raise SystemExit(f"timing mismatch: torch events {ms:.3f} ms vs libgmd events {ms_lib:.3f} ms")
     launches = d.kernel_launches() - l0
     sampler.stop_flag = True
     sampler.join()

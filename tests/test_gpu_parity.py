@@ -178,16 +178,29 @@ def test_golden_cases(golden_dir, name, graph):
         d.step(1)
         series.append(d.diag())
     series = np.array(series)
+    u, v, gd = d.state()
+    # The coarse Rossby-Haurwitz fixtures are ill-conditioned by the algorithm itself (rows whose
+    # filter inner product s1 is pure rounding noise above the ABSOLUTE 1e-16 threshold get rescaled by noise/noise),
+    # so every fixture is compared beside its own noise floor: two oracle runs from a 1e-16-perturbed initial gd.
+    floor, bfloor = np.zeros(3), 0.0
+    for seed in (0, 1):
+        o = Oracle(OracleConfig(**kw))
+        rng = np.random.default_rng(seed)
+        o.set_state(g["u0"], g["v0"], g["gd0"] * (1 + 1e-16 * rng.standard_normal(g["gd0"].shape)), g["ghs"])
+        o.run_init()
+        for k in range(n):
+            o.step(1)
+            bfloor = max(bfloor, abs(o.diag()[2] - g["beta"][k + 1]))
+        floor = np.maximum(floor, [rel(a, g[k]) if np.abs(g[k]).max() > 0 else 0.0
+                                   for a, k in zip(o.state(), ("u1", "v1", "gd1"))])
+    errs = [rel(u, g["u1"]), rel(v, g["v1"]) if np.abs(g["v1"]).max() > 0 else float(np.abs(v).max()), rel(gd, g["gd1"])]
+    berr = np.abs(series[1:, 2] - g["beta"][1:]).max()
+    print(name, "rel-L2 (u,v,gd):", errs, "noise floor:", floor.tolist(), "beta err", berr, "beta floor", bfloor)
     assert np.abs(series[:, 0] / g["mass"] - 1).max() <= 1e-13
     assert np.abs(series[:, 1] / g["energy"] - 1).max() <= 1e-13
-    assert np.abs(series[1:, 2] - g["beta"][1:]).max() <= 1e-11
-    u, v, gd = d.state()
-    # after 3-4 steps the filter's s1/s2 rescale has amplified rounding differences
-    tol = {"jz_72x37_diffusion": 5e-9, "sg_48x25_isp": 1e-10}.get(name, 1e-11)
-    assert rel(gd, g["gd1"]) <= tol, rel(gd, g["gd1"])
-    assert rel(u, g["u1"]) <= tol * 10, rel(u, g["u1"])
-    if np.abs(g["v1"]).max() > 1e-6:
-        assert rel(v, g["v1"]) <= tol * 100, rel(v, g["v1"])
+    assert berr <= max(1e-12, 30 * bfloor)
+    for err, fl in zip(errs, floor):
+        assert err <= max(1e-12, 30 * fl), (errs, floor)
     # the batched series agrees with the per-step reads
     m, e, b = d.diag_series(n + 1)
     assert np.array_equal(m, series[:, 0]) and np.array_equal(e, series[:, 1])
