@@ -522,7 +522,7 @@ static int stage(gmd_model *m, int pass, int mode, const State &E, const State *
     p.rescale = 1;
     p.radius = m->mesh.radius;
     p.dlat = m->mesh.dlat;
-    const size_t sh = (size_t)m->geo.nlon * sizeof(double);
+    const size_t sh = 2 * (size_t)m->geo.nlon * sizeof(double);
     switch (mode) {
       case MODE_S1: if (!m->dry) k_polar<MODE_S1><<<m->n_items[li], PT, sh, m->stream>>>(p); break;
       case MODE_S2: if (!m->dry) k_polar<MODE_S2><<<m->n_items[li], PT, sh, m->stream>>>(p); break;
@@ -693,7 +693,7 @@ static int polar_filter_only(gmd_model *m, double *ud, double *vd, double *gdd) 
   p.TU = ud; p.TV = vd; p.Tgd = gdd;
   p.rescale = 0;
   p.partials = m->d_partials;
-  const size_t sh = (size_t)m->geo.nlon * sizeof(double);
+  const size_t sh = 2 * (size_t)m->geo.nlon * sizeof(double);
   if (!m->dry) k_polar<MODE_EVAL><<<m->n_items[2], PT, sh, m->stream>>>(p);
   return post_launch(m);
 }
@@ -718,7 +718,7 @@ static int diffusion(gmd_model *m, double dt, const State &in, State *out) {
     if (!m->dry) k_laplace<<<m->ew_blocks, 256, 0, m->stream>>>(m->geo, m->tab, qu, qv, qg, ou, ov, og);
     if ((r = post_launch(m))) return r;
     if (south || north) {
-      if (!m->dry) k_lap_pole<<<2, PT, 0, m->stream>>>(m->geo, m->tab, qg, og, south ? 1 : 0, north ? 1 : 0);
+      if (!m->dry) k_lap_pole<<<2, PT_EW, 0, m->stream>>>(m->geo, m->tab, qg, og, south ? 1 : 0, north ? 1 : 0);
       if ((r = post_launch(m))) return r;
     }
     if (order != norder) {
@@ -949,7 +949,7 @@ int gmd_create(const gmd_config *cfg, gmd_model **out) {
   CKD(cudaFuncSetAttribute(k_polar<MODE_S2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CKD(cudaFuncSetAttribute(k_polar<MODE_S3A>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CKD(cudaFuncSetAttribute(k_polar<MODE_EVAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  if ((size_t)nlon * sizeof(double) > 200 * 1024) { fail(GMD_ERR_ARG, "num_lon too large for the polar-row kernel"); gmd_destroy(m); return GMD_ERR_ARG; }
+  if (2 * (size_t)nlon * sizeof(double) > 200 * 1024) { fail(GMD_ERR_ARG, "num_lon too large for the polar-row kernel"); gmd_destroy(m); return GMD_ERR_ARG; }
   // persistent buffers
   if ((r = new_state(m, &m->cur, nullptr)) || (r = acquire(m, KIND_G, &m->ghs)) || (r = new_tend(m, &m->tendOld)) ||
       (r = new_tend(m, &m->tendNew))) {
@@ -1327,7 +1327,7 @@ int gmd_filter_row(gmd_model *m, int half, int row0, double *x) {
     release(m, buf);
     return fail(GMD_ERR_STATE, "internal: basis too small");
   }
-  k_polar<MODE_EVAL><<<1, PT, (size_t)nlon * sizeof(double), m->stream>>>(p);
+  k_polar<MODE_EVAL><<<1, PT, 2 * (size_t)nlon * sizeof(double), m->stream>>>(p);
   if ((r = post_launch(m))) return r;
   CK(cudaMemcpyAsync(x, buf, (size_t)nlon * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
   CK(cudaStreamSynchronize(m->stream));

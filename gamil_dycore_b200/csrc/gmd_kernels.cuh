@@ -394,7 +394,9 @@ __global__ void __launch_bounds__(BX) k_stage(const StageArgs a) {
 // (2c+2 dot products with a host-precomputed basis + reconstruction): same result to rounding, no
 // butterflies, and the row never leaves shared memory.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int PT = 256;
+constexpr int PT = 1024;      // threads per polar-row CTA
+constexpr int PT_EW = 256;   // threads of the small pole-cap kernels
+constexpr int PB = 4;        // row elements per thread per batch (independent loads in flight)
 enum { IT_DU = 0, IT_DV = 1, IT_DGD = 2, IT_POLE_S = 3, IT_POLE_N = 4 };
 
 struct PolarItem {
@@ -411,99 +413,152 @@ struct PolarArgs {
   double *NU, *NV, *Ngd;
   double *TU, *TV, *Tgd;
   const double *PU, *PV, *Pgd;
-  double dt, pole_scale;  // pole_scale = 2 / nlon / radius / dlat applied as in :578,591
+  double dt;
   double *partials;       // [nitems][2]
   int rescale;            // 1: tendency filter with inner-product rescale; 0: plain filter (diffusion)
-  int radius_dlat_div;    // unused
   double radius, dlat;
 };
 
-// project x[0..n) (shared) onto the kept modes; coef/red are shared scratch; result overwrites x
+// Project x[0..n) (shared) onto the kept modes, result overwrites x.  The 2c+2 dot products are spread over
+// the CTA's warps (one (coefficient, segment) item per warp, fixed summation order => deterministic); all
+// basis loads are read-only-path loads that the compiler may hoist and batch.
 __device__ inline void project_row(double *x, int n, int cutoff, const double *__restrict__ basis, double *coef,
-                                   double *red) {
-  int K = cutoff + 1;  // highest (cosine-only) wavenumber kept
-  if (cutoff < 0) {    // all-zero mask
+                                   double *part) {
+  const int K = cutoff + 1;  // highest (cosine-only) wavenumber kept
+  if (cutoff < 0) {          // all-zero mask
     for (int i = threadIdx.x; i < n; i += PT) x[i] = 0.0;
     __syncthreads();
     return;
   }
-  if (2 * K >= n) return;  // mask keeps every entry: the FFT round trip is the identity
-  const int ncoef = 2 * K;  // entries 0 .. 2c+1
-  const bool nyq = ((n & 1) == 0) && (K == n / 2);
-  for (int m0 = 0; m0 < ncoef; m0 += 4) {
-    double acc[4] = {0.0, 0.0, 0.0, 0.0};
-    for (int i = threadIdx.x; i < n; i += PT) {
-      const double xi = x[i];
-#pragma unroll
-      for (int q = 0; q < 4; q++)
-        if (m0 + q < ncoef) acc[q] += xi * basis[(size_t)(m0 + q) * n + i];
+  if (2 * K >= n) return;    // mask keeps every entry: the FFT round trip is the identity
+  const int ncoef = 2 * K;   // halfcomplex entries 0 .. 2c+1
+  const int nwarp = PT / 32, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nseg = (ncoef >= nwarp) ? 1 : nwarp / ncoef;
+  const int seglen = (n + nseg - 1) / nseg;
+  for (int item = warp; item < ncoef * nseg; item += nwarp) {
+    const int m = item / nseg, q = item - m * nseg;
+    const int lo = q * seglen, hi = min(n, lo + seglen);
+    const double *__restrict__ b = basis + (size_t)m * n;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    for (int i = lo + lane; i < hi; i += 128) {
+      a0 += x[i] * __ldg(b + i);
+      if (i + 32 < hi) a1 += x[i + 32] * __ldg(b + i + 32);
+      if (i + 64 < hi) a2 += x[i + 64] * __ldg(b + i + 64);
+      if (i + 96 < hi) a3 += x[i + 96] * __ldg(b + i + 96);
     }
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-      const double r = block_sum<PT>(acc[q], red);
-      if (threadIdx.x == 0 && m0 + q < ncoef) {
-        const int m = m0 + q;
-        double sc = (m == 0) ? 1.0 / n : 2.0 / n;
-        if (nyq && m == ncoef - 1) sc = 1.0 / n;
-        coef[m] = r * sc;
-      }
-    }
+    const double r = warp_sum((a0 + a1) + (a2 + a3));
+    if (lane == 0) part[item] = r;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < n; i += PT) {
-    double y = 0.0;
-    for (int m = 0; m < ncoef; m++) y += coef[m] * basis[(size_t)m * n + i];
-    x[i] = y;
+  if ((int)threadIdx.x < ncoef) {
+    const int m = threadIdx.x;
+    double r = 0.0;
+    for (int q = 0; q < nseg; q++) r += part[m * nseg + q];
+    const double sc = (m == 0) ? 1.0 / n : 2.0 / n;  // rfftf1.f:87-107 normalisation
+    coef[m] = r * sc;
+  }
+  __syncthreads();
+  for (int i0 = threadIdx.x; i0 < n; i0 += PT * PB) {
+    double y[PB];
+#pragma unroll
+    for (int q = 0; q < PB; q++) y[q] = 0.0;
+    for (int m = 0; m < ncoef; m++) {
+      const double cm = coef[m];
+      const double *__restrict__ b = basis + (size_t)m * n;
+#pragma unroll
+      for (int q = 0; q < PB; q++) {
+        const int i = i0 + q * PT;
+        if (i < n) y[q] += cm * __ldg(b + i);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < PB; q++) {
+      const int i = i0 + q * PT;
+      if (i < n) x[i] = y[q];
+    }
   }
   __syncthreads();
 }
 
 template <int MODE>
 __global__ void __launch_bounds__(PT) k_polar(const PolarArgs a) {
-  extern __shared__ double psm[];
+  extern __shared__ double psm[];  // x[n], w[n]
   __shared__ double red[32];
   __shared__ double coef[512];
+  __shared__ double part[512];
   __shared__ double bc[2];
   const PolarItem it = a.items[blockIdx.x];
   const int n = a.g.nlon, r0 = a.g.r0;
-  double *x = psm;
+  double *x = psm, *w = psm + n;
   const int j = it.row;
   const ptrdiff_t off = (ptrdiff_t)(j - r0) * (ptrdiff_t)n;
   double ip1 = 0.0, ip2 = 0.0;
 
   if (it.kind == IT_POLE_S || it.kind == IT_POLE_N) {
     // src/dycore_mod.F90:572-596: zonal sum of the single adjacent flux, broadcast along the pole row
+    const double *__restrict__ g0 = a.Egd + off;
+    const double *__restrict__ g1 = (it.kind == IT_POLE_S) ? a.Egd + off + n : a.Egd + off - n;
+    const double *__restrict__ vv = (it.kind == IT_POLE_S) ? a.EV + off : a.EV + off - n;
     double acc = 0.0;
-    if (it.kind == IT_POLE_S) {
-      for (int i = threadIdx.x; i < n; i += PT)
-        acc = acc + (sqrt(a.Egd[off + i]) + sqrt(a.Egd[off + n + i])) * a.EV[off + i];
-    } else {
-      for (int i = threadIdx.x; i < n; i += PT)
-        acc = acc - (sqrt(a.Egd[off + i]) + sqrt(a.Egd[off - n + i])) * a.EV[off - n + i];
+    for (int i = threadIdx.x; i < n; i += PT) {
+      const double f = (sqrt(__ldg(g0 + i)) + sqrt(__ldg(g1 + i))) * __ldg(vv + i);
+      acc = (it.kind == IT_POLE_S) ? acc + f : acc - f;
     }
     const double r = block_sum<PT>(acc, red);
     if (threadIdx.x == 0) bc[0] = -(r * 2.0 / n / a.radius / a.dlat);  // dgd = -mass_div_lon(=0) - mass_div_lat
     __syncthreads();
     const double dG = bc[0];
     const double cw = a.t.cosf[j];
-    for (int i = threadIdx.x; i < n; i += PT) {
-      if (MODE == MODE_S1 || MODE == MODE_S2) a.Ngd[off + i] = a.Ogd[off + i] + a.dt * dG;
-      if (MODE != MODE_S1) a.Tgd[off + i] = dG;
-      if (MODE == MODE_S3A) {
-        ip1 = ip1 + dG * a.Pgd[off + i] * cw;
-        ip2 = ip2 + dG * dG * cw;
+    for (int i0 = threadIdx.x; i0 < n; i0 += PT * PB) {
+      double o[PB], pr[PB];
+#pragma unroll
+      for (int q = 0; q < PB; q++) {
+        const int i = i0 + q * PT;
+        o[q] = pr[q] = 0.0;
+        if (i < n) {
+          if (MODE == MODE_S1 || MODE == MODE_S2) o[q] = __ldg(a.Ogd + off + i);
+          if (MODE == MODE_S3A) pr[q] = __ldg(a.Pgd + off + i);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < PB; q++) {
+        const int i = i0 + q * PT;
+        if (i < n) {
+          if (MODE == MODE_S1 || MODE == MODE_S2) a.Ngd[off + i] = o[q] + a.dt * dG;
+          if (MODE != MODE_S1) a.Tgd[off + i] = dG;
+          if (MODE == MODE_S3A) {
+            ip1 = ip1 + dG * pr[q] * cw;
+            ip2 = ip2 + dG * dG * cw;
+          }
+        }
       }
     }
   } else {
     double *T = (it.kind == IT_DU) ? a.TU : (it.kind == IT_DV) ? a.TV : a.Tgd;
-    const double *W = (it.kind == IT_DU) ? a.EU : (it.kind == IT_DV) ? a.EV : a.Egd;
+    const double *__restrict__ W = (it.kind == IT_DU) ? a.EU : (it.kind == IT_DV) ? a.EV : a.Egd;
     double s1p = 0.0;
-    for (int i = threadIdx.x; i < n; i += PT) {
-      const double xi = T[off + i];
-      x[i] = xi;
-      if (a.rescale) {
-        const double w = (it.kind == IT_DGD) ? (W[off + i] + a.ghs[off + i]) : W[off + i];
-        s1p = s1p + xi * w;
+    for (int i0 = threadIdx.x; i0 < n; i0 += PT * PB) {
+      double xv[PB], wv[PB];
+#pragma unroll
+      for (int q = 0; q < PB; q++) {
+        const int i = i0 + q * PT;
+        xv[q] = wv[q] = 0.0;
+        if (i < n) {
+          xv[q] = T[off + i];
+          if (a.rescale) {
+            wv[q] = __ldg(W + off + i);
+            if (it.kind == IT_DGD) wv[q] = wv[q] + __ldg(a.ghs + off + i);
+          }
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < PB; q++) {
+        const int i = i0 + q * PT;
+        if (i < n) {
+          x[i] = xv[q];
+          w[i] = wv[q];
+          s1p = s1p + xv[q] * wv[q];
+        }
       }
     }
     bool do_filter = true;
@@ -517,32 +572,47 @@ __global__ void __launch_bounds__(PT) k_polar(const PolarArgs a) {
     } else {
       __syncthreads();
     }
+    double s2 = 1.0;
     if (do_filter) {
-      project_row(x, n, it.cutoff, a.basis, coef, red);
+      project_row(x, n, it.cutoff, a.basis, coef, part);
       if (a.rescale) {
         double s2p = 0.0;
-        for (int i = threadIdx.x; i < n; i += PT) {
-          const double w = (it.kind == IT_DGD) ? (W[off + i] + a.ghs[off + i]) : W[off + i];
-          s2p = s2p + x[i] * w;
-        }
+        for (int i = threadIdx.x; i < n; i += PT) s2p = s2p + x[i] * w[i];
         const double r = block_sum<PT>(s2p, red);
         if (threadIdx.x == 0) bc[1] = r;
         __syncthreads();
-        const double s2 = bc[1];
-        for (int i = threadIdx.x; i < n; i += PT) x[i] = x[i] * s1 / s2;  // :218
+        s2 = bc[1];
       }
     }
-    const double *O = (it.kind == IT_DU) ? a.OU : (it.kind == IT_DV) ? a.OV : a.Ogd;
+    const double *__restrict__ O = (it.kind == IT_DU) ? a.OU : (it.kind == IT_DV) ? a.OV : a.Ogd;
     double *N = (it.kind == IT_DU) ? a.NU : (it.kind == IT_DV) ? a.NV : a.Ngd;
-    const double *P = (it.kind == IT_DU) ? a.PU : (it.kind == IT_DV) ? a.PV : a.Pgd;
+    const double *__restrict__ P = (it.kind == IT_DU) ? a.PU : (it.kind == IT_DV) ? a.PV : a.Pgd;
     const double cw = (it.kind == IT_DV) ? a.t.cosh[j] : a.t.cosf[j];
-    for (int i = threadIdx.x; i < n; i += PT) {
-      const double d = x[i];
-      if (MODE == MODE_S1 || MODE == MODE_S2) N[off + i] = O[off + i] + a.dt * d;
-      if (MODE != MODE_S1) T[off + i] = d;
-      if (MODE == MODE_S3A) {
-        ip1 = ip1 + d * P[off + i] * cw;
-        ip2 = ip2 + d * d * cw;
+    const bool scale = do_filter && a.rescale;
+    for (int i0 = threadIdx.x; i0 < n; i0 += PT * PB) {
+      double o[PB], pr[PB];
+#pragma unroll
+      for (int q = 0; q < PB; q++) {
+        const int i = i0 + q * PT;
+        o[q] = pr[q] = 0.0;
+        if (i < n) {
+          if (MODE == MODE_S1 || MODE == MODE_S2) o[q] = __ldg(O + off + i);
+          if (MODE == MODE_S3A) pr[q] = __ldg(P + off + i);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < PB; q++) {
+        const int i = i0 + q * PT;
+        if (i < n) {
+          double d = x[i];
+          if (scale) d = d * s1 / s2;  // src/dycore_mod.F90:218
+          if (MODE == MODE_S1 || MODE == MODE_S2) N[off + i] = o[q] + a.dt * d;
+          if (MODE != MODE_S1) T[off + i] = d;
+          if (MODE == MODE_S3A) {
+            ip1 = ip1 + d * pr[q] * cw;
+            ip2 = ip2 + d * d * cw;
+          }
+        }
       }
     }
   }
@@ -795,7 +865,7 @@ __global__ void __launch_bounds__(256) k_laplace(Geo g, Tab t, const double *u, 
 }
 
 // gd pole caps of the Laplacian (src/diffusion_mod.F90:116-133); blockIdx.x: 0 south, 1 north
-__global__ void __launch_bounds__(PT) k_lap_pole(Geo g, Tab t, const double *gd, double *gdd, int do_south,
+__global__ void __launch_bounds__(PT_EW) k_lap_pole(Geo g, Tab t, const double *gd, double *gdd, int do_south,
                                                  int do_north) {
   __shared__ double red[32];
   __shared__ double bc;
@@ -806,18 +876,18 @@ __global__ void __launch_bounds__(PT) k_lap_pole(Geo g, Tab t, const double *gd,
   const ptrdiff_t off = (ptrdiff_t)(j - g.r0) * n;
   double acc = 0.0;
   if (south) {
-    for (int i = threadIdx.x; i < n; i += PT) acc = acc + gd[off + n + i] - gd[off + i];
+    for (int i = threadIdx.x; i < n; i += PT_EW) acc = acc + gd[off + n + i] - gd[off + i];
   } else {
-    for (int i = threadIdx.x; i < n; i += PT) acc = acc - (gd[off + i] - gd[off - n + i]);
+    for (int i = threadIdx.x; i < n; i += PT_EW) acc = acc - (gd[off + i] - gd[off - n + i]);
   }
-  const double r = block_sum<PT>(acc, red);
+  const double r = block_sum<PT_EW>(acc, red);
   if (threadIdx.x == 0) {
     const double hc = south ? t.cosh[0] : t.cosh[nlat - 2];
     bc = r * hc / (t.fdlat[j] * t.fdlat[j]) * t.cosf[j] / n;
   }
   __syncthreads();
   const double vv = bc;
-  for (int i = threadIdx.x; i < n; i += PT) gdd[off + i] = vv;
+  for (int i = threadIdx.x; i < n; i += PT_EW) gdd[off + i] = vv;
 }
 
 // q += sign dt coef lap(q) for gd,u,v, then iap_transform (src/diffusion_mod.F90:195-215)
