@@ -872,6 +872,7 @@ int gmd_create(const gmd_config *cfg, gmd_model **out) {
   if (!cfg || !out) return fail(GMD_ERR_ARG, "null argument");
   *out = nullptr;
   if (cfg->num_lon < 4 || cfg->num_lat < 5) return fail(GMD_ERR_ARG, "grid too small: %d x %d", cfg->num_lon, cfg->num_lat);
+  if (cfg->num_lon % 2) return fail(GMD_ERR_ARG, "num_lon must be even (16-byte column pairs); got %d", cfg->num_lon);
   if (cfg->nranks < 1 || cfg->rank < 0 || cfg->rank >= cfg->nranks) return fail(GMD_ERR_ARG, "bad rank %d of %d", cfg->rank, cfg->nranks);
   if (cfg->uv_adv_scheme < 0 || cfg->uv_adv_scheme > 2)
     return fail(GMD_ERR_ARG, "Unknown uv_adv_scheme %d!", cfg->uv_adv_scheme);  // dycore_mod.F90:104-106
@@ -925,11 +926,21 @@ int gmd_create(const gmd_config *cfg, gmd_model **out) {
   // stage grid: ~6 CTAs per SM
   int nsm = 148;
   cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, m->dev);
-  m->nbx = (nlon + NOUT - 1) / NOUT;
-  int want = std::max(1, (nsm * 6) / m->nbx);
-  m->rows_per_cta = std::max(4, (m->nr + want - 1) / want);
-  if (const char *ev = getenv("GMD_ROWS_PER_CTA")) m->rows_per_cta = std::max(1, atoi(ev));
-  m->nchunks = (m->nr + m->rows_per_cta - 1) / m->rows_per_cta;
+  {
+    // one wave of CTAs: as many row chunks as the resident-CTA slots allow (no tail wave)
+    const int nstrips = (nlon + WOUT - 1) / WOUT;
+    m->nbx = (nstrips + SW - 1) / SW;
+    int per_sm = 0;
+    const int pass0 = (cfg->split_scheme == GMD_SPLIT_CSP2 || cfg->split_scheme == GMD_SPLIT_ISP) ? PASS_FAST : PASS_ALL;
+    CKD(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pick_stage(pass0, cfg->uv_adv_scheme, MODE_S2), BX, 0));
+    per_sm = std::max(per_sm, 1);
+    if (const char *ev = getenv("GMD_CTAS_PER_SM")) per_sm = std::max(1, atoi(ev));
+    const int slots = nsm * per_sm;
+    int want = std::max(1, slots / m->nbx);
+    m->rows_per_cta = std::max(8, (m->nr + want - 1) / want);
+    if (const char *ev = getenv("GMD_ROWS_PER_CTA")) m->rows_per_cta = std::max(1, atoi(ev));
+    m->nchunks = (m->nr + m->rows_per_cta - 1) / m->rows_per_cta;
+  }
   const size_t total = (size_t)m->nr * nlon;
   m->ew_blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)nsm * 8);
   m->n_partials = std::max(m->nbx * m->nchunks + m->n_items[0] + m->n_items[1], m->ew_blocks) + 16;

@@ -23,8 +23,6 @@
 namespace gmd {
 
 constexpr int GHOST = 2;      // ghost rows on each side of a band
-constexpr int BX = 128;       // threads per CTA of the stage kernel = columns held on chip
-constexpr int NOUT = BX - 3;  // output columns per CTA (1 west + 2 east columns are halo)
 
 enum { PASS_ALL = 0, PASS_FAST = 1, PASS_SLOW = 2 };
 enum { ADV_CENTER = 0, ADV_UPWIND = 1, ADV_WENO = 2 };
@@ -91,298 +89,397 @@ __device__ __forceinline__ double block_sum(double v, double *red) {
 // ---------------------------------------------------------------------------------------------------------
 // Fused stage kernel: one operator evaluation (space_operators, src/dycore_mod.F90:184-365, with the seven
 // operators :367-598 fused) + update_state (:600-652) + inner_product (src/types_mod.F90:347-371) in ONE
-// sweep.  A CTA owns NOUT columns and marches south -> north over `rows_per_cta` rows, keeping rolling row
-// windows of sqrt(gd), u, v, U, V, gd+ghs in shared memory, so every field element is read from HBM once
-// (plus 3 halo columns per 128 and 3 prologue rows per chunk).
+// sweep over the minimal state.
+//
+// Mapping ("warp marching"): a warp owns a strip of 64 columns (2 per lane, 16-byte loads) of which the inner
+// WOUT = 60 are outputs (2 halo columns each side), and marches south -> north over `rows_per_cta` rows.
+// Each lane keeps the rolling row window of ITS two columns in registers -- sqrt(gd) rows j-1..j+2, u rows
+// j..j+1, v / U / V rows j-1..j+1, gd+ghs rows j..j+1 -- and gets the longitude neighbours with warp
+// shuffles.  There is no shared memory and no block barrier on the path: warps are fully independent, every
+// field element is read from HBM once (plus 4 halo columns per 64 and 3 prologue rows per chunk).
 // ---------------------------------------------------------------------------------------------------------
-#define S_(j, c) sS[(((j)&7) * BX) + (c)]
-#define U_(j, c) sU[(((j)&3) * BX) + (c)]
-#define V_(j, c) sV[(((j)&3) * BX) + (c)]
-#define u_(j, c) su[(((j)&3) * BX) + (c)]
-#define v_(j, c) sv[(((j)&3) * BX) + (c)]
+struct D2 {
+  double x, y;
+};
+__device__ __forceinline__ D2 ld2(const double *p) {
+  const double2 v = __ldg(reinterpret_cast<const double2 *>(p));
+  D2 r;
+  r.x = v.x;
+  r.y = v.y;
+  return r;
+}
+__device__ __forceinline__ void st2(double *p, double x, double y) {
+  *reinterpret_cast<double2 *>(p) = make_double2(x, y);
+}
+__device__ __forceinline__ double shfl_up1(double v) { return __shfl_up_sync(0xffffffffu, v, 1); }
+__device__ __forceinline__ double shfl_dn1(double v) { return __shfl_down_sync(0xffffffffu, v, 1); }
+
+// tendencies of ONE column at row j; all operands are scalars already in registers
+template <int PASS, int ADV>
+__device__ __forceinline__ void tend_col(
+    const Tab &t, const int j, const bool rowU, const bool rowV, const bool rowG, const double bl, const double bt,
+    const double hc0, const double hc1, const double hc2,
+    // row j
+    const double uw, const double uc, const double ue, const double Uw, const double Uc, const double Ue,
+    const double Vw, const double Vc, const double Ve, const double sw, const double sc, const double se,
+    const double vc, const double ve,
+    // row j-1
+    const double Us, const double Vs, const double Vse, const double vs, const double vse, const double ss,
+    // row j+1
+    const double Un, const double Unw, const double un, const double unw, const double Vn, const double vn,
+    const double sn,
+    // (gd+ghs)(i+1,j) - (gd+ghs)(i,j) and (gd+ghs)(i,j+1) - (gd+ghs)(i,j)
+    const double ghdx, const double ghdy,
+    // precomputed WENO advection terms
+    const double aulon, const double aulat, const double avlon, const double avlat,
+    double &dU, double &dV, double &dG) {
+  dU = 0.0;
+  dV = 0.0;
+  dG = 0.0;
+  // ===================== du, full rows 1..nlat-2 (src/dycore_mod.F90:207-210) ===========================
+  if (rowU) {
+    if (PASS != PASS_FAST) {
+      double alon, alat;
+      if (ADV == ADV_WENO) {
+        alon = aulon;
+        alat = aulat;
+      } else {
+        const double u1 = uc + uw, u2 = uc + ue;
+        const double v1 = (vs + vse) * hc0;
+        const double v2 = (vc + ve) * hc1;
+        if (ADV == ADV_CENTER) {
+          alon = t.q_fdlon[j] * (u2 * Ue - u1 * Uw);   // :378-384
+          alat = t.q_fdlat[j] * (v2 * Un - v1 * Us);   // :433-439
+        } else {
+          alon = t.q_fdlon[j] * (u2 * (Uc + Ue) - bl * fabs(u2) * (Ue - Uc) - u1 * (Uc + Uw) +
+                                 bl * fabs(u1) * (Uc - Uw) - (u2 - u1) * Uc);   // :395-404
+          alat = t.q_fdlat[j] * (v2 * (Uc + Un) - bt * fabs(v2) * (Un - Uc) - v1 * (Uc + Us) +
+                                 bt * fabs(v1) * (Uc - Us) - (v2 - v1) * Uc);   // :450-459
+        }
+      }
+      dU = -alon - alat;
+    }
+    if (PASS != PASS_SLOW) {
+      const double fv = 0.25 * (t.ff[j] + t.fc[j] * uc) * (t.cor1[j] * (Vs + Vse) + t.cor2[j] * (Vc + Ve));  // :485-493
 #if GMD_STRICT
-#define GD_(j, c) sG[(((j)&3) * BX) + (c)]
-#define GS_(j, c) sH[(((j)&3) * BX) + (c)]
-// gd(a) + ghs(a) - gd(b) - ghs(b), left to right (src/dycore_mod.F90:516-517,532-533)
-#define GHDIFF(ja, ca, jb, cb) (((GD_(ja, ca) + GS_(ja, ca)) - GD_(jb, cb)) - GS_(jb, cb))
-constexpr int STAGE_SMEM_ROWS = 8 + 4 * 6;
+      const double pgf = 0.5 * (sc + se) / t.fdlon[j] * ghdx;  // :514-519
 #else
-#define G_(j, c) sG[(((j)&3) * BX) + (c)]
-#define GHDIFF(ja, ca, jb, cb) (G_(ja, ca) - G_(jb, cb))
-constexpr int STAGE_SMEM_ROWS = 8 + 4 * 5;
+      const double pgf = 0.5 * (sc + se) * t.r_fdlon[j] * ghdx;
 #endif
-constexpr int STAGE_SMEM_BYTES = STAGE_SMEM_ROWS * BX * 8;
+      dU = (PASS == PASS_ALL) ? (dU + fv - pgf) : (fv - pgf);
+    }
+  }
+  // ===================== dv, half rows 0..nlat-2 ==========================================================
+  if (rowV) {
+    if (PASS != PASS_FAST) {
+      double alon, alat;
+      if (ADV == ADV_WENO) {
+        alon = avlon;
+        alat = avlat;
+      } else {
+        const double u1 = uw + unw;
+        const double u2 = uc + un;
+        const double vh = vc * hc1;
+        const double v1 = vh + vs * hc0;
+        const double v2 = vh + vn * hc2;
+        if (ADV == ADV_CENTER) {
+          alon = t.q_hdlon[j] * (u2 * Ve - u1 * Vw);   // :386-392
+          alat = t.q_hdlat[j] * (v2 * Vn - v1 * Vs);   // :441-447
+        } else {
+          alon = t.q_hdlon[j] * (u2 * (Vc + Ve) - bl * fabs(u2) * (Ve - Vc) - u1 * (Vc + Vw) +
+                                 bl * fabs(u1) * (Vc - Vw) - (u2 - u1) * Vc);   // :406-415
+          alat = t.q_hdlat[j] * (v2 * (Vc + Vn) - bt * fabs(v2) * (Vn - Vc) - v1 * (Vc + Vs) +
+                                 bt * fabs(v1) * (Vc - Vs) - (v2 - v1) * Vc);   // :461-470
+        }
+      }
+      dV = -alon - alat;
+    }
+    if (PASS != PASS_SLOW) {
+      const double f0 = t.ff[j], c0 = t.fc[j], f1 = t.ff[j + 1], c1 = t.fc[j + 1];
+      const double fu = 0.25 * ((f0 + c0 * uc) * Uc + (f0 + c0 * uw) * Uw + (f1 + c1 * un) * Un +
+                                (f1 + c1 * unw) * Unw);   // :495-503
+#if GMD_STRICT
+      const double pgf = 0.5 * (sc + sn) / t.hdlat[j] * hc1 * ghdy;  // :530-535
+#else
+      const double pgf = 0.5 * (sc + sn) * t.hc_hdlat[j] * ghdy;
+#endif
+      dV = (PASS == PASS_ALL) ? (dV - fu - pgf) : (-fu - pgf);
+    }
+  }
+  // ===================== dgd, full rows 1..nlat-2 (pole rows: k_polar) ====================================
+  if (rowG) {
+#if GMD_STRICT
+    const double mlon = ((sc + se) * Uc - (sc + sw) * Uw) * 0.5 / t.fdlon[j];                   // :546-552
+    const double mlat = ((sc + sn) * Vc * hc1 - (sc + ss) * Vs * hc0) * 0.5 / t.fdlat[j];       // :564-570
+#else
+    const double mlon = ((sc + se) * Uc - (sc + sw) * Uw) * t.h_fdlon[j];
+    const double mlat = ((sc + sn) * Vc * hc1 - (sc + ss) * Vs * hc0) * t.h_fdlat[j];
+#endif
+    dG = -mlon - mlat;
+  }
+}
+
+constexpr int WOUT = 60;  // output columns per warp strip (64 held)
+constexpr int SW = 4;     // warps per CTA
+constexpr int BX = SW * 32;
 
 template <int PASS, int ADV, int MODE>
 __global__ void __launch_bounds__(BX) k_stage(const StageArgs a) {
-  __shared__ double sm[STAGE_SMEM_ROWS * BX];
-  __shared__ double red[32];
-  double *sS = sm;
-  double *sU = sS + 8 * BX;
-  double *sV = sU + 4 * BX;
-  double *su = sV + 4 * BX;
-  double *sv = su + 4 * BX;
-  double *sG = sv + 4 * BX;
-#if GMD_STRICT
-  double *sH = sG + 4 * BX;
-#endif
+  __shared__ double red[2 * SW];
   const int nlon = a.g.nlon, nlat = a.g.nlat, r0 = a.g.r0;
-  const int c = threadIdx.x;
-  const int col0 = blockIdx.x * NOUT;
-  int i = col0 + c - 1;
-  i %= nlon;
-  if (i < 0) i += nlon;
-  const bool out_col = (c >= 1) && (c <= NOUT) && (col0 + c - 1 < nlon);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int strip = blockIdx.x * SW + warp;
+  const int nstrips = (nlon + WOUT - 1) / WOUT;
   const int ja = r0 + blockIdx.y * a.rows_per_cta;
   const int jb = min(ja + a.rows_per_cta, a.g.r1);
   const bool need_gh = (PASS != PASS_SLOW);
+  const bool upd = (MODE == MODE_S1 || MODE == MODE_S2);
   const Tab &t = a.t;
-
-  // address of column i on global row j of a band field
-#define AT(p, j) ((p)[(ptrdiff_t)((j)-r0) * (ptrdiff_t)nlon + (ptrdiff_t)i])
-
   double ip1 = 0.0, ip2 = 0.0;
 
-  // ---- prologue: rows ja-1, ja, ja+1 of sqrt(gd); rows ja-1, ja of U, V; gh row ja -----------------------
-  {
-    S_(ja - 1, c) = sqrt(AT(a.Egd, ja - 1));
-    S_(ja, c) = sqrt(AT(a.Egd, ja));
-    S_(ja + 1, c) = sqrt(AT(a.Egd, ja + 1));
-    U_(ja - 1, c) = AT(a.EU, ja - 1);
-    U_(ja, c) = AT(a.EU, ja);
-    V_(ja - 1, c) = AT(a.EV, ja - 1);
-    V_(ja, c) = AT(a.EV, ja);
-    if (need_gh) {
+  if (strip < nstrips) {
+    int c0 = strip * WOUT - 2 + 2 * lane;  // even; (c0, c0+1) never straddles the seam because nlon is even
+    c0 %= nlon;
+    if (c0 < 0) c0 += nlon;
+    const bool out = (lane >= 1) && (lane <= WOUT / 2) && (strip * WOUT + 2 * (lane - 1) < nlon);
+#define AT(p, j) ((p) + ((ptrdiff_t)((j)-r0) * (ptrdiff_t)nlon + (ptrdiff_t)c0))
+    const D2 zero2 = {0.0, 0.0};
+    // ---- prologue: rows ja-1, ja, ja+1 of sqrt(gd); rows ja-1, ja of U, V; gh row ja --------------------
+    D2 sm_, s0, sp, sq, u0, up, vm, v0, vp, Um, U0, Up, Vm, V0, Vp;
+    D2 g0 = zero2, gp = zero2;
 #if GMD_STRICT
-      GD_(ja, c) = AT(a.Egd, ja);
-      GS_(ja, c) = AT(a.ghs, ja);
-#else
-      G_(ja, c) = AT(a.Egd, ja) + AT(a.ghs, ja);
+    D2 h0 = zero2, hp = zero2;  // ghs rows j, j+1 (g0/gp then hold gd alone)
 #endif
-    }
-  }
-  __syncthreads();
-  {
-    // u(ja), v(ja-1), v(ja): update_state :636-645 (u = 2U/(s_i + s_i+1), v = 2V/(s_j + s_j+1))
-    const int cc = (c < BX - 1) ? c + 1 : c;
-    const bool uok = (ja >= 0 && ja < nlat);
-    u_(ja, c) = uok ? U_(ja, c) * 2.0 / (S_(ja, c) + S_(ja, cc)) : 0.0;
-    const bool v0 = (ja - 1 >= 0 && ja - 1 < nlat - 1), v1 = (ja >= 0 && ja < nlat - 1);
-    v_(ja - 1, c) = v0 ? V_(ja - 1, c) * 2.0 / (S_(ja - 1, c) + S_(ja, c)) : 0.0;
-    v_(ja, c) = v1 ? V_(ja, c) * 2.0 / (S_(ja, c) + S_(ja + 1, c)) : 0.0;
-  }
-  // first prefetch: gd(ja+2), U(ja+1), V(ja+1), ghs(ja+1)
-  double n_gd2 = AT(a.Egd, ja + 2);
-  double n_U = AT(a.EU, ja + 1);
-  double n_V = AT(a.EV, ja + 1);
-  double n_gd1 = 0.0, n_hs = 0.0;
-  if (need_gh) {
-    n_gd1 = AT(a.Egd, ja + 1);
-    n_hs = AT(a.ghs, ja + 1);
-  }
-
-  for (int j = ja; j < jb; j++) {
-    // ---- advance the window: s(j+2), U(j+1), V(j+1), gh(j+1), u(j+1), v(j+1) ----------------------------
     {
-      const double s2 = sqrt(n_gd2);
-      S_(j + 2, c) = s2;
-      U_(j + 1, c) = n_U;
-      V_(j + 1, c) = n_V;
+      const D2 a0 = ld2(AT(a.Egd, ja - 1)), a1 = ld2(AT(a.Egd, ja)), a2 = ld2(AT(a.Egd, ja + 1));
+      sm_.x = sqrt(a0.x); sm_.y = sqrt(a0.y);
+      s0.x = sqrt(a1.x); s0.y = sqrt(a1.y);
+      sp.x = sqrt(a2.x); sp.y = sqrt(a2.y);
+      Um = ld2(AT(a.EU, ja - 1));
+      U0 = ld2(AT(a.EU, ja));
+      Vm = ld2(AT(a.EV, ja - 1));
+      V0 = ld2(AT(a.EV, ja));
       if (need_gh) {
+        const D2 hs = ld2(AT(a.ghs, ja));
 #if GMD_STRICT
-        GD_(j + 1, c) = n_gd1;
-        GS_(j + 1, c) = n_hs;
+        g0 = a1;
+        h0 = hs;
 #else
-        G_(j + 1, c) = n_gd1 + n_hs;
+        g0.x = a1.x + hs.x;
+        g0.y = a1.y + hs.y;
 #endif
       }
-      const int cc = (c < BX - 1) ? c + 1 : c;
-      const double s1c = S_(j + 1, c), s1e = S_(j + 1, cc);  // written one iteration ago (or prologue)
-      const bool uok = (j + 1 < nlat);
-      const bool vok = (j + 1 < nlat - 1);
-      u_(j + 1, c) = uok ? n_U * 2.0 / (s1c + s1e) : 0.0;
-      v_(j + 1, c) = vok ? n_V * 2.0 / (s1c + s2) : 0.0;
+      // u(ja), v(ja-1), v(ja): update_state :636-645 (u = 2U/(s_i + s_i+1), v = 2V/(s_j + s_j+1))
+      const double s0e = shfl_dn1(s0.x);
+      u0.x = U0.x * 2.0 / (s0.x + s0.y);
+      u0.y = U0.y * 2.0 / (s0.y + s0e);
+      const bool vmok = (ja - 1 >= 0), v0ok = (ja < nlat - 1);
+      vm.x = vmok ? Vm.x * 2.0 / (sm_.x + s0.x) : 0.0;
+      vm.y = vmok ? Vm.y * 2.0 / (sm_.y + s0.y) : 0.0;
+      v0.x = v0ok ? V0.x * 2.0 / (s0.x + sp.x) : 0.0;
+      v0.y = v0ok ? V0.y * 2.0 / (s0.y + sp.y) : 0.0;
     }
-    // ---- prefetch the next row and the operands of this row's update ------------------------------------
-    if (j + 1 < jb) {
-      n_gd2 = AT(a.Egd, j + 3);
-      n_U = AT(a.EU, j + 2);
-      n_V = AT(a.EV, j + 2);
-      if (need_gh) {
-        n_gd1 = AT(a.Egd, j + 2);
-        n_hs = AT(a.ghs, j + 2);
-      }
+    // longitude-neighbour values carried from one row to the next
+    double uw_a = shfl_up1(u0.y);    // u(i-1, j)   for column a
+    double Uw_a = shfl_up1(U0.y);    // U(i-1, j)
+    double Vse_b = shfl_dn1(Vm.x);   // V(i+1, j-1) for column b
+    double vse_b = shfl_dn1(vm.x);   // v(i+1, j-1)
+    double se_b = shfl_dn1(s0.x);    // s(i+1, j)
+    // first prefetch: gd(ja+2), U(ja+1), V(ja+1), gd(ja+1), ghs(ja+1)
+    D2 n_gd2 = ld2(AT(a.Egd, ja + 2));
+    D2 n_U = ld2(AT(a.EU, ja + 1));
+    D2 n_V = ld2(AT(a.EV, ja + 1));
+    D2 n_gd1 = zero2, n_hs = zero2;
+    if (need_gh) {
+      n_gd1 = ld2(AT(a.Egd, ja + 1));
+      n_hs = ld2(AT(a.ghs, ja + 1));
     }
-    const unsigned fl = t.flags[j];
-    const bool rowU = (j >= 1 && j <= nlat - 2);
-    const bool rowV = (j <= nlat - 2);
-    const bool rowG = rowU && (PASS != PASS_SLOW);
-    double oU = 0.0, oV = 0.0, oG = 0.0, pU = 0.0, pV = 0.0, pG = 0.0;
-    if (out_col) {
-      if (MODE == MODE_S1 || MODE == MODE_S2) {
-        oU = AT(a.OU, j);
-        if (rowV) oV = AT(a.OV, j);
-        if (rowG) oG = AT(a.Ogd, j);
-      }
-      if (MODE == MODE_S3A) {
-        if (rowU) pU = AT(a.PU, j);
-        if (rowV) pV = AT(a.PV, j);
-        if (rowG) pG = AT(a.Pgd, j);
-      }
-    }
-    __syncthreads();
 
-    if (out_col) {
+    for (int j = ja; j < jb; j++) {
+      // ---- advance the window: s(j+2), U(j+1), V(j+1), gh(j+1), u(j+1), v(j+1) --------------------------
+      sq.x = sqrt(n_gd2.x);
+      sq.y = sqrt(n_gd2.y);
+      Up = n_U;
+      Vp = n_V;
+      if (need_gh) {
+#if GMD_STRICT
+        gp = n_gd1;
+        hp = n_hs;
+#else
+        gp.x = n_gd1.x + n_hs.x;
+        gp.y = n_gd1.y + n_hs.y;
+#endif
+      }
+      const double spe_b = shfl_dn1(sp.x);  // s(i+1, j+1) for column b
+      {
+        const bool uok = (j + 1 < nlat), vok = (j + 1 < nlat - 1);
+        up.x = uok ? Up.x * 2.0 / (sp.x + sp.y) : 0.0;
+        up.y = uok ? Up.y * 2.0 / (sp.y + spe_b) : 0.0;
+        vp.x = vok ? Vp.x * 2.0 / (sp.x + sq.x) : 0.0;
+        vp.y = vok ? Vp.y * 2.0 / (sp.y + sq.y) : 0.0;
+      }
+      // ---- prefetch the next row and the operands of this row's update ----------------------------------
+      if (j + 1 < jb) {
+        n_gd2 = ld2(AT(a.Egd, j + 3));
+        n_U = ld2(AT(a.EU, j + 2));
+        n_V = ld2(AT(a.EV, j + 2));
+        if (need_gh) {
+          n_gd1 = ld2(AT(a.Egd, j + 2));
+          n_hs = ld2(AT(a.ghs, j + 2));
+        }
+      }
+      const unsigned fl = t.flags[j];
+      const bool rowU = (j >= 1 && j <= nlat - 2);
+      const bool rowV = (j <= nlat - 2);
+      const bool rowG = rowU && (PASS != PASS_SLOW);
+      D2 oU = zero2, oV = zero2, oG = zero2, pU = zero2, pV = zero2, pG = zero2;
+      D2 wul = zero2, wut = zero2, wvl = zero2, wvt = zero2;
+      if (out) {
+        if (upd) {
+          oU = ld2(AT(a.OU, j));
+          if (rowV) oV = ld2(AT(a.OV, j));
+          if (rowG) oG = ld2(AT(a.Ogd, j));
+        }
+        if (MODE == MODE_S3A) {
+          if (rowU) pU = ld2(AT(a.PU, j));
+          if (rowV) pV = ld2(AT(a.PV, j));
+          if (rowG) pG = ld2(AT(a.Pgd, j));
+        }
+        if (ADV == ADV_WENO && PASS != PASS_FAST) {
+          if (rowU) {
+            wul = ld2(AT(a.AUlon, j));
+            wut = ld2(AT(a.AUlat, j));
+          }
+          if (rowV) {
+            wvl = ld2(AT(a.AVlon, j));
+            wvt = ld2(AT(a.AVlat, j));
+          }
+        }
+      }
+      // ---- longitude neighbours of row j / j+1 ------------------------------------------------------------
+      const double unw_a = shfl_up1(up.y);   // u(i-1, j+1) for a
+      const double Unw_a = shfl_up1(Up.y);   // U(i-1, j+1)
+      const double Vw_a = shfl_up1(V0.y);    // V(i-1, j)
+      const double sw_a = shfl_up1(s0.y);    // s(i-1, j)
+      const double ue_b = shfl_dn1(u0.x);    // u(i+1, j) for b
+      const double Ue_b = shfl_dn1(U0.x);
+      const double Ve_b = shfl_dn1(V0.x);
+      const double ve_b = shfl_dn1(v0.x);
+      double ghdx_a = 0.0, ghdx_b = 0.0, ghdy_a = 0.0, ghdy_b = 0.0;
+      if (need_gh) {
+#if GMD_STRICT
+        const double ge_b = shfl_dn1(g0.x), he_b = shfl_dn1(h0.x);
+        // gd(b) + ghs(b) - gd(a) - ghs(a), left to right (src/dycore_mod.F90:516-517,532-533)
+        ghdx_a = ((g0.y + h0.y) - g0.x) - h0.x;
+        ghdx_b = ((ge_b + he_b) - g0.y) - h0.y;
+        ghdy_a = ((gp.x + hp.x) - g0.x) - h0.x;
+        ghdy_b = ((gp.y + hp.y) - g0.y) - h0.y;
+#else
+        const double ge_b = shfl_dn1(g0.x);
+        ghdx_a = g0.y - g0.x;
+        ghdx_b = ge_b - g0.y;
+        ghdy_a = gp.x - g0.x;
+        ghdy_b = gp.y - g0.y;
+#endif
+      }
       const double hc0 = t.cosh[j - 1], hc1 = t.cosh[j], hc2 = t.cosh[j + 1];
-      // ===================== du, full rows 1..nlat-2 (src/dycore_mod.F90:207-210) =======================
-      if (rowU) {
-        const double uc = u_(j, c), Uc = U_(j, c);
-        double dU = 0.0;
-        if (PASS != PASS_FAST) {
-          double alon, alat;
-          if (ADV == ADV_WENO) {
-            alon = AT(a.AUlon, j);
-            alat = AT(a.AUlat, j);
+      double dUa, dVa, dGa, dUb, dVb, dGb;
+      // column a: west = lane-1's b (shuffled / carried), east = own b
+      tend_col<PASS, ADV>(t, j, rowU, rowV, rowG, a.beta_lon, a.beta_lat, hc0, hc1, hc2,
+                          uw_a, u0.x, u0.y, Uw_a, U0.x, U0.y, Vw_a, V0.x, V0.y, sw_a, s0.x, s0.y, v0.x, v0.y,
+                          Um.x, Vm.x, Vm.y, vm.x, vm.y, sm_.x,
+                          Up.x, Unw_a, up.x, unw_a, Vp.x, vp.x, sp.x,
+                          ghdx_a, ghdy_a, wul.x, wut.x, wvl.x, wvt.x, dUa, dVa, dGa);
+      // column b: west = own a, east = lane+1's a (shuffled / carried)
+      tend_col<PASS, ADV>(t, j, rowU, rowV, rowG, a.beta_lon, a.beta_lat, hc0, hc1, hc2,
+                          u0.x, u0.y, ue_b, U0.x, U0.y, Ue_b, V0.x, V0.y, Ve_b, s0.x, s0.y, se_b, v0.y, ve_b,
+                          Um.y, Vm.y, Vse_b, vm.y, vse_b, sm_.y,
+                          Up.y, Up.x, up.y, up.x, Vp.y, vp.y, sp.y,
+                          ghdx_b, ghdy_b, wul.y, wut.y, wvl.y, wvt.y, dUb, dVb, dGb);
+      if (out) {
+        if (rowU) {
+          if (fl & FL_DU) {
+            st2(AT(a.TU, j), dUa, dUb);  // filtered + applied by k_polar
           } else {
-            const double uw = u_(j, c - 1), ue = u_(j, c + 1);
-            const double Uw = U_(j, c - 1), Ue = U_(j, c + 1);
-            const double Us = U_(j - 1, c), Un = U_(j + 1, c);
-            const double u1 = uc + uw, u2 = uc + ue;
-            const double v1 = (v_(j - 1, c) + v_(j - 1, c + 1)) * hc0;
-            const double v2 = (v_(j, c) + v_(j, c + 1)) * hc1;
-            if (ADV == ADV_CENTER) {
-              alon = t.q_fdlon[j] * (u2 * Ue - u1 * Uw);   // :378-384
-              alat = t.q_fdlat[j] * (v2 * Un - v1 * Us);   // :433-439
-            } else {
-              const double bl = a.beta_lon, bt = a.beta_lat;
-              alon = t.q_fdlon[j] * (u2 * (Uc + Ue) - bl * fabs(u2) * (Ue - Uc) - u1 * (Uc + Uw) +
-                                     bl * fabs(u1) * (Uc - Uw) - (u2 - u1) * Uc);   // :395-404
-              alat = t.q_fdlat[j] * (v2 * (Uc + Un) - bt * fabs(v2) * (Un - Uc) - v1 * (Uc + Us) +
-                                     bt * fabs(v1) * (Uc - Us) - (v2 - v1) * Uc);   // :450-459
+            if (upd) st2(AT(a.NU, j), oU.x + a.dt * dUa, oU.y + a.dt * dUb);
+            if (MODE != MODE_S1) st2(AT(a.TU, j), dUa, dUb);
+            if (MODE == MODE_S3A) {
+              ip1 = ip1 + dUa * pU.x * t.cosf[j];
+              ip2 = ip2 + dUa * dUa * t.cosf[j];
+              ip1 = ip1 + dUb * pU.y * t.cosf[j];
+              ip2 = ip2 + dUb * dUb * t.cosf[j];
             }
           }
-          dU = -alon - alat;
+        } else if (upd) {
+          // pole rows: du is never written there (stays 0), so U' = U (src/dycore_mod.F90:623-627)
+          st2(AT(a.NU, j), oU.x, oU.y);
         }
-        if (PASS != PASS_SLOW) {
-          const double fv = 0.25 * (t.ff[j] + t.fc[j] * uc) *
-                            (t.cor1[j] * (V_(j - 1, c) + V_(j - 1, c + 1)) +
-                             t.cor2[j] * (V_(j, c) + V_(j, c + 1)));                // :485-493
-#if GMD_STRICT
-          const double pgf = 0.5 * (S_(j, c) + S_(j, c + 1)) / t.fdlon[j] * GHDIFF(j, c + 1, j, c);  // :514-519
-#else
-          const double pgf = 0.5 * (S_(j, c) + S_(j, c + 1)) * t.r_fdlon[j] * GHDIFF(j, c + 1, j, c);
-#endif
-          dU = (PASS == PASS_ALL) ? (dU + fv - pgf) : (fv - pgf);
-        }
-        if (fl & FL_DU) {
-          AT(a.TU, j) = dU;  // filtered + applied by k_polar
-        } else {
-          if (MODE == MODE_S1 || MODE == MODE_S2) AT(a.NU, j) = oU + a.dt * dU;
-          if (MODE != MODE_S1) AT(a.TU, j) = dU;
-          if (MODE == MODE_S3A) {
-            ip1 = ip1 + dU * pU * t.cosf[j];
-            ip2 = ip2 + dU * dU * t.cosf[j];
-          }
-        }
-      } else {
-        // pole rows: du is never written there (stays 0), so U' = U (src/dycore_mod.F90:623-627)
-        if (MODE == MODE_S1 || MODE == MODE_S2) AT(a.NU, j) = oU;
-      }
-      // ===================== dv, half rows 0..nlat-2 =====================================================
-      if (rowV) {
-        double dV = 0.0;
-        const double Vc = V_(j, c);
-        if (PASS != PASS_FAST) {
-          double alon, alat;
-          if (ADV == ADV_WENO) {
-            alon = AT(a.AVlon, j);
-            alat = AT(a.AVlat, j);
+        if (rowV) {
+          if (fl & FL_DV) {
+            st2(AT(a.TV, j), dVa, dVb);
           } else {
-            const double Vw = V_(j, c - 1), Ve = V_(j, c + 1);
-            const double Vs = V_(j - 1, c), Vn = V_(j + 1, c);
-            const double u1 = u_(j, c - 1) + u_(j + 1, c - 1);
-            const double u2 = u_(j, c) + u_(j + 1, c);
-            const double vh = v_(j, c) * hc1;
-            const double v1 = vh + v_(j - 1, c) * hc0;
-            const double v2 = vh + v_(j + 1, c) * hc2;
-            if (ADV == ADV_CENTER) {
-              alon = t.q_hdlon[j] * (u2 * Ve - u1 * Vw);   // :386-392
-              alat = t.q_hdlat[j] * (v2 * Vn - v1 * Vs);   // :441-447
-            } else {
-              const double bl = a.beta_lon, bt = a.beta_lat;
-              alon = t.q_hdlon[j] * (u2 * (Vc + Ve) - bl * fabs(u2) * (Ve - Vc) - u1 * (Vc + Vw) +
-                                     bl * fabs(u1) * (Vc - Vw) - (u2 - u1) * Vc);   // :406-415
-              alat = t.q_hdlat[j] * (v2 * (Vc + Vn) - bt * fabs(v2) * (Vn - Vc) - v1 * (Vc + Vs) +
-                                     bt * fabs(v1) * (Vc - Vs) - (v2 - v1) * Vc);   // :461-470
+            if (upd) st2(AT(a.NV, j), oV.x + a.dt * dVa, oV.y + a.dt * dVb);
+            if (MODE != MODE_S1) st2(AT(a.TV, j), dVa, dVb);
+            if (MODE == MODE_S3A) {
+              ip1 = ip1 + dVa * pV.x * hc1;
+              ip2 = ip2 + dVa * dVa * hc1;
+              ip1 = ip1 + dVb * pV.y * hc1;
+              ip2 = ip2 + dVb * dVb * hc1;
             }
           }
-          dV = -alon - alat;
         }
-        if (PASS != PASS_SLOW) {
-          const double f0 = t.ff[j], c0 = t.fc[j], f1 = t.ff[j + 1], c1 = t.fc[j + 1];
-          const double fu = 0.25 * ((f0 + c0 * u_(j, c)) * U_(j, c) + (f0 + c0 * u_(j, c - 1)) * U_(j, c - 1) +
-                                    (f1 + c1 * u_(j + 1, c)) * U_(j + 1, c) +
-                                    (f1 + c1 * u_(j + 1, c - 1)) * U_(j + 1, c - 1));   // :495-503
-#if GMD_STRICT
-          const double pgf = 0.5 * (S_(j, c) + S_(j + 1, c)) / t.hdlat[j] * hc1 * GHDIFF(j + 1, c, j, c);  // :530-535
-#else
-          const double pgf = 0.5 * (S_(j, c) + S_(j + 1, c)) * t.hc_hdlat[j] * GHDIFF(j + 1, c, j, c);
-#endif
-          dV = (PASS == PASS_ALL) ? (dV - fu - pgf) : (-fu - pgf);
-        }
-        if (fl & FL_DV) {
-          AT(a.TV, j) = dV;
-        } else {
-          if (MODE == MODE_S1 || MODE == MODE_S2) AT(a.NV, j) = oV + a.dt * dV;
-          if (MODE != MODE_S1) AT(a.TV, j) = dV;
-          if (MODE == MODE_S3A) {
-            ip1 = ip1 + dV * pV * hc1;
-            ip2 = ip2 + dV * dV * hc1;
+        if (rowG) {
+          if (fl & FL_DGD) {
+            st2(AT(a.Tgd, j), dGa, dGb);
+          } else {
+            if (upd) st2(AT(a.Ngd, j), oG.x + a.dt * dGa, oG.y + a.dt * dGb);
+            if (MODE != MODE_S1) st2(AT(a.Tgd, j), dGa, dGb);
+            if (MODE == MODE_S3A) {
+              ip1 = ip1 + dGa * pG.x * t.cosf[j];
+              ip2 = ip2 + dGa * dGa * t.cosf[j];
+              ip1 = ip1 + dGb * pG.y * t.cosf[j];
+              ip2 = ip2 + dGb * dGb * t.cosf[j];
+            }
           }
         }
       }
-      // ===================== dgd, full rows 1..nlat-2 (pole rows: k_polar) ===============================
-      if (rowG) {
-        const double sc = S_(j, c);
+      // ---- rotate the window ------------------------------------------------------------------------------
+      sm_ = s0; s0 = sp; sp = sq;
+      u0 = up;
+      vm = v0; v0 = vp;
+      Um = U0; U0 = Up;
+      Vm = V0; V0 = Vp;
+      g0 = gp;
 #if GMD_STRICT
-        const double mlon = ((sc + S_(j, c + 1)) * U_(j, c) - (sc + S_(j, c - 1)) * U_(j, c - 1)) * 0.5 / t.fdlon[j];  // :546-552
-        const double mlat = ((sc + S_(j + 1, c)) * V_(j, c) * hc1 - (sc + S_(j - 1, c)) * V_(j - 1, c) * hc0) * 0.5 /
-                            t.fdlat[j];                                                                              // :564-570
-#else
-        const double mlon = ((sc + S_(j, c + 1)) * U_(j, c) - (sc + S_(j, c - 1)) * U_(j, c - 1)) * t.h_fdlon[j];
-        const double mlat =
-            ((sc + S_(j + 1, c)) * V_(j, c) * hc1 - (sc + S_(j - 1, c)) * V_(j - 1, c) * hc0) * t.h_fdlat[j];
+      h0 = hp;
 #endif
-        const double dG = -mlon - mlat;
-        if (fl & FL_DGD) {
-          AT(a.Tgd, j) = dG;
-        } else {
-          if (MODE == MODE_S1 || MODE == MODE_S2) AT(a.Ngd, j) = oG + a.dt * dG;
-          if (MODE != MODE_S1) AT(a.Tgd, j) = dG;
-          if (MODE == MODE_S3A) {
-            ip1 = ip1 + dG * pG * t.cosf[j];
-            ip2 = ip2 + dG * dG * t.cosf[j];
-          }
-        }
-      }
+      uw_a = unw_a;
+      Uw_a = Unw_a;
+      Vse_b = Ve_b;
+      vse_b = ve_b;
+      se_b = spe_b;
     }
+#undef AT
   }
   if (MODE == MODE_S3A) {
-    const double r1 = block_sum<BX>(ip1, red);
-    const double r2 = block_sum<BX>(ip2, red);
+    const double r1 = warp_sum(ip1), r2 = warp_sum(ip2);
+    if (lane == 0) {
+      red[2 * warp] = r1;
+      red[2 * warp + 1] = r2;
+    }
+    __syncthreads();
     if (threadIdx.x == 0) {
+      double q1 = 0.0, q2 = 0.0;
+      for (int w = 0; w < SW; w++) {
+        q1 += red[2 * w];
+        q2 += red[2 * w + 1];
+      }
       const size_t b = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
-      a.partials[2 * b] = r1;
-      a.partials[2 * b + 1] = r2;
+      a.partials[2 * b] = q1;
+      a.partials[2 * b + 1] = q2;
     }
   }
-#undef AT
 }
-#undef S_
-#undef U_
-#undef V_
-#undef u_
-#undef v_
 
 // ---------------------------------------------------------------------------------------------------------
 // Polar rows: the SMOOTHING blocks of space_operators (src/dycore_mod.F90:212-219,228-235,244-251) with
