@@ -98,10 +98,11 @@ _LIBS = {}
 
 
 def load(kind: str = "fast") -> C.CDLL:
-    """Load the product library.  Raises (never falls back) if it has not been built."""
+    """Load the product library.  Raises (never falls back) if it has not been built.
+    `kind` may also be a path to an experimental build of the same sources (tools/tune_stage.py)."""
     if kind in _LIBS:
         return _LIBS[kind]
-    path = os.path.join(_HERE, LIB_NAMES[kind])
+    path = kind if os.path.sep in kind else os.path.join(_HERE, LIB_NAMES[kind])
     if not os.path.exists(path):
         raise FileNotFoundError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                                 "(there is no CPU fallback)")
@@ -141,6 +142,7 @@ def load(kind: str = "fast") -> C.CDLL:
     lib.gmd_algorithmic_bytes_per_column_step.argtypes = [P]
     lib.gmd_algorithmic_bytes_per_column_step.restype = C.c_double
     lib.gmd_time_stage_kernel.argtypes = [P, C.c_int, C.POINTER(C.c_float), D]
+    lib.gmd_time_stage_variant.argtypes = [P, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), D]
     _LIBS[kind] = lib
     return lib
 
@@ -301,6 +303,11 @@ class Dycore:
 
     def algorithmic_bytes_per_column_step(self) -> float:
         return float(self.lib.gmd_algorithmic_bytes_per_column_step(self.h))
+
+    def time_stage_variant(self, pass_: str, mode: int, reps: int = 20):
+        ms, nb = C.c_float(), C.c_double()
+        self._chk(self.lib.gmd_time_stage_variant(self.h, PASS[pass_], mode, reps, C.byref(ms), C.byref(nb)))
+        return ms.value, nb.value
 
     def time_stage_kernel(self, reps: int = 20):
         ms, nb = C.c_float(), C.c_double()

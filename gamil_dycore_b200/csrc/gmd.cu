@@ -1384,35 +1384,39 @@ int gmd_get_table(const gmd_model *m, int which, double *out) {
   return 0;
 }
 
-int gmd_time_stage_kernel(gmd_model *m, int reps, float *ms_per_launch, double *alg_bytes) {
-  if (!m || !ms_per_launch) return fail(GMD_ERR_ARG, "null argument");
-  if (!m->run_inited) return fail(GMD_ERR_STATE, "gmd_run_init has not been called");
-  if (reps < 1) return fail(GMD_ERR_ARG, "reps < 1");
-  int r = set_dev(m);
-  if (r) return r;
-  const int pass = (m->cfg.split_scheme == GMD_SPLIT_CSP2 || m->cfg.split_scheme == GMD_SPLIT_ISP) ? PASS_FAST : PASS_ALL;
+}  // extern "C"
+
+// time `reps` back-to-back launches of one stage-kernel variant (no polar rows), CUDA events on the stream
+static int time_stage(gmd_model *m, int pass, int mode, int reps, float *ms_per_launch) {
+  int r;
   State A, B;
-  if ((r = new_state(m, &A, nullptr))) return r;
-  if ((r = new_state(m, &B, nullptr))) return r;
+  const bool slow = (pass == PASS_SLOW);
+  if ((r = new_state(m, &A, slow ? m->cur.gd : nullptr))) return r;
+  if ((r = new_state(m, &B, slow ? m->cur.gd : nullptr))) return r;
   const double dt = 0.5 * m->cfg.time_step_size / std::max(1, m->cfg.subcycles);
-  // warm-up: A = cur + dt L(cur)
+  // warm-up / valid operands: A = cur + dt L(cur), tendOld = L(A), tendNew = L(B)
   if ((r = stage(m, pass, MODE_S1, m->cur, &m->cur, dt, &A, &m->tendOld, nullptr))) return r;
   if ((r = stage(m, pass, MODE_S2, A, &m->cur, dt, &B, &m->tendOld, nullptr))) return r;
-  // time the stage kernel only (not k_polar): launch it directly
+  if ((r = stage(m, pass, MODE_S3A, B, nullptr, 0.0, nullptr, &m->tendNew, &m->tendOld))) return r;
   StageArgs a;
   memset(&a, 0, sizeof a);
   a.g = m->geo; a.t = m->tab;
   a.EU = A.U; a.EV = A.V; a.Egd = A.gd; a.ghs = m->ghs;
   a.OU = m->cur.U; a.OV = m->cur.V; a.Ogd = m->cur.gd;
   a.NU = B.U; a.NV = B.V; a.Ngd = B.gd;
-  a.TU = m->tendOld.U; a.TV = m->tendOld.V; a.Tgd = m->tendOld.gd;
+  if (mode == MODE_S3A) {
+    a.TU = m->tendNew.U; a.TV = m->tendNew.V; a.Tgd = m->tendNew.gd;
+    a.PU = m->tendOld.U; a.PV = m->tendOld.V; a.Pgd = m->tendOld.gd;
+  } else {
+    a.TU = m->tendOld.U; a.TV = m->tendOld.V; a.Tgd = m->tendOld.gd;
+  }
   a.dt = dt;
   a.beta_lon = m->cfg.uv_adv_upwind_lon_beta; a.beta_lat = m->cfg.uv_adv_upwind_lat_beta;
   a.AUlon = m->w_alon_u; a.AUlat = m->w_alat_u; a.AVlon = m->w_alon_v; a.AVlat = m->w_alat_v;
   a.partials = m->d_partials;
   a.rows_per_cta = m->rows_per_cta;
   dim3 grid((unsigned)m->nbx, (unsigned)m->nchunks);
-  stage_fn fn = pick_stage(pass, m->cfg.uv_adv_scheme, MODE_S2);
+  stage_fn fn = pick_stage(pass, m->cfg.uv_adv_scheme, mode);
   cudaEvent_t e0, e1;
   CK(cudaEventCreate(&e0));
   CK(cudaEventCreate(&e1));
@@ -1429,11 +1433,37 @@ int gmd_time_stage_kernel(gmd_model *m, int reps, float *ms_per_launch, double *
   cudaEventDestroy(e1);
   CK(cudaGetLastError());
   *ms_per_launch = ms / reps;
+  release_state(m, &A);
+  release_state(m, &B);
+  return 0;
+}
+
+extern "C" {
+
+int gmd_time_stage_kernel(gmd_model *m, int reps, float *ms_per_launch, double *alg_bytes) {
+  if (!m || !ms_per_launch) return fail(GMD_ERR_ARG, "null argument");
+  if (!m->run_inited) return fail(GMD_ERR_STATE, "gmd_run_init has not been called");
+  if (reps < 1) return fail(GMD_ERR_ARG, "reps < 1");
+  int r = set_dev(m);
+  if (r) return r;
+  const int pass = (m->cfg.split_scheme == GMD_SPLIT_CSP2 || m->cfg.split_scheme == GMD_SPLIT_ISP) ? PASS_FAST : PASS_ALL;
+  if ((r = time_stage(m, pass, MODE_S2, reps, ms_per_launch))) return r;
   // S2 of the all/fast pass: reads U,V,gd,ghs of the evaluated state + U,V,gd of the base state, writes the
   // new U,V,gd and the three tendencies: 13 words per column
   if (alg_bytes) *alg_bytes = 13.0 * 8.0 * (double)m->nr * (double)m->geo.nlon;
-  release_state(m, &A);
-  release_state(m, &B);
+  return 0;
+}
+
+int gmd_time_stage_variant(gmd_model *m, int pass, int mode, int reps, float *ms_per_launch, double *alg_bytes) {
+  if (!m || !ms_per_launch) return fail(GMD_ERR_ARG, "null argument");
+  if (!m->run_inited) return fail(GMD_ERR_STATE, "gmd_run_init has not been called");
+  if (reps < 1 || pass < 0 || pass > 2 || mode < 0 || mode > 3) return fail(GMD_ERR_ARG, "bad argument");
+  int r = set_dev(m);
+  if (r) return r;
+  if ((r = time_stage(m, pass, mode, reps, ms_per_launch))) return r;
+  // words per column: fast/all S1 7, S2 13, S3a 10; slow S1 5, S2 9, S3a 7; EVAL = reads + 3 (2) writes
+  static const double words[2][4] = {{7, 13, 10, 7}, {5, 9, 7, 5}};
+  if (alg_bytes) *alg_bytes = words[pass == PASS_SLOW ? 1 : 0][mode] * 8.0 * (double)m->nr * (double)m->geo.nlon;
   return 0;
 }
 

@@ -111,6 +111,55 @@ __device__ __forceinline__ D2 ld2(const double *p) {
 __device__ __forceinline__ void st2(double *p, double x, double y) {
   *reinterpret_cast<double2 *>(p) = make_double2(x, y);
 }
+#ifndef GMD_FAST_DIV
+#define GMD_FAST_DIV (!GMD_STRICT)
+#endif
+#ifndef GMD_UNROLL
+#define GMD_UNROLL 2
+#endif
+#ifndef GMD_MINB
+#define GMD_MINB 4   // 4 CTAs x 128 threads per SM => <= 128 registers (measured best, profiles/r1_c_stage_tuning.txt)
+#endif
+#define GMD_PRAGMA_(x) _Pragma(#x)
+#define GMD_UNROLL_PRAGMA(n) GMD_PRAGMA_(unroll n)
+// 2 a / b and sqrt(x) for the on-chip recomputation of u, v, sqrt(gd).  Strict build: IEEE division / sqrt.
+// Product build: MUFU seed + Newton steps without the special-operand slow path (operands are O(1e2)
+// geopotential roots, never 0, inf or denormal on rows where the result is used); error <= 1 ulp.
+__device__ __forceinline__ double two_a_over_b(double a, double b) {
+#if GMD_FAST_DIV
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+  double e = fma(-b, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-b, r, 1.0);
+  r = fma(r, e, r);
+  const double a2 = a + a;
+  double q = a2 * r;
+  const double rem = fma(-b, q, a2);
+  return fma(rem, r, q);
+#else
+  return a * 2.0 / b;
+#endif
+}
+__device__ __forceinline__ double fast_sqrt(double x) {
+#if GMD_FAST_DIV
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  // y ~ x^-1/2 (about 20 bits): two Newton steps on y, then s = x y with one correction
+  double h = 0.5 * y;
+  double e = fma(-x * y, h, 0.5);   // 0.5 - 0.5 x y^2
+  y = fma(y, e, y);
+  h = 0.5 * y;
+  e = fma(-x * y, h, 0.5);
+  y = fma(y, e, y);
+  double sr = x * y;
+  const double rem = fma(-sr, sr, x);
+  sr = fma(rem, 0.5 * y, sr);
+  return (x > 0.0) ? sr : 0.0;
+#else
+  return sqrt(x);
+#endif
+}
 __device__ __forceinline__ double shfl_up1(double v) { return __shfl_up_sync(0xffffffffu, v, 1); }
 __device__ __forceinline__ double shfl_dn1(double v) { return __shfl_down_sync(0xffffffffu, v, 1); }
 
@@ -224,7 +273,7 @@ constexpr int SW = 4;     // warps per CTA
 constexpr int BX = SW * 32;
 
 template <int PASS, int ADV, int MODE>
-__global__ void __launch_bounds__(BX) k_stage(const StageArgs a) {
+__global__ void __launch_bounds__(BX, GMD_MINB) k_stage(const StageArgs a) {
   __shared__ double red[2 * SW];
   const int nlon = a.g.nlon, nlat = a.g.nlat, r0 = a.g.r0;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -242,7 +291,11 @@ __global__ void __launch_bounds__(BX) k_stage(const StageArgs a) {
     c0 %= nlon;
     if (c0 < 0) c0 += nlon;
     const bool out = (lane >= 1) && (lane <= WOUT / 2) && (strip * WOUT + 2 * (lane - 1) < nlon);
-#define AT(p, j) ((p) + ((ptrdiff_t)((j)-r0) * (ptrdiff_t)nlon + (ptrdiff_t)c0))
+    // element offset of (row j, column c0) is `off`, advanced by nlon per row; AT addresses row j + k
+    const ptrdiff_t nl = nlon;
+    ptrdiff_t off = (ptrdiff_t)(ja - r0) * nl + (ptrdiff_t)c0;
+#define ATK(p, k) ((p) + (off + (ptrdiff_t)(k) * nl))
+#define AT(p, jj) ATK(p, (jj) - j)
     const D2 zero2 = {0.0, 0.0};
     // ---- prologue: rows ja-1, ja, ja+1 of sqrt(gd); rows ja-1, ja of U, V; gh row ja --------------------
     D2 sm_, s0, sp, sq, u0, up, vm, v0, vp, Um, U0, Up, Vm, V0, Vp;
@@ -251,10 +304,11 @@ __global__ void __launch_bounds__(BX) k_stage(const StageArgs a) {
     D2 h0 = zero2, hp = zero2;  // ghs rows j, j+1 (g0/gp then hold gd alone)
 #endif
     {
+      const int j = ja;
       const D2 a0 = ld2(AT(a.Egd, ja - 1)), a1 = ld2(AT(a.Egd, ja)), a2 = ld2(AT(a.Egd, ja + 1));
-      sm_.x = sqrt(a0.x); sm_.y = sqrt(a0.y);
-      s0.x = sqrt(a1.x); s0.y = sqrt(a1.y);
-      sp.x = sqrt(a2.x); sp.y = sqrt(a2.y);
+      sm_.x = fast_sqrt(a0.x); sm_.y = fast_sqrt(a0.y);
+      s0.x = fast_sqrt(a1.x); s0.y = fast_sqrt(a1.y);
+      sp.x = fast_sqrt(a2.x); sp.y = fast_sqrt(a2.y);
       Um = ld2(AT(a.EU, ja - 1));
       U0 = ld2(AT(a.EU, ja));
       Vm = ld2(AT(a.EV, ja - 1));
@@ -271,13 +325,13 @@ __global__ void __launch_bounds__(BX) k_stage(const StageArgs a) {
       }
       // u(ja), v(ja-1), v(ja): update_state :636-645 (u = 2U/(s_i + s_i+1), v = 2V/(s_j + s_j+1))
       const double s0e = shfl_dn1(s0.x);
-      u0.x = U0.x * 2.0 / (s0.x + s0.y);
-      u0.y = U0.y * 2.0 / (s0.y + s0e);
+      u0.x = two_a_over_b(U0.x, s0.x + s0.y);
+      u0.y = two_a_over_b(U0.y, s0.y + s0e);
       const bool vmok = (ja - 1 >= 0), v0ok = (ja < nlat - 1);
-      vm.x = vmok ? Vm.x * 2.0 / (sm_.x + s0.x) : 0.0;
-      vm.y = vmok ? Vm.y * 2.0 / (sm_.y + s0.y) : 0.0;
-      v0.x = v0ok ? V0.x * 2.0 / (s0.x + sp.x) : 0.0;
-      v0.y = v0ok ? V0.y * 2.0 / (s0.y + sp.y) : 0.0;
+      vm.x = vmok ? two_a_over_b(Vm.x, sm_.x + s0.x) : 0.0;
+      vm.y = vmok ? two_a_over_b(Vm.y, sm_.y + s0.y) : 0.0;
+      v0.x = v0ok ? two_a_over_b(V0.x, s0.x + sp.x) : 0.0;
+      v0.y = v0ok ? two_a_over_b(V0.y, s0.y + sp.y) : 0.0;
     }
     // longitude-neighbour values carried from one row to the next
     double uw_a = shfl_up1(u0.y);    // u(i-1, j)   for column a
@@ -286,19 +340,20 @@ __global__ void __launch_bounds__(BX) k_stage(const StageArgs a) {
     double vse_b = shfl_dn1(vm.x);   // v(i+1, j-1)
     double se_b = shfl_dn1(s0.x);    // s(i+1, j)
     // first prefetch: gd(ja+2), U(ja+1), V(ja+1), gd(ja+1), ghs(ja+1)
-    D2 n_gd2 = ld2(AT(a.Egd, ja + 2));
-    D2 n_U = ld2(AT(a.EU, ja + 1));
-    D2 n_V = ld2(AT(a.EV, ja + 1));
+    D2 n_gd2 = ld2(ATK(a.Egd, 2));
+    D2 n_U = ld2(ATK(a.EU, 1));
+    D2 n_V = ld2(ATK(a.EV, 1));
     D2 n_gd1 = zero2, n_hs = zero2;
     if (need_gh) {
-      n_gd1 = ld2(AT(a.Egd, ja + 1));
-      n_hs = ld2(AT(a.ghs, ja + 1));
+      n_gd1 = ld2(ATK(a.Egd, 1));
+      n_hs = ld2(ATK(a.ghs, 1));
     }
 
+    GMD_UNROLL_PRAGMA(GMD_UNROLL)
     for (int j = ja; j < jb; j++) {
       // ---- advance the window: s(j+2), U(j+1), V(j+1), gh(j+1), u(j+1), v(j+1) --------------------------
-      sq.x = sqrt(n_gd2.x);
-      sq.y = sqrt(n_gd2.y);
+      sq.x = fast_sqrt(n_gd2.x);
+      sq.y = fast_sqrt(n_gd2.y);
       Up = n_U;
       Vp = n_V;
       if (need_gh) {
@@ -313,20 +368,18 @@ __global__ void __launch_bounds__(BX) k_stage(const StageArgs a) {
       const double spe_b = shfl_dn1(sp.x);  // s(i+1, j+1) for column b
       {
         const bool uok = (j + 1 < nlat), vok = (j + 1 < nlat - 1);
-        up.x = uok ? Up.x * 2.0 / (sp.x + sp.y) : 0.0;
-        up.y = uok ? Up.y * 2.0 / (sp.y + spe_b) : 0.0;
-        vp.x = vok ? Vp.x * 2.0 / (sp.x + sq.x) : 0.0;
-        vp.y = vok ? Vp.y * 2.0 / (sp.y + sq.y) : 0.0;
+        up.x = uok ? two_a_over_b(Up.x, sp.x + sp.y) : 0.0;
+        up.y = uok ? two_a_over_b(Up.y, sp.y + spe_b) : 0.0;
+        vp.x = vok ? two_a_over_b(Vp.x, sp.x + sq.x) : 0.0;
+        vp.y = vok ? two_a_over_b(Vp.y, sp.y + sq.y) : 0.0;
       }
       // ---- prefetch the next row and the operands of this row's update ----------------------------------
+      if (need_gh) n_gd1 = n_gd2;  // gd(j+2) is next iteration's gd(j'+1)
       if (j + 1 < jb) {
         n_gd2 = ld2(AT(a.Egd, j + 3));
         n_U = ld2(AT(a.EU, j + 2));
         n_V = ld2(AT(a.EV, j + 2));
-        if (need_gh) {
-          n_gd1 = ld2(AT(a.Egd, j + 2));
-          n_hs = ld2(AT(a.ghs, j + 2));
-        }
+        if (need_gh) n_hs = ld2(AT(a.ghs, j + 2));
       }
       const unsigned fl = t.flags[j];
       const bool rowU = (j >= 1 && j <= nlat - 2);
@@ -458,8 +511,10 @@ __global__ void __launch_bounds__(BX) k_stage(const StageArgs a) {
       Vse_b = Ve_b;
       vse_b = ve_b;
       se_b = spe_b;
+      off += nl;
     }
 #undef AT
+#undef ATK
   }
   if (MODE == MODE_S3A) {
     const double r1 = warp_sum(ip1), r2 = warp_sum(ip2);

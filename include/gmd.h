@@ -150,6 +150,10 @@ double gmd_algorithmic_bytes_per_column_step(const gmd_model *m);
    `reps` back-to-back launches between CUDA events on the model's stream; returns average ms per
    launch and the algorithmic bytes one launch moves on this rank */
 int gmd_time_stage_kernel(gmd_model *m, int reps, float *ms_per_launch, double *alg_bytes_per_launch);
+/* the same for any (pass, mode) instantiation: mode 0 = S1 (predict), 1 = S2 (predict + store tendency),
+   2 = S3a (tendency + inner products), 3 = evaluation only */
+int gmd_time_stage_variant(gmd_model *m, int pass, int mode, int reps, float *ms_per_launch,
+                           double *alg_bytes_per_launch);
 
 #ifdef __cplusplus
 }
