@@ -1,0 +1,46 @@
+"""Host-side helpers for the latitude-band decomposition (one process per GPU, torch.distributed for the plumbing).
+
+The data path itself (halo rows, the two-scalar all-reduces) lives inside libgmd over NCCL; this module only mirrors
+the band arithmetic of gmd_create (gamil_dycore_b200/csrc/gmd.cu) and gathers bands on the host for output."""
+from __future__ import annotations
+
+import numpy as np
+
+
+def band(rank: int, nranks: int, num_lat: int):
+    """full-latitude rows [r0, r1) owned by `rank`: rows split as evenly as possible, the first `num_lat % nranks`
+    ranks get one more (identical to gmd_get_band)."""
+    base, rem = divmod(num_lat, nranks)
+    r0 = rank * base + min(rank, rem)
+    return r0, r0 + base + (1 if rank < rem else 0)
+
+
+def halo_rows(rank: int, nranks: int, num_lat: int):
+    """global rows a rank receives from its neighbours before each stage:
+    south: U, V, gd row r0-1; north: U, V row r1 and gd rows r1, r1+1."""
+    r0, r1 = band(rank, nranks, num_lat)
+    south = [r0 - 1] if rank > 0 else []
+    north = [r1, r1 + 1] if rank + 1 < nranks else []
+    return south, north
+
+
+def gather_field(local: np.ndarray, num_lat: int, group=None) -> np.ndarray:
+    """`local` is a global-shaped array ([num_lat][num_lon] or, for half-latitude fields, [num_lat-1][num_lon]) in
+    which only this rank's band rows are filled (what Dycore.state() returns); all ranks receive the assembled
+    field.  Works with any torch.distributed backend."""
+    import torch
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    nrows_global = local.shape[0]
+    dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+    out = np.zeros_like(local)
+    for r in range(world):
+        r0, r1 = band(r, world, num_lat)
+        r1 = min(r1, nrows_global)
+        if r1 <= r0:
+            continue
+        buf = torch.from_numpy(np.ascontiguousarray(local[r0:r1])).to(dev) if r == rank else \
+            torch.empty((r1 - r0,) + local.shape[1:], dtype=torch.float64, device=dev)
+        dist.broadcast(buf, src=dist.get_global_rank(group, r) if group is not None else r, group=group)
+        out[r0:r1] = buf.cpu().numpy()
+    return out

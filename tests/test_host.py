@@ -1,0 +1,231 @@
+"""CPU tests of the host side: the C ABI surface, the namelist reader, the log / clock formats, the IC plugins and
+the history writer of gamil_dycore_b200/host (mirrors of src/params_mod.F90, log_mod, time_mod, test_cases, history_mod),
+and the latitude-band helpers over a 2-process gloo group.  No GPU, no compute call into libgmd."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import gamil_dycore_b200 as gmd
+from oracle.oracle import Oracle, OracleConfig
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SELF = os.path.join(ROOT, "gamil_dycore_b200", "host_selftest")
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _build_product():
+    gmd.build()
+
+
+def selftest(*args, cwd=None):
+    res = subprocess.run([SELF, *map(str, args)], capture_output=True, text=True, cwd=cwd)
+    return res.returncode, res.stdout
+
+
+def write(tmp_path, text, name="namelist"):
+    p = tmp_path / name
+    p.write_text(text)
+    return str(p)
+
+
+# ------------------------------------------------------------------------------------------------ C ABI
+@pytest.mark.parametrize("kind", ["fast", "strict"])
+def test_library_exports_every_declared_symbol(kind):
+    hdr = open(os.path.join(ROOT, "include", "gmd.h")).read()
+    names = sorted(set(re.findall(r"\b(gmd_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(names) >= 30
+    lib = ctypes.CDLL(os.path.join(ROOT, "gamil_dycore_b200", gmd.LIB_NAMES[kind]))
+    for n in names:
+        assert hasattr(lib, n), n
+    assert lib.gmd_version() == 100
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(gmd.GmdError) as ei:
+        gmd.Dycore(gmd.Config(num_lon=36, num_lat=19, time_step_size=600.0))
+    assert ei.value.code == gmd.ERR_CUDA and "no CPU fallback" in str(ei.value)
+
+
+def test_config_defaults_match_params_mod():
+    lib = gmd.load()
+    c = gmd._Cfg()
+    lib.gmd_config_defaults(ctypes.byref(c))
+    # src/params_mod.F90:15,55-56,59,65-66
+    assert (c.subcycles, c.uv_adv_upwind_lon_beta, c.uv_adv_upwind_lat_beta) == (4, 0.0, 0.5)
+    assert (c.use_zonal_tend_filter, c.diffusion_order, c.use_diffusion) == (1, 2, 0)
+    assert list(c.cutoff) == [0] * 20 and (c.rank, c.nranks, c.device) == (0, 1, -1)
+
+
+# ------------------------------------------------------------------------------------------------ namelist
+def parse(path):
+    rc, out = selftest("parse", path)
+    return rc, dict(l.split("=", 1) for l in out.strip().splitlines() if "=" in l), out
+
+
+@pytest.mark.parametrize("name,expect", [
+    ("namelist.rh_test", dict(test_case="rossby_haurwitz_wave", num_lon="360", num_lat="181", time_step_size="240", subcycles="6",
+                              split_scheme="csp2", cutoff="4,4,4,4,4" + ",0" * 15)),
+    ("namelist.mz_test", dict(test_case="mountain_zonal_flow", num_lon="180", num_lat="90", uv_adv_scheme="upwind",
+                              uv_adv_upwind_lat_beta="0.10000000000000001", subcycles="8", restart_period="10 days")),
+    ("namelist.jz_test", dict(test_case="jet_zonal_flow", use_diffusion="1", cutoff=",".join(["4"] * 20), run_hours="6")),
+    ("namelist.sg_test", dict(test_case="steady_geostrophic_flow", num_lon="3600", num_lat="1801")),
+])
+def test_shipped_namelists_parse(name, expect):
+    rc, kv, out = parse(os.path.join(ROOT, "run", name))
+    assert rc == 0, out
+    for k, v in expect.items():
+        assert kv[k] == v, (k, kv[k])
+
+
+def test_namelist_defaults_comments_and_unknown_keys(tmp_path):
+    text = """! leading comment
+&dycore_params
+ test_case = 'rossby_haurwitz_wave', case_name='x' ! trailing comment
+ num_lon = 36
+ num_lat = 19, time_step_size = 1.5d2
+ time_scheme = "predict_correct"
+ split_scheme = 'none'
+ qcon_modified = .false.
+ history_periods = '12 hours'
+/
+"""
+    rc, kv, out = parse(write(tmp_path, text))
+    assert rc == 0, out
+    # defaults of src/params_mod.F90:13-66; restart_period falls back to history_periods (:113)
+    assert kv["subcycles"] == "4" and kv["uv_adv_scheme"] == "center_diff" and kv["uv_adv_upwind_lat_beta"] == "0.5"
+    assert kv["use_zonal_tend_filter"] == "1" and kv["time_step_size"] == "150" and kv["restart_period"] == "12 hours"
+    # the reference's own rh/jz namelists use keys this commit does not define: a namelist read aborts
+    bad = text.replace(" num_lon = 36", " days = 3\n num_lon = 36")
+    rc, _, out = parse(write(tmp_path, bad, "bad"))
+    assert rc == 2 and "Cannot match namelist object name days" in out
+
+
+# ------------------------------------------------------------------------------------------------ formats
+@pytest.mark.parametrize("x,s", [(2.812376625197987e19, "0.28123766251980E+20"), (5.083437998896658e12, "0.50834379988967E+13"),
+                                 (1.0000123, "0.10000123000000E+01"), (-0.5, "-0.5000000000000E+00"), (0.0, "0.00000000000000E+00"),
+                                 (9.9999999999999e-5, "0.99999999999999E-04"), (9.99999999999999e-5, "0.10000000000000E-03")])
+def test_to_string_real8_is_fortran_E20_14(x, s):
+    rc, out = selftest("fmt", repr(x))
+    assert rc == 0 and out.strip() == s
+
+
+def test_clock_and_history_alert(tmp_path):
+    nml = os.path.join(ROOT, "run", "namelist.rh_test")   # dt 240 s, history every 6 hours, 1 day
+    rc, out = selftest("clock", nml, 95)
+    lines = out.strip().splitlines()
+    assert lines[0] == "0001-01-01T00:00:00Z 0 90 360"      # no frame at t = 0 (src/time_mod.F90:192-213)
+    assert lines[1].split()[0] == "0001-01-01T00:04:00Z"
+    rings = [k for k, l in enumerate(lines[1:], 1) if l.split()[1] == "1"]
+    assert rings[0] == 90 and lines[90].split()[0] == "0001-01-01T06:00:00Z"
+    assert rings == [90]                                     # rings once, re-armed by the next time_advance
+
+
+# ------------------------------------------------------------------------------------------------ IC plugins
+@pytest.mark.parametrize("tc,extra,tol", [("rossby_haurwitz_wave", "", 1e-15), ("steady_geostrophic_flow", "", 1e-15),
+                                          ("mountain_zonal_flow", "", 1e-15), ("jet_zonal_flow", "", 1e-9),
+                                          ("mountain_zonal_flow", "&mountain_zonal_flow_test_params\n smooth_mountain = .true.\n/\n", 1e-14)])
+def test_ic_plugins_match_oracle(tmp_path, tc, extra, tol):
+    nlon, nlat = 72, 37
+    text = f"&dycore_params\n test_case='{tc}'\n case_name='t'\n num_lon={nlon}\n num_lat={nlat}\n time_step_size=100\n/\n" + extra
+    out_bin = str(tmp_path / "ic.bin")
+    rc, out = selftest("ic", write(tmp_path, text), out_bin)
+    assert rc == 0 and out.startswith("Use "), out
+    a = np.fromfile(out_bin)
+    nf, nh = nlon * nlat, nlon * (nlat - 1)
+    u, v, gd, ghs = a[:nf].reshape(nlat, nlon), a[nf:nf + nh].reshape(nlat - 1, nlon), a[nf + nh:2 * nf + nh].reshape(nlat, nlon), a[2 * nf + nh:].reshape(nlat, nlon)
+    o = Oracle(OracleConfig(num_lon=nlon, num_lat=nlat, time_step_size=100.0))
+    o.set_initial_condition(tc, params=[1.0] if extra else None)
+    uo, vo, gdo = o.state()
+    for x, y in ((u, uo), (v, vo), (gd, gdo), (ghs, o.ghs())):
+        assert np.abs(x - y).max() <= tol * max(np.abs(y).max(), 1.0)
+    assert not u[0].any() and not u[-1].any()   # u = 0 on the pole rows: the invariant gmd_set_state checks
+
+
+def test_unknown_test_case_message(tmp_path):
+    text = "&dycore_params\n test_case='nope'\n case_name='t'\n num_lon=36\n num_lat=19\n time_step_size=100\n/\n"
+    rc, out = selftest("ic", write(tmp_path, text), str(tmp_path / "x"))
+    assert rc == 2 and "Unknown test case nope!" in out   # src/dycore_test.F90:41
+
+
+# ------------------------------------------------------------------------------------------------ history file
+def test_history_file_schema(tmp_path):
+    from scipy.io import netcdf_file
+    nml = os.path.join(ROOT, "run", "namelist.mz_test")
+    rc, out = selftest("history", nml, 120, cwd=str(tmp_path))
+    assert rc == 0, out
+    name = out.strip()
+    assert name == "mz_c_u_01.180x90.dt720.h0.0001-01-02T00:00:00Z.nc"    # src/io_mod.F90:417-419, time_mod.F90:128
+    raw = open(tmp_path / name, "rb").read(4)
+    assert raw == b"CDF\x01"                                                 # classic format (NF90_CLOBBER)
+    f = netcdf_file(str(tmp_path / name), "r", mmap=False)
+    assert list(f.dimensions.items()) == [("time", None), ("lon", 180), ("lat", 90), ("ilon", 180), ("ilat", 89)]
+    assert list(f.variables) == ["time", "lon", "lat", "ilon", "ilat", "u", "v", "gh", "ghs", "vor", "div", "te", "tm"]
+    attrs = list(f._attributes)
+    assert attrs == ["dataset", "desc", "author", "time_step_size", "time_scheme", "split_scheme", "subcycles"]
+    assert f.dataset.decode().rstrip() == "hist0" and len(f.desc) == 256 and f.author.decode().rstrip() == "N/A"
+    assert f.time_step_size == 720.0 and f.subcycles == 8 and f.split_scheme.decode().rstrip() == "csp2"
+    for v in f.variables.values():
+        assert v.data.dtype == np.dtype(">f8")
+    assert f.variables["u"].dimensions == ("time", "lat", "lon") and f.variables["vor"].dimensions == ("time", "lat", "ilon")
+    assert f.variables["div"].dimensions == ("time", "ilat", "lon") and f.variables["te"].dimensions == ("time",)
+    assert f.variables["time"].units == b"days since 0001-01-01T00_00_00" and f.variables["time"][0] == 1.0
+    assert f.variables["u"].long_name == b"u wind component" and f.variables["gh"].units == b"m2 s-2"
+    assert f.variables["lat"][0] == -90.0 and f.variables["lat"][-1] == 90.0 and abs(f.variables["ilon"][0] - 1.0) < 1e-12
+    # A-grid averaging of the C-grid winds (src/history_mod.F90:102-108)
+    o = Oracle(OracleConfig(num_lon=180, num_lat=90, time_step_size=720.0))
+    o.set_initial_condition("mountain_zonal_flow")
+    u, v, gd = o.state()
+    ua = 0.5 * (u + np.roll(u, 1, axis=1))
+    assert np.allclose(f.variables["u"][0], ua, rtol=0, atol=1e-12)
+    assert np.allclose(f.variables["gh"][0], gd + o.ghs(), rtol=1e-15)
+    assert f.variables["te"][0] == 2.5 and f.variables["tm"][0] == 1.5
+    assert not f.variables["vor"][0][-1].any()
+
+
+# ------------------------------------------------------------------------------------------------ decomposition
+def test_band_arithmetic():
+    from gamil_dycore_b200 import parallel
+    for nlat, n in ((1801, 8), (3601, 8), (181, 2), (90, 4), (721, 3)):
+        rows = [parallel.band(r, n, nlat) for r in range(n)]
+        assert rows[0][0] == 0 and rows[-1][1] == nlat
+        assert all(a[1] == b[0] for a, b in zip(rows, rows[1:]))
+        sizes = [b - a for a, b in rows]
+        assert max(sizes) - min(sizes) <= 1
+    assert parallel.halo_rows(0, 2, 181) == ([], [91, 92]) and parallel.halo_rows(1, 2, 181) == ([90], [])
+
+
+def _gloo_worker(rank, world, port, nlat, nlon, q):
+    import torch.distributed as dist
+    from gamil_dycore_b200 import parallel
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    rng = np.random.default_rng(7)
+    full, half = rng.standard_normal((nlat, nlon)), rng.standard_normal((nlat - 1, nlon))
+    r0, r1 = parallel.band(rank, world, nlat)
+    lf, lh = np.zeros_like(full), np.zeros_like(half)
+    lf[r0:r1] = full[r0:r1]
+    lh[r0:min(r1, nlat - 1)] = half[r0:min(r1, nlat - 1)]
+    gf = parallel.gather_field(lf, nlat)
+    gh = parallel.gather_field(lh, nlat)
+    q.put((rank, bool(np.array_equal(gf, full) and np.array_equal(gh, half))))
+    dist.destroy_process_group()
+
+
+def test_gather_bands_over_gloo_world_size_2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, 29577, 37, 12, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True), (1, True)]
