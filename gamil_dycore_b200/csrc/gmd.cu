@@ -147,6 +147,7 @@ struct gmd_model {
 
   // stage launch geometry
   int nbx = 0, nchunks = 0, rows_per_cta = 0;
+  size_t stage_smem = 0;  // dynamic shared memory of k_stage: (rows_per_cta + 2) row records
   int ew_blocks = 0;  // grid of element-wise kernels
 
   // comm
@@ -295,6 +296,24 @@ static int build_tables(gmd_model *m) {
   CK(cudaMalloc(&m->d_flags_alloc, n));
   CK(cudaMemcpy(m->d_flags_alloc, fl.data(), n, cudaMemcpyHostToDevice));
   t.flags = m->d_flags_alloc + TPAD;
+  {  // packed per-row records for the stage kernel (one 128-byte line per row)
+    std::vector<double> rec(n * RC_N, 0.0);
+    for (size_t k = 0; k < n; k++) {
+      double *r = &rec[k * RC_N];
+      r[RC_COSF] = M.full_cos[k]; r[RC_COSH] = M.half_cos[k]; r[RC_FF] = M.full_f[k]; r[RC_FC] = M.full_c[k];
+      r[RC_Q_FDLON] = q_fdlon[k]; r[RC_Q_FDLAT] = q_fdlat[k]; r[RC_Q_HDLON] = q_hdlon[k]; r[RC_Q_HDLAT] = q_hdlat[k];
+      r[RC_COR1] = cor1[k]; r[RC_COR2] = cor2[k];
+#if GMD_STRICT
+      r[RC_PGFU] = fdlon[k]; r[RC_PGFV] = hdlat[k]; r[RC_MLON] = fdlon[k]; r[RC_MLAT] = fdlat[k];
+#else
+      r[RC_PGFU] = r_fdlon[k]; r[RC_PGFV] = hc_hdlat[k]; r[RC_MLON] = h_fdlon[k]; r[RC_MLAT] = h_fdlat[k];
+#endif
+      r[RC_FLAGS] = (double)fl[k];
+    }
+    const double *d = nullptr;
+    if ((r = upload_table(m, rec, &d))) return r;
+    t.rowrec = d - TPAD + (size_t)TPAD * RC_N;  // upload_table offsets by TPAD doubles; records need TPAD rows
+  }
 
   // filter basis: row 0 = 1, row 2k-1 = cos(k x_i), row 2k = sin(k x_i), x_i = 2 pi i / nlon
   const int nlon = M.nlon;
@@ -500,7 +519,7 @@ static int stage(gmd_model *m, int pass, int mode, const State &E, const State *
   a.partials = m->d_partials;
   a.rows_per_cta = m->rows_per_cta;
   dim3 grid((unsigned)m->nbx, (unsigned)m->nchunks);
-  if (!m->dry) pick_stage(pass, adv, mode)<<<grid, BX, 0, m->stream>>>(a);
+  if (!m->dry) pick_stage(pass, adv, mode)<<<grid, BX, m->stage_smem, m->stream>>>(a);
   if ((r = post_launch(m))) return r;
 
   const int li = (pass == PASS_SLOW) ? 1 : 0;
@@ -932,7 +951,8 @@ int gmd_create(const gmd_config *cfg, gmd_model **out) {
     m->nbx = (nstrips + SW - 1) / SW;
     int per_sm = 0;
     const int pass0 = (cfg->split_scheme == GMD_SPLIT_CSP2 || cfg->split_scheme == GMD_SPLIT_ISP) ? PASS_FAST : PASS_ALL;
-    CKD(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pick_stage(pass0, cfg->uv_adv_scheme, MODE_S2), BX, 0));
+    CKD(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pick_stage(pass0, cfg->uv_adv_scheme, MODE_S2), BX,
+                                                      (size_t)(64 + 2) * RC_N * sizeof(double)));
     per_sm = std::max(per_sm, 1);
     if (const char *ev = getenv("GMD_CTAS_PER_SM")) per_sm = std::max(1, atoi(ev));
     const int slots = nsm * per_sm;
@@ -940,6 +960,12 @@ int gmd_create(const gmd_config *cfg, gmd_model **out) {
     m->rows_per_cta = std::max(8, (m->nr + want - 1) / want);
     if (const char *ev = getenv("GMD_ROWS_PER_CTA")) m->rows_per_cta = std::max(1, atoi(ev));
     m->nchunks = (m->nr + m->rows_per_cta - 1) / m->rows_per_cta;
+    m->stage_smem = (size_t)(m->rows_per_cta + 2) * RC_N * sizeof(double);
+    if (m->stage_smem > 48 * 1024) {  // very tall chunks (tiny nlon): cap the chunk height instead of opting in to more smem
+      m->rows_per_cta = 48 * 1024 / (RC_N * (int)sizeof(double)) - 2;
+      m->nchunks = (m->nr + m->rows_per_cta - 1) / m->rows_per_cta;
+      m->stage_smem = (size_t)(m->rows_per_cta + 2) * RC_N * sizeof(double);
+    }
   }
   const size_t total = (size_t)m->nr * nlon;
   m->ew_blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)nsm * 8);
@@ -1422,7 +1448,7 @@ static int time_stage(gmd_model *m, int pass, int mode, int reps, float *ms_per_
   CK(cudaEventCreate(&e1));
   CK(cudaEventRecord(e0, m->stream));
   for (int k = 0; k < reps; k++) {
-    fn<<<grid, BX, 0, m->stream>>>(a);
+    fn<<<grid, BX, m->stage_smem, m->stream>>>(a);
     m->launches++;
   }
   CK(cudaEventRecord(e1, m->stream));

@@ -43,7 +43,16 @@ struct Tab {  // device pointers, already offset by TPAD: valid for j in [-TPAD,
   const double *r_fdlon, *hc_hdlat, *h_fdlon, *h_fdlat; // 1/fdlon, cosh/hdlat, 0.5/fdlon, 0.5/fdlat
   const double *r_fdlon2, *r_hdlon2, *r_fdlat2, *r_hdlat2; // unused in strict mode (diffusion)
   const unsigned char *flags;                           // FL_* per row
+  const double *rowrec;                                 // packed per-row record for k_stage, RC_N doubles per row
 };
+
+// packed row record (one 128-byte line per latitude row; copied to shared memory by k_stage)
+enum { RC_COSF = 0, RC_COSH, RC_FF, RC_FC, RC_Q_FDLON, RC_Q_FDLAT, RC_Q_HDLON, RC_Q_HDLAT, RC_COR1, RC_COR2,
+       RC_PGFU,   // product: 1/fdlon      strict: fdlon
+       RC_PGFV,   // product: cosh/hdlat   strict: hdlat
+       RC_MLON,   // product: 0.5/fdlon    strict: fdlon
+       RC_MLAT,   // product: 0.5/fdlat    strict: fdlat
+       RC_FLAGS, RC_PAD, RC_N };
 
 struct Geo {
   int nlon, nlat;
@@ -166,7 +175,7 @@ __device__ __forceinline__ double shfl_dn1(double v) { return __shfl_down_sync(0
 // tendencies of ONE column at row j; all operands are scalars already in registers
 template <int PASS, int ADV>
 __device__ __forceinline__ void tend_col(
-    const Tab &t, const int j, const bool rowU, const bool rowV, const bool rowG, const double bl, const double bt,
+    const double *__restrict__ rc, const bool rowU, const bool rowV, const bool rowG, const double bl, const double bt,
     const double hc0, const double hc1, const double hc2,
     // row j
     const double uw, const double uc, const double ue, const double Uw, const double Uc, const double Ue,
@@ -197,23 +206,23 @@ __device__ __forceinline__ void tend_col(
         const double v1 = (vs + vse) * hc0;
         const double v2 = (vc + ve) * hc1;
         if (ADV == ADV_CENTER) {
-          alon = t.q_fdlon[j] * (u2 * Ue - u1 * Uw);   // :378-384
-          alat = t.q_fdlat[j] * (v2 * Un - v1 * Us);   // :433-439
+          alon = rc[RC_Q_FDLON] * (u2 * Ue - u1 * Uw);   // :378-384
+          alat = rc[RC_Q_FDLAT] * (v2 * Un - v1 * Us);   // :433-439
         } else {
-          alon = t.q_fdlon[j] * (u2 * (Uc + Ue) - bl * fabs(u2) * (Ue - Uc) - u1 * (Uc + Uw) +
+          alon = rc[RC_Q_FDLON] * (u2 * (Uc + Ue) - bl * fabs(u2) * (Ue - Uc) - u1 * (Uc + Uw) +
                                  bl * fabs(u1) * (Uc - Uw) - (u2 - u1) * Uc);   // :395-404
-          alat = t.q_fdlat[j] * (v2 * (Uc + Un) - bt * fabs(v2) * (Un - Uc) - v1 * (Uc + Us) +
+          alat = rc[RC_Q_FDLAT] * (v2 * (Uc + Un) - bt * fabs(v2) * (Un - Uc) - v1 * (Uc + Us) +
                                  bt * fabs(v1) * (Uc - Us) - (v2 - v1) * Uc);   // :450-459
         }
       }
       dU = -alon - alat;
     }
     if (PASS != PASS_SLOW) {
-      const double fv = 0.25 * (t.ff[j] + t.fc[j] * uc) * (t.cor1[j] * (Vs + Vse) + t.cor2[j] * (Vc + Ve));  // :485-493
+      const double fv = 0.25 * (rc[RC_FF] + rc[RC_FC] * uc) * (rc[RC_COR1] * (Vs + Vse) + rc[RC_COR2] * (Vc + Ve));  // :485-493
 #if GMD_STRICT
-      const double pgf = 0.5 * (sc + se) / t.fdlon[j] * ghdx;  // :514-519
+      const double pgf = 0.5 * (sc + se) / rc[RC_PGFU] * ghdx;  // :514-519
 #else
-      const double pgf = 0.5 * (sc + se) * t.r_fdlon[j] * ghdx;
+      const double pgf = 0.5 * (sc + se) * rc[RC_PGFU] * ghdx;
 #endif
       dU = (PASS == PASS_ALL) ? (dU + fv - pgf) : (fv - pgf);
     }
@@ -232,25 +241,25 @@ __device__ __forceinline__ void tend_col(
         const double v1 = vh + vs * hc0;
         const double v2 = vh + vn * hc2;
         if (ADV == ADV_CENTER) {
-          alon = t.q_hdlon[j] * (u2 * Ve - u1 * Vw);   // :386-392
-          alat = t.q_hdlat[j] * (v2 * Vn - v1 * Vs);   // :441-447
+          alon = rc[RC_Q_HDLON] * (u2 * Ve - u1 * Vw);   // :386-392
+          alat = rc[RC_Q_HDLAT] * (v2 * Vn - v1 * Vs);   // :441-447
         } else {
-          alon = t.q_hdlon[j] * (u2 * (Vc + Ve) - bl * fabs(u2) * (Ve - Vc) - u1 * (Vc + Vw) +
+          alon = rc[RC_Q_HDLON] * (u2 * (Vc + Ve) - bl * fabs(u2) * (Ve - Vc) - u1 * (Vc + Vw) +
                                  bl * fabs(u1) * (Vc - Vw) - (u2 - u1) * Vc);   // :406-415
-          alat = t.q_hdlat[j] * (v2 * (Vc + Vn) - bt * fabs(v2) * (Vn - Vc) - v1 * (Vc + Vs) +
+          alat = rc[RC_Q_HDLAT] * (v2 * (Vc + Vn) - bt * fabs(v2) * (Vn - Vc) - v1 * (Vc + Vs) +
                                  bt * fabs(v1) * (Vc - Vs) - (v2 - v1) * Vc);   // :461-470
         }
       }
       dV = -alon - alat;
     }
     if (PASS != PASS_SLOW) {
-      const double f0 = t.ff[j], c0 = t.fc[j], f1 = t.ff[j + 1], c1 = t.fc[j + 1];
+      const double f0 = rc[RC_FF], c0 = rc[RC_FC], f1 = rc[RC_N + RC_FF], c1 = rc[RC_N + RC_FC];
       const double fu = 0.25 * ((f0 + c0 * uc) * Uc + (f0 + c0 * uw) * Uw + (f1 + c1 * un) * Un +
                                 (f1 + c1 * unw) * Unw);   // :495-503
 #if GMD_STRICT
-      const double pgf = 0.5 * (sc + sn) / t.hdlat[j] * hc1 * ghdy;  // :530-535
+      const double pgf = 0.5 * (sc + sn) / rc[RC_PGFV] * hc1 * ghdy;  // :530-535
 #else
-      const double pgf = 0.5 * (sc + sn) * t.hc_hdlat[j] * ghdy;
+      const double pgf = 0.5 * (sc + sn) * rc[RC_PGFV] * ghdy;
 #endif
       dV = (PASS == PASS_ALL) ? (dV - fu - pgf) : (-fu - pgf);
     }
@@ -258,11 +267,11 @@ __device__ __forceinline__ void tend_col(
   // ===================== dgd, full rows 1..nlat-2 (pole rows: k_polar) ====================================
   if (rowG) {
 #if GMD_STRICT
-    const double mlon = ((sc + se) * Uc - (sc + sw) * Uw) * 0.5 / t.fdlon[j];                   // :546-552
-    const double mlat = ((sc + sn) * Vc * hc1 - (sc + ss) * Vs * hc0) * 0.5 / t.fdlat[j];       // :564-570
+    const double mlon = ((sc + se) * Uc - (sc + sw) * Uw) * 0.5 / rc[RC_MLON];                   // :546-552
+    const double mlat = ((sc + sn) * Vc * hc1 - (sc + ss) * Vs * hc0) * 0.5 / rc[RC_MLAT];       // :564-570
 #else
-    const double mlon = ((sc + se) * Uc - (sc + sw) * Uw) * t.h_fdlon[j];
-    const double mlat = ((sc + sn) * Vc * hc1 - (sc + ss) * Vs * hc0) * t.h_fdlat[j];
+    const double mlon = ((sc + se) * Uc - (sc + sw) * Uw) * rc[RC_MLON];
+    const double mlat = ((sc + sn) * Vc * hc1 - (sc + ss) * Vs * hc0) * rc[RC_MLAT];
 #endif
     dG = -mlon - mlat;
   }
@@ -275,6 +284,7 @@ constexpr int BX = SW * 32;
 template <int PASS, int ADV, int MODE>
 __global__ void __launch_bounds__(BX, GMD_MINB) k_stage(const StageArgs a) {
   __shared__ double red[2 * SW];
+  extern __shared__ double srow[];  // row records of rows ja-1 .. jb: [(jb - ja + 2)][RC_N]
   const int nlon = a.g.nlon, nlat = a.g.nlat, r0 = a.g.r0;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int strip = blockIdx.x * SW + warp;
@@ -283,8 +293,13 @@ __global__ void __launch_bounds__(BX, GMD_MINB) k_stage(const StageArgs a) {
   const int jb = min(ja + a.rows_per_cta, a.g.r1);
   const bool need_gh = (PASS != PASS_SLOW);
   const bool upd = (MODE == MODE_S1 || MODE == MODE_S2);
-  const Tab &t = a.t;
   double ip1 = 0.0, ip2 = 0.0;
+  {
+    const int nrec = (jb - ja + 2) * RC_N;
+    const double *__restrict__ src = a.t.rowrec + (ptrdiff_t)(ja - 1) * RC_N;
+    for (int k = threadIdx.x; k < nrec; k += BX) srow[k] = __ldg(src + k);
+  }
+  __syncthreads();
 
   if (strip < nstrips) {
     int c0 = strip * WOUT - 2 + 2 * lane;  // even; (c0, c0+1) never straddles the seam because nlon is even
@@ -351,37 +366,18 @@ __global__ void __launch_bounds__(BX, GMD_MINB) k_stage(const StageArgs a) {
 
     GMD_UNROLL_PRAGMA(GMD_UNROLL)
     for (int j = ja; j < jb; j++) {
-      // ---- advance the window: s(j+2), U(j+1), V(j+1), gh(j+1), u(j+1), v(j+1) --------------------------
-      sq.x = fast_sqrt(n_gd2.x);
-      sq.y = fast_sqrt(n_gd2.y);
-      Up = n_U;
-      Vp = n_V;
-      if (need_gh) {
-#if GMD_STRICT
-        gp = n_gd1;
-        hp = n_hs;
-#else
-        gp.x = n_gd1.x + n_hs.x;
-        gp.y = n_gd1.y + n_hs.y;
-#endif
-      }
-      const double spe_b = shfl_dn1(sp.x);  // s(i+1, j+1) for column b
-      {
-        const bool uok = (j + 1 < nlat), vok = (j + 1 < nlat - 1);
-        up.x = uok ? two_a_over_b(Up.x, sp.x + sp.y) : 0.0;
-        up.y = uok ? two_a_over_b(Up.y, sp.y + spe_b) : 0.0;
-        vp.x = vok ? two_a_over_b(Vp.x, sp.x + sq.x) : 0.0;
-        vp.y = vok ? two_a_over_b(Vp.y, sp.y + sq.y) : 0.0;
-      }
-      // ---- prefetch the next row and the operands of this row's update ----------------------------------
-      if (need_gh) n_gd1 = n_gd2;  // gd(j+2) is next iteration's gd(j'+1)
+      // ---- issue every load of this iteration first: the next row of the evaluated state (consumed one
+      //      iteration later) and the operands of this row's update (consumed at the end of this iteration) ---
+      const D2 c_gd2 = n_gd2, c_U = n_U, c_V = n_V, c_gd1 = n_gd1, c_hs = n_hs;
+      if (need_gh) n_gd1 = c_gd2;  // gd(j+2) is next iteration's gd(j'+1)
       if (j + 1 < jb) {
         n_gd2 = ld2(AT(a.Egd, j + 3));
         n_U = ld2(AT(a.EU, j + 2));
         n_V = ld2(AT(a.EV, j + 2));
         if (need_gh) n_hs = ld2(AT(a.ghs, j + 2));
       }
-      const unsigned fl = t.flags[j];
+      const double *__restrict__ rc = srow + (j - ja + 1) * RC_N;
+      const unsigned fl = (unsigned)rc[RC_FLAGS];
       const bool rowU = (j >= 1 && j <= nlat - 2);
       const bool rowV = (j <= nlat - 2);
       const bool rowG = rowU && (PASS != PASS_SLOW);
@@ -409,6 +405,28 @@ __global__ void __launch_bounds__(BX, GMD_MINB) k_stage(const StageArgs a) {
           }
         }
       }
+      // ---- advance the window: s(j+2), U(j+1), V(j+1), gh(j+1), u(j+1), v(j+1) --------------------------
+      sq.x = fast_sqrt(c_gd2.x);
+      sq.y = fast_sqrt(c_gd2.y);
+      Up = c_U;
+      Vp = c_V;
+      if (need_gh) {
+#if GMD_STRICT
+        gp = c_gd1;
+        hp = c_hs;
+#else
+        gp.x = c_gd1.x + c_hs.x;
+        gp.y = c_gd1.y + c_hs.y;
+#endif
+      }
+      const double spe_b = shfl_dn1(sp.x);  // s(i+1, j+1) for column b
+      {
+        const bool uok = (j + 1 < nlat), vok = (j + 1 < nlat - 1);
+        up.x = uok ? two_a_over_b(Up.x, sp.x + sp.y) : 0.0;
+        up.y = uok ? two_a_over_b(Up.y, sp.y + spe_b) : 0.0;
+        vp.x = vok ? two_a_over_b(Vp.x, sp.x + sq.x) : 0.0;
+        vp.y = vok ? two_a_over_b(Vp.y, sp.y + sq.y) : 0.0;
+      }
       // ---- longitude neighbours of row j / j+1 ------------------------------------------------------------
       const double unw_a = shfl_up1(up.y);   // u(i-1, j+1) for a
       const double Unw_a = shfl_up1(Up.y);   // U(i-1, j+1)
@@ -435,16 +453,17 @@ __global__ void __launch_bounds__(BX, GMD_MINB) k_stage(const StageArgs a) {
         ghdy_b = gp.y - g0.y;
 #endif
       }
-      const double hc0 = t.cosh[j - 1], hc1 = t.cosh[j], hc2 = t.cosh[j + 1];
+      const double hc0 = rc[RC_COSH - RC_N], hc1 = rc[RC_COSH], hc2 = rc[RC_COSH + RC_N];
+      const double cfj = rc[RC_COSF];
       double dUa, dVa, dGa, dUb, dVb, dGb;
       // column a: west = lane-1's b (shuffled / carried), east = own b
-      tend_col<PASS, ADV>(t, j, rowU, rowV, rowG, a.beta_lon, a.beta_lat, hc0, hc1, hc2,
+      tend_col<PASS, ADV>(rc, rowU, rowV, rowG, a.beta_lon, a.beta_lat, hc0, hc1, hc2,
                           uw_a, u0.x, u0.y, Uw_a, U0.x, U0.y, Vw_a, V0.x, V0.y, sw_a, s0.x, s0.y, v0.x, v0.y,
                           Um.x, Vm.x, Vm.y, vm.x, vm.y, sm_.x,
                           Up.x, Unw_a, up.x, unw_a, Vp.x, vp.x, sp.x,
                           ghdx_a, ghdy_a, wul.x, wut.x, wvl.x, wvt.x, dUa, dVa, dGa);
       // column b: west = own a, east = lane+1's a (shuffled / carried)
-      tend_col<PASS, ADV>(t, j, rowU, rowV, rowG, a.beta_lon, a.beta_lat, hc0, hc1, hc2,
+      tend_col<PASS, ADV>(rc, rowU, rowV, rowG, a.beta_lon, a.beta_lat, hc0, hc1, hc2,
                           u0.x, u0.y, ue_b, U0.x, U0.y, Ue_b, V0.x, V0.y, Ve_b, s0.x, s0.y, se_b, v0.y, ve_b,
                           Um.y, Vm.y, Vse_b, vm.y, vse_b, sm_.y,
                           Up.y, Up.x, up.y, up.x, Vp.y, vp.y, sp.y,
@@ -457,10 +476,10 @@ __global__ void __launch_bounds__(BX, GMD_MINB) k_stage(const StageArgs a) {
             if (upd) st2(AT(a.NU, j), oU.x + a.dt * dUa, oU.y + a.dt * dUb);
             if (MODE != MODE_S1) st2(AT(a.TU, j), dUa, dUb);
             if (MODE == MODE_S3A) {
-              ip1 = ip1 + dUa * pU.x * t.cosf[j];
-              ip2 = ip2 + dUa * dUa * t.cosf[j];
-              ip1 = ip1 + dUb * pU.y * t.cosf[j];
-              ip2 = ip2 + dUb * dUb * t.cosf[j];
+              ip1 = ip1 + dUa * pU.x * cfj;
+              ip2 = ip2 + dUa * dUa * cfj;
+              ip1 = ip1 + dUb * pU.y * cfj;
+              ip2 = ip2 + dUb * dUb * cfj;
             }
           }
         } else if (upd) {
@@ -488,10 +507,10 @@ __global__ void __launch_bounds__(BX, GMD_MINB) k_stage(const StageArgs a) {
             if (upd) st2(AT(a.Ngd, j), oG.x + a.dt * dGa, oG.y + a.dt * dGb);
             if (MODE != MODE_S1) st2(AT(a.Tgd, j), dGa, dGb);
             if (MODE == MODE_S3A) {
-              ip1 = ip1 + dGa * pG.x * t.cosf[j];
-              ip2 = ip2 + dGa * dGa * t.cosf[j];
-              ip1 = ip1 + dGb * pG.y * t.cosf[j];
-              ip2 = ip2 + dGb * dGb * t.cosf[j];
+              ip1 = ip1 + dGa * pG.x * cfj;
+              ip2 = ip2 + dGa * dGa * cfj;
+              ip1 = ip1 + dGb * pG.y * cfj;
+              ip2 = ip2 + dGb * dGb * cfj;
             }
           }
         }

@@ -348,3 +348,47 @@ def test_two_band_decomposition_matches_oracle():
                          capture_output=True, text=True, timeout=600)
     print(res.stdout[-3000:], res.stderr[-3000:])
     assert res.returncode == 0
+
+
+def test_dycore_test_driver_end_to_end(tmp_path):
+    """The C++ `dycore_test` host program (namelist -> init -> IC plugin -> run -> final, src/dycore_test.F90) on the
+    as-shipped mountain-zonal-flow configuration (run/namelist.mz_test, 2 model days): log lines and h0 frames
+    against the oracle."""
+    import os
+    import subprocess
+    from scipy.io import netcdf_file
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "gamil_dycore_b200", "dycore_test")
+    res = subprocess.run([exe, os.path.join(root, "run", "namelist.mz_test")], capture_output=True, text=True,
+                         cwd=str(tmp_path), timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    lines = res.stdout.splitlines()
+    assert lines[0] == " [Notice]: Log module is initialized."
+    assert " [Notice]: Use mountain zonal flow initial condition." in lines
+    assert lines[-1] == " [Notice]: Dycore module is finalized."
+    steps = [l for l in lines if l.startswith(" => ")]
+    assert len(steps) == 241 and steps[0].startswith(" => 0001-01-01T00:00:00Z ") and steps[-1].startswith(" => 0001-01-03T00:00:00Z ")
+    assert len(steps[0].split()) == 4 and len(steps[1].split()) == 5      # beta appears from the first step on
+    kw = dict(num_lon=180, num_lat=90, time_step_size=720.0, subcycles=8, split_scheme="csp2", uv_adv_scheme="upwind",
+              uv_adv_upwind_lat_beta=0.1, zonal_tend_filter_cutoff_wavenumber=[4, 4, 4])
+    o = Oracle(OracleConfig(**kw))
+    o.set_initial_condition("mountain_zonal_flow")
+    o.run_init()
+    m0, e0, _ = o.diag()
+    assert abs(float(steps[0].split()[2]) / m0 - 1) < 1e-13 and abs(float(steps[0].split()[3]) / e0 - 1) < 1e-13
+    frames = sorted(p for p in os.listdir(tmp_path) if p.endswith(".nc"))
+    assert frames == ["mz_c_u_01.180x90.dt720.h0.0001-01-02T00:00:00Z.nc", "mz_c_u_01.180x90.dt720.h0.0001-01-03T00:00:00Z.nc"]
+    for k, name in enumerate(frames):
+        o.step(120)
+        f = netcdf_file(str(tmp_path / name), "r", mmap=False)
+        u, v, gd = o.state()
+        assert rel(f.variables["gh"][0], gd + o.ghs()) < 1e-12
+        assert rel(f.variables["u"][0], 0.5 * (u + np.roll(u, 1, axis=1))) < 1e-11
+        vor, div = o.vor_div()
+        assert rel(f.variables["vor"][0][:-1], vor) < 1e-9 and rel(f.variables["div"][0], div[:-1]) < 1e-8
+        m, e, _ = o.diag()
+        assert abs(f.variables["tm"][0] / m - 1) < 2e-13 and abs(f.variables["te"][0] / e - 1) < 2e-13
+        assert f.variables["time"][0] == float(k + 1)
+        last = steps[120 * (k + 1)].split()
+        # the log prints 14 significant digits (E20.14)
+        assert abs(float(last[2]) / m - 1) < 3e-13 and abs(float(last[3]) / e - 1) < 3e-13
