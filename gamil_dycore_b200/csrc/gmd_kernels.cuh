@@ -69,8 +69,11 @@ struct StageArgs {
   const double *PU, *PV, *Pgd;        // previous tendency for <tend, prev>
   const double *AUlon, *AUlat, *AVlon, *AVlat;  // WENO advection terms, precomputed
   double dt, beta_lon, beta_lat;
-  double *partials;  // [gridDim.x * gridDim.y][2]
+  double *partials;  // pairs {ip1, ip2}, one per CTA
   int rows_per_cta;
+  // row ranges of this launch, selected by blockIdx.z (boundary launches cover two disjoint ranges)
+  int rb[2], re[2];
+  int pofs[2];       // first partial slot of each range
 };
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -289,8 +292,16 @@ __global__ void __launch_bounds__(BX, GMD_MINB) k_stage(const StageArgs a) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int strip = blockIdx.x * SW + warp;
   const int nstrips = (nlon + WOUT - 1) / WOUT;
-  const int ja = r0 + blockIdx.y * a.rows_per_cta;
-  const int jb = min(ja + a.rows_per_cta, a.g.r1);
+  const int ja = a.rb[blockIdx.z] + blockIdx.y * a.rows_per_cta;
+  const int jb = min(ja + a.rows_per_cta, a.re[blockIdx.z]);
+  if (ja >= jb) {  // whole CTA: this range has fewer chunks than gridDim.y
+    if (MODE == MODE_S3A && threadIdx.x == 0) {
+      const size_t b = (size_t)a.pofs[blockIdx.z] + (size_t)blockIdx.y * gridDim.x + blockIdx.x;
+      a.partials[2 * b] = 0.0;
+      a.partials[2 * b + 1] = 0.0;
+    }
+    return;
+  }
   const bool need_gh = (PASS != PASS_SLOW);
   const bool upd = (MODE == MODE_S1 || MODE == MODE_S2);
   double ip1 = 0.0, ip2 = 0.0;
@@ -548,7 +559,7 @@ __global__ void __launch_bounds__(BX, GMD_MINB) k_stage(const StageArgs a) {
         q1 += red[2 * w];
         q2 += red[2 * w + 1];
       }
-      const size_t b = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
+      const size_t b = (size_t)a.pofs[blockIdx.z] + (size_t)blockIdx.y * gridDim.x + blockIdx.x;
       a.partials[2 * b] = q1;
       a.partials[2 * b + 1] = q2;
     }
@@ -827,6 +838,7 @@ struct UpdateArgs {
   double dt0;
   double *beta_out;   // device scalar, written by one thread
   int with_gd;        // 0: slow pass, gd is shared
+  int rb[2], re[2];   // up to two row ranges handled by this launch (empty when rb >= re)
 };
 
 __device__ __forceinline__ double beta_from_ip(const double *ip, int qcon) {
@@ -844,14 +856,17 @@ __global__ void __launch_bounds__(256) k_update(const UpdateArgs a) {
     if (blockIdx.x == 0 && threadIdx.x == 0 && a.beta_out) *a.beta_out = beta;
   }
   const int nlon = a.g.nlon, nlat = a.g.nlat;
-  const size_t nrow = (size_t)(a.g.r1 - a.g.r0);
-  const size_t total = nrow * (size_t)nlon;
-  for (ptrdiff_t k = (ptrdiff_t)blockIdx.x * 256 + threadIdx.x; k < (ptrdiff_t)total; k += (ptrdiff_t)gridDim.x * 256) {
-    const int j = a.g.r0 + (int)(k / (ptrdiff_t)nlon);
-    if (j >= 1 && j <= nlat - 2) a.NU[k] = a.OU[k] + dt * a.TU[k];
-    else a.NU[k] = a.OU[k];
-    if (j <= nlat - 2) a.NV[k] = a.OV[k] + dt * a.TV[k];
-    if (a.with_gd) a.Ngd[k] = a.Ogd[k] + dt * a.Tgd[k];
+#pragma unroll
+  for (int z = 0; z < 2; z++) {
+    if (a.rb[z] >= a.re[z]) continue;
+    const ptrdiff_t k0 = (ptrdiff_t)(a.rb[z] - a.g.r0) * nlon, k1 = (ptrdiff_t)(a.re[z] - a.g.r0) * nlon;
+    for (ptrdiff_t k = k0 + (ptrdiff_t)blockIdx.x * 256 + threadIdx.x; k < k1; k += (ptrdiff_t)gridDim.x * 256) {
+      const int j = a.g.r0 + (int)(k / (ptrdiff_t)nlon);
+      if (j >= 1 && j <= nlat - 2) a.NU[k] = a.OU[k] + dt * a.TU[k];
+      else a.NU[k] = a.OU[k];
+      if (j <= nlat - 2) a.NV[k] = a.OV[k] + dt * a.TV[k];
+      if (a.with_gd) a.Ngd[k] = a.Ogd[k] + dt * a.Tgd[k];
+    }
   }
 }
 
