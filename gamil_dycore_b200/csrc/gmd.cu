@@ -16,6 +16,7 @@
 #include <cstring>
 #include <map>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace gmd;
@@ -173,6 +174,16 @@ struct gmd_model {
   std::vector<GraphEntry> graphs;
   bool capturing = false;
   bool dry = false;  // bookkeeping-only pass of the step logic (graph replay): no launches
+
+  // host <-> device transfer lanes (pinned double buffers, one copy stream each)
+  struct Lane {
+    cudaStream_t s = nullptr;
+    double *pin[2] = {nullptr, nullptr};
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+  };
+  Lane lanes[4];
+  bool lanes_ready = false;
+  int lane_rows = 0;
 
   float last_ms = 0.f;
   bool span_open = false;
@@ -884,53 +895,143 @@ static int one_step(gmd_model *m) {
 // ---------------------------------------------------------------------------------------------------------
 // host <-> device field transfer
 // ---------------------------------------------------------------------------------------------------------
-// global host array (layout) -> band staging incl. ghost rows; nrows_valid = rows of the field on the globe
-static void pack_band(const gmd_model *m, const double *src, int layout, int nrows_valid, std::vector<double> &st) {
-  const int nlon = m->geo.nlon, r0 = m->geo.r0;
-  st.assign(m->fld_elems, 0.0);
-  for (int l = 0; l < m->nr + 2 * GHOST; l++) {
-    const int j = r0 - GHOST + l;
-    if (j < 0 || j >= nrows_valid) continue;
-    const double *row = (layout == GMD_LAYOUT_REFERENCE) ? src + (size_t)(j + 2) * (nlon + 4) + 2 : src + (size_t)j * nlon;
-    memcpy(&st[(size_t)l * nlon], row, (size_t)nlon * sizeof(double));
+// Host arrays are pageable and borrowed, so every field goes through a pinned double buffer on its own copy
+// stream ("lane"): a host thread per field packs chunk k+1 while the DMA engine moves chunk k, and the fields of
+// one set/get call travel concurrently.  This is what the end-to-end number (bench.py "e2e") pays per call.
+struct XferJob {
+  bool up;                 // host -> device (else device -> host)
+  const double *hsrc;      // up: global host array or NULL (zeros)
+  double *hdst;            // down: global host array
+  double *dev;             // device field pointer (row r0)
+  int layout, nrows_valid;
+  bool zero_poles;
+  cudaError_t err;
+};
+static int lanes_init(gmd_model *m) {
+  if (m->lanes_ready) return 0;
+  const int nlon = m->geo.nlon;
+  m->lane_rows = std::max(1, (int)((size_t)(4u << 20) / sizeof(double) / (size_t)nlon));
+  m->lane_rows = std::min(m->lane_rows, m->nr + 2 * GHOST);
+  for (auto &L : m->lanes) {
+    CK(cudaStreamCreateWithFlags(&L.s, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; k++) {
+      CK(cudaMallocHost(&L.pin[k], (size_t)m->lane_rows * nlon * sizeof(double)));
+      CK(cudaEventCreateWithFlags(&L.ev[k], cudaEventDisableTiming));
+    }
   }
-}
-static int upload_field(gmd_model *m, const double *src, int layout, int nrows_valid, double *dst) {
-  if (int rj = join(m)) return rj;
-  std::vector<double> st;
-  if (src) pack_band(m, src, layout, nrows_valid, st);
-  else st.assign(m->fld_elems, 0.0);
-  CK(cudaMemcpyAsync(dst - (size_t)GHOST * m->geo.nlon, st.data(), m->fld_elems * sizeof(double), cudaMemcpyHostToDevice,
-                     m->stream));
-  CK(cudaStreamSynchronize(m->stream));
+  m->lanes_ready = true;
   return 0;
 }
-// owned rows of a band field -> global host array
-static int download_field(gmd_model *m, const double *src, int layout, int nrows_valid, double *dst, bool zero_poles) {
-  if (!dst) return 0;
-  if (int rj = join(m)) return rj;
+static inline const double *host_row(const double *base, int layout, int nlon, int j) {
+  return (layout == GMD_LAYOUT_REFERENCE) ? base + (size_t)(j + 2) * (nlon + 4) + 2 : base + (size_t)j * nlon;
+}
+static void lane_upload(gmd_model *m, gmd_model::Lane &L, XferJob &job) {
+#define CKL(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { job.err = e_; return; } } while (0)
+  CKL(cudaSetDevice(m->dev));
   const int nlon = m->geo.nlon, r0 = m->geo.r0;
-  std::vector<double> st((size_t)m->nr * nlon);
-  CK(cudaMemcpyAsync(st.data(), src, st.size() * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
-  CK(cudaStreamSynchronize(m->stream));
-  for (int l = 0; l < m->nr; l++) {
-    const int j = r0 + l;
-    if (j >= nrows_valid) continue;
-    const double *row = &st[(size_t)l * nlon];
-    const bool zero = zero_poles && (j == 0 || j == m->geo.nlat - 1);
-    if (layout == GMD_LAYOUT_REFERENCE) {
-      double *d = dst + (size_t)(j + 2) * (nlon + 4);
-      for (int i = 0; i < nlon; i++) d[i + 2] = zero ? 0.0 : row[i];
+  double *base = job.dev - (size_t)GHOST * nlon;
+  // rows outside the globe (and a missing field) are zeros
+  CKL(cudaMemsetAsync(base, 0, m->fld_elems * sizeof(double), L.s));
+  if (job.hsrc) {
+    const int jlo = std::max(0, r0 - GHOST), jhi = std::min(job.nrows_valid, m->geo.r1 + GHOST);
+    int k = 0;
+    for (int ja = jlo; ja < jhi; ja += m->lane_rows, k++) {
+      const int jb = std::min(jhi, ja + m->lane_rows), b = k & 1;
+      if (k >= 2) CKL(cudaEventSynchronize(L.ev[b]));
+      if (job.layout == GMD_LAYOUT_COMPACT) {
+        memcpy(L.pin[b], job.hsrc + (size_t)ja * nlon, (size_t)(jb - ja) * nlon * sizeof(double));
+      } else {
+        for (int j = ja; j < jb; j++)
+          memcpy(L.pin[b] + (size_t)(j - ja) * nlon, host_row(job.hsrc, job.layout, nlon, j), (size_t)nlon * sizeof(double));
+      }
+      CKL(cudaMemcpyAsync(base + (size_t)(ja - (r0 - GHOST)) * nlon, L.pin[b], (size_t)(jb - ja) * nlon * sizeof(double),
+                          cudaMemcpyHostToDevice, L.s));
+      CKL(cudaEventRecord(L.ev[b], L.s));
+    }
+  }
+  CKL(cudaStreamSynchronize(L.s));
+}
+static void lane_unpack(const gmd_model *m, const XferJob &job, const double *pin, int ja, int jb) {
+  const int nlon = m->geo.nlon;
+  for (int j = ja; j < jb; j++) {
+    const double *row = pin + (size_t)(j - ja) * nlon;
+    const bool zero = job.zero_poles && (j == 0 || j == m->geo.nlat - 1);
+    if (job.layout == GMD_LAYOUT_REFERENCE) {
+      double *d = job.hdst + (size_t)(j + 2) * (nlon + 4);
+      if (zero) memset(d + 2, 0, (size_t)nlon * sizeof(double));
+      else memcpy(d + 2, row, (size_t)nlon * sizeof(double));
       d[0] = d[nlon];      // parallel_fill_halo, src/parallel_mod.F90:466-524
       d[1] = d[nlon + 1];
       d[nlon + 2] = d[2];
       d[nlon + 3] = d[3];
     } else {
-      double *d = dst + (size_t)j * nlon;
-      for (int i = 0; i < nlon; i++) d[i] = zero ? 0.0 : row[i];
+      double *d = job.hdst + (size_t)j * nlon;
+      if (zero) memset(d, 0, (size_t)nlon * sizeof(double));
+      else memcpy(d, row, (size_t)nlon * sizeof(double));
     }
   }
+}
+static void lane_download(gmd_model *m, gmd_model::Lane &L, XferJob &job) {
+  CKL(cudaSetDevice(m->dev));
+  const int nlon = m->geo.nlon, r0 = m->geo.r0;
+  const int jlo = r0, jhi = std::min(job.nrows_valid, m->geo.r1);
+  int k = 0, pja = 0, pjb = 0;
+  for (int ja = jlo; ja < jhi; ja += m->lane_rows, k++) {
+    const int jb = std::min(jhi, ja + m->lane_rows), b = k & 1;
+    CKL(cudaMemcpyAsync(L.pin[b], job.dev + (size_t)(ja - r0) * nlon, (size_t)(jb - ja) * nlon * sizeof(double),
+                        cudaMemcpyDeviceToHost, L.s));
+    CKL(cudaEventRecord(L.ev[b], L.s));
+    if (k >= 1) {  // unpack the previous chunk while this one is in flight
+      CKL(cudaEventSynchronize(L.ev[b ^ 1]));
+      lane_unpack(m, job, L.pin[b ^ 1], pja, pjb);
+    }
+    pja = ja;
+    pjb = jb;
+  }
+  if (k >= 1) {
+    CKL(cudaEventSynchronize(L.ev[(k - 1) & 1]));
+    lane_unpack(m, job, L.pin[(k - 1) & 1], pja, pjb);
+  }
+#undef CKL
+}
+// run up to 4 transfers concurrently; the compute streams are drained first and the call returns when all are done
+static int run_xfers(gmd_model *m, XferJob *jobs, int n) {
+  int r;
+  if ((r = lanes_init(m))) return r;
+  if ((r = join(m))) return r;
+  CK(cudaStreamSynchronize(m->stream));
+  std::thread th[4];
+  for (int k = 0; k < n; k++) {
+    jobs[k].err = cudaSuccess;
+    if (k == n - 1) {  // the calling thread takes the last one
+      if (jobs[k].up) lane_upload(m, m->lanes[k], jobs[k]);
+      else lane_download(m, m->lanes[k], jobs[k]);
+    } else {
+      th[k] = std::thread([m, jobs, k]() {
+        if (jobs[k].up) lane_upload(m, m->lanes[k], jobs[k]);
+        else lane_download(m, m->lanes[k], jobs[k]);
+      });
+    }
+  }
+  for (int k = 0; k + 1 < n; k++) th[k].join();
+  for (int k = 0; k < n; k++)
+    if (jobs[k].err != cudaSuccess)
+      return fail(GMD_ERR_CUDA, "CUDA error %s in host<->device field transfer (%s)", cudaGetErrorName(jobs[k].err),
+                  cudaGetErrorString(jobs[k].err));
   return 0;
+}
+static XferJob up_job(const double *src, int layout, int nrows_valid, double *dst) {
+  XferJob j = {true, src, nullptr, dst, layout, nrows_valid, false, cudaSuccess};
+  return j;
+}
+// up to 3 device fields -> global host arrays (NULL destinations are skipped)
+static int download_fields(gmd_model *m, int n, double *const dev[], double *const host[], const int nrows_valid[],
+                           const bool zero_poles[], int layout) {
+  XferJob jobs[4];
+  int nj = 0;
+  for (int k = 0; k < n; k++)
+    if (host[k]) jobs[nj++] = XferJob{false, nullptr, host[k], dev[k], layout, nrows_valid[k], zero_poles[k], cudaSuccess};
+  return nj ? run_xfers(m, jobs, nj) : 0;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -972,6 +1073,13 @@ void gmd_destroy(gmd_model *m) {
   if (m->ev0) cudaEventDestroy(m->ev0);
   if (m->ev1) cudaEventDestroy(m->ev1);
   for (auto e : m->evpool) cudaEventDestroy(e);
+  for (auto &L : m->lanes) {
+    for (int k = 0; k < 2; k++) {
+      if (L.pin[k]) cudaFreeHost(L.pin[k]);
+      if (L.ev[k]) cudaEventDestroy(L.ev[k]);
+    }
+    if (L.s) cudaStreamDestroy(L.s);
+  }
   if (m->stream2) cudaStreamDestroy(m->stream2);
   if (m->own_stream) cudaStreamDestroy(m->own_stream);
   delete m;
@@ -1153,12 +1261,24 @@ int gmd_set_graph_mode(gmd_model *m, int on) {
 
 static int diag_now(gmd_model *m) { return diag(m, m->cur, 0); }
 
+// fetch the ring slots of the last n steps into h (full ring layout); one slot costs one 24-byte copy
+static int ring_fetch(gmd_model *m, int n, std::vector<double> &h) {
+  h.resize((size_t)3 * gmd_model::RING);
+  if (n <= 1) {
+    const int slot = m->step % gmd_model::RING;
+    CK(cudaMemcpyAsync(&h[3 * (size_t)slot], m->d_ring + 3 * (size_t)slot, 3 * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+  } else {
+    CK(cudaMemcpyAsync(h.data(), m->d_ring, h.size() * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+  }
+  CK(cudaStreamSynchronize(m->stream));
+  return 0;
+}
+
 static int check_nan_last(gmd_model *m, int n) {
   // diag_run NaN abort, src/diag_mod.F90:79-87
   n = std::min(n, (int)gmd_model::RING);
-  std::vector<double> h((size_t)3 * gmd_model::RING);
-  CK(cudaMemcpyAsync(h.data(), m->d_ring, h.size() * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
-  CK(cudaStreamSynchronize(m->stream));
+  std::vector<double> h;
+  if (int r = ring_fetch(m, n, h)) return r;
   for (int k = 0; k < n; k++) {
     const int slot = (m->step - k) % gmd_model::RING;
     if (slot < 0) break;
@@ -1182,10 +1302,11 @@ int gmd_set_state(gmd_model *m, const double *u, const double *v, const double *
       if (row[i] != 0.0) return fail(GMD_ERR_ARG, "u must be 0 on the pole rows (row %d, column %d is %g)", j, i, row[i]);
   }
   if ((r = ensure_uv(m))) return r;
-  if ((r = upload_field(m, u, layout, nlat, m->w_u))) return r;
-  if ((r = upload_field(m, v, layout, nlat - 1, m->w_v))) return r;
-  if ((r = upload_field(m, gd, layout, nlat, m->cur.gd))) return r;
-  if ((r = upload_field(m, ghs, layout, nlat, m->ghs))) return r;
+  {
+    XferJob jobs[4] = {up_job(u, layout, nlat, m->w_u), up_job(v, layout, nlat - 1, m->w_v),
+                       up_job(gd, layout, nlat, m->cur.gd), up_job(ghs, layout, nlat, m->ghs)};
+    if ((r = run_xfers(m, jobs, 4))) return r;
+  }
   // iap_transform on owned + ghost rows inside the globe (src/types_mod.F90:399-426)
   Geo g = m->geo;
   g.r0 = std::max(m->geo.r0 - 1, 0);
@@ -1337,9 +1458,8 @@ int gmd_get_diag_series(gmd_model *m, int n, double *mass, double *energy, doubl
   if (n < 0 || n > gmd_model::RING || n > m->step + 1) return fail(GMD_ERR_ARG, "bad series length %d", n);
   int r = set_dev(m);
   if (r) return r;
-  std::vector<double> h((size_t)3 * gmd_model::RING);
-  CK(cudaMemcpyAsync(h.data(), m->d_ring, h.size() * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
-  CK(cudaStreamSynchronize(m->stream));
+  std::vector<double> h;
+  if ((r = ring_fetch(m, n, h))) return r;
   for (int k = 0; k < n; k++) {
     const int slot = (m->step - (n - 1 - k)) % gmd_model::RING;
     if (mass) mass[k] = h[3 * (size_t)slot];
@@ -1362,9 +1482,11 @@ int gmd_get_state(gmd_model *m, double *u, double *v, double *gd, int layout) {
   if (r) return r;
   if ((r = derive_uv(m, m->cur))) return r;
   const int nlat = m->geo.nlat;
-  if ((r = download_field(m, m->w_u, layout, nlat, u, false))) return r;
-  if ((r = download_field(m, m->w_v, layout, nlat - 1, v, false))) return r;
-  return download_field(m, m->cur.gd, layout, nlat, gd, false);
+  double *const dev[3] = {m->w_u, m->w_v, m->cur.gd};
+  double *const host[3] = {u, v, gd};
+  const int rows[3] = {nlat, nlat - 1, nlat};
+  const bool zp[3] = {false, false, false};
+  return download_fields(m, 3, dev, host, rows, zp, layout);
 }
 
 int gmd_get_iap_state(gmd_model *m, double *iu, double *iv, double *igd, int layout) {
@@ -1373,19 +1495,21 @@ int gmd_get_iap_state(gmd_model *m, double *iu, double *iv, double *igd, int lay
   int r = set_dev(m);
   if (r) return r;
   const int nlat = m->geo.nlat;
-  if ((r = download_field(m, m->cur.U, layout, nlat, iu, false))) return r;
-  if ((r = download_field(m, m->cur.V, layout, nlat - 1, iv, false))) return r;
+  double *tmp = nullptr;
   if (igd) {
-    double *tmp = nullptr;
     if ((r = acquire(m, KIND_G, &tmp))) return r;
+    if ((r = join(m))) return r;
     k_derive<<<m->ew_blocks, 256, 0, m->stream>>>(m->geo, m->geo.r0, m->geo.r1, m->cur.U, m->cur.V, m->cur.gd, nullptr,
                                                  nullptr, tmp);
     if ((r = post_launch(m))) return r;
-    r = download_field(m, tmp, layout, nlat, igd, false);
-    release(m, tmp);
-    if (r) return r;
   }
-  return 0;
+  double *const dev[3] = {m->cur.U, m->cur.V, tmp};
+  double *const host[3] = {iu, iv, igd};
+  const int rows[3] = {nlat, nlat - 1, nlat};
+  const bool zp[3] = {false, false, false};
+  r = download_fields(m, 3, dev, host, rows, zp, layout);
+  if (tmp) release(m, tmp);
+  return r;
 }
 
 int gmd_get_vor_div(gmd_model *m, double *vor, double *div, int layout) {
@@ -1400,8 +1524,13 @@ int gmd_get_vor_div(gmd_model *m, double *vor, double *div, int layout) {
   k_vor_div<<<m->ew_blocks, 256, 0, m->stream>>>(m->geo, m->tab, m->w_u, m->w_v, dv, dd);
   if ((r = post_launch(m))) return r;
   const int nlat = m->geo.nlat;
-  r = download_field(m, dv, layout, nlat - 1, vor, false);
-  if (!r) r = download_field(m, dd, layout, nlat, div, false);
+  {
+    double *const dev[2] = {dv, dd};
+    double *const host[2] = {vor, div};
+    const int rows[2] = {nlat - 1, nlat};
+    const bool zp[2] = {false, false};
+    r = download_fields(m, 2, dev, host, rows, zp, layout);
+  }
   release(m, dv);
   release(m, dd);
   return r;
@@ -1418,9 +1547,11 @@ int gmd_space_operators(gmd_model *m, int pass, double *du, double *dv, double *
   if (pass == PASS_SLOW) CK(cudaMemsetAsync(m->tendNew.gd, 0, bytes, m->stream));  // dgd = 0, :297
   if ((r = stage(m, pass, MODE_EVAL, m->cur, nullptr, 0.0, nullptr, &m->tendNew, nullptr))) return r;
   const int nlat = m->geo.nlat;
-  if ((r = download_field(m, m->tendNew.U, layout, nlat, du, true))) return r;
-  if ((r = download_field(m, m->tendNew.V, layout, nlat - 1, dv, false))) return r;
-  return download_field(m, m->tendNew.gd, layout, nlat, dgd, false);
+  double *const dev[3] = {m->tendNew.U, m->tendNew.V, m->tendNew.gd};
+  double *const host[3] = {du, dv, dgd};
+  const int rows[3] = {nlat, nlat - 1, nlat};
+  const bool zp[3] = {true, false, false};
+  return download_fields(m, 3, dev, host, rows, zp, layout);
 }
 
 int gmd_predict_correct(gmd_model *m, double dt, int pass) {

@@ -375,7 +375,8 @@ def test_dycore_test_driver_end_to_end(tmp_path):
     o.set_initial_condition("mountain_zonal_flow")
     o.run_init()
     m0, e0, _ = o.diag()
-    assert abs(float(steps[0].split()[2]) / m0 - 1) < 1e-13 and abs(float(steps[0].split()[3]) / e0 - 1) < 1e-13
+    # the log prints 14 significant digits (E20.14); the oracle sums serially, the GPU in a fixed tree
+    assert abs(float(steps[0].split()[2]) / m0 - 1) < 3e-13 and abs(float(steps[0].split()[3]) / e0 - 1) < 3e-13
     frames = sorted(p for p in os.listdir(tmp_path) if p.endswith(".nc"))
     assert frames == ["mz_c_u_01.180x90.dt720.h0.0001-01-02T00:00:00Z.nc", "mz_c_u_01.180x90.dt720.h0.0001-01-03T00:00:00Z.nc"]
     for k, name in enumerate(frames):
