@@ -120,8 +120,9 @@ struct gmd_model {
   int ncoef_max = 0;
 
   // polar items: [0] all/fast pass, [1] slow pass, [2] plain filter (diffusion)
-  PolarItem *d_items[3] = {nullptr, nullptr, nullptr};
+  std::vector<unsigned> items[3];  // packed (kind, row, cutoff), passed in the kernel parameters
   int n_items[3] = {0, 0, 0};
+  double *d_rot = nullptr;         // [PQ][KF][2] rotation table of the fast projector
 
   // buffers
   std::vector<double *> free_[3];
@@ -340,9 +341,12 @@ static int build_tables(gmd_model *m) {
   const int cmax = std::max(M.cutoff_max, 0);
   m->ncoef_max = 2 * (cmax + 1);
   {
-    std::vector<double> B((size_t)m->ncoef_max * nlon);
+    // one row more than the projector keeps (sin of the highest wavenumber): the fast path of k_polar rotates
+    // (cos, sin) pairs
+    const int nrows_b = m->ncoef_max + 1;
+    std::vector<double> B((size_t)nrows_b * nlon);
     const long double twopi = 8.0L * atanl(1.0L);
-    for (int mm = 0; mm < m->ncoef_max; mm++) {
+    for (int mm = 0; mm < nrows_b; mm++) {
       const int k = (mm + 1) / 2;
       for (int i = 0; i < nlon; i++) {
         const long long rr = ((long long)k * i) % nlon;  // exact argument reduction
@@ -352,16 +356,27 @@ static int build_tables(gmd_model *m) {
     }
     CK(cudaMalloc(&m->d_basis, B.size() * sizeof(double)));
     CK(cudaMemcpy(m->d_basis, B.data(), B.size() * sizeof(double), cudaMemcpyHostToDevice));
+    // rot[q][k-1] = (cos, sin)(2 pi k (q PT) / nlon): basis(i + q PT) = basis(i) rotated
+    std::vector<double> R((size_t)PQ * KF * 2);
+    for (int q = 0; q < PQ; q++)
+      for (int k = 1; k <= KF; k++) {
+        const long long rr = ((long long)k * q * PT) % nlon;
+        const long double ang = twopi * (long double)rr / (long double)nlon;
+        R[((size_t)q * KF + (k - 1)) * 2] = (double)cosl(ang);
+        R[((size_t)q * KF + (k - 1)) * 2 + 1] = (double)sinl(ang);
+      }
+    CK(cudaMalloc(&m->d_rot, R.size() * sizeof(double)));
+    CK(cudaMemcpy(m->d_rot, R.data(), R.size() * sizeof(double), cudaMemcpyHostToDevice));
   }
 
   // polar items for this band
   const int r0 = m->geo.r0, r1 = m->geo.r1;
-  std::vector<PolarItem> it[3];
+  std::vector<unsigned> *it = m->items;
   for (int j = r0; j < r1; j++) {
     const bool fullrow = (j >= 1 && j <= nlat - 2);
     if (fullrow && M.flag_full[(size_t)j]) {
-      PolarItem a = {IT_DU, j, M.cut_full[(size_t)j], 0};
-      PolarItem g = {IT_DGD, j, M.cut_full[(size_t)j], 0};
+      const unsigned a = pack_item(IT_DU, j, M.cut_full[(size_t)j]);
+      const unsigned g = pack_item(IT_DGD, j, M.cut_full[(size_t)j]);
       it[0].push_back(a);
       it[0].push_back(g);
       it[1].push_back(a);
@@ -369,20 +384,17 @@ static int build_tables(gmd_model *m) {
       it[2].push_back(g);
     }
     if (j <= nlat - 2 && M.flag_half[(size_t)j]) {
-      PolarItem v = {IT_DV, j, M.cut_half[(size_t)j], 0};
+      const unsigned v = pack_item(IT_DV, j, M.cut_half[(size_t)j]);
       it[0].push_back(v);
       it[1].push_back(v);
       it[2].push_back(v);
     }
-    if (j == 0) it[0].push_back(PolarItem{IT_POLE_S, j, -1, 0});
-    if (j == nlat - 1) it[0].push_back(PolarItem{IT_POLE_N, j, -1, 0});
+    if (j == 0) it[0].push_back(pack_item(IT_POLE_S, j, -1));
+    if (j == nlat - 1) it[0].push_back(pack_item(IT_POLE_N, j, -1));
   }
   for (int k = 0; k < 3; k++) {
     m->n_items[k] = (int)it[k].size();
-    if (m->n_items[k]) {
-      CK(cudaMalloc(&m->d_items[k], it[k].size() * sizeof(PolarItem)));
-      CK(cudaMemcpy(m->d_items[k], it[k].data(), it[k].size() * sizeof(PolarItem), cudaMemcpyHostToDevice));
-    }
+    if (m->n_items[k] > MAX_ITEMS) return fail(GMD_ERR_STATE, "internal: %d polar-row items exceed %d", m->n_items[k], MAX_ITEMS);
   }
   return 0;
 }
@@ -545,6 +557,27 @@ static int weno_terms(gmd_model *m, const State &E) {
   return 0;
 }
 
+// polar-row kernel launch: items in the parameters, rows (x, w and, if it fits, the prefetched base row) in smem
+static size_t polar_smem(const gmd_model *m, int *use_q) {
+  const size_t row = (size_t)m->geo.nlon * sizeof(double);
+  *use_q = (3 * row <= 200 * 1024) ? 1 : 0;
+  return (*use_q ? 3 : 2) * row;
+}
+static void fill_items(PolarArgs &p, const std::vector<unsigned> &v) {
+  for (size_t k = 0; k < v.size() && k < (size_t)MAX_ITEMS; k++) p.items[k] = v[k];
+}
+static void launch_polar(gmd_model *m, int mode, int nitems, PolarArgs &p, cudaStream_t st) {
+  p.basis = m->d_basis;
+  p.rot = m->d_rot;
+  const size_t sh = polar_smem(m, &p.use_q);
+  switch (mode) {
+    case MODE_S1: k_polar<MODE_S1><<<nitems, PT, sh, st>>>(p); break;
+    case MODE_S2: k_polar<MODE_S2><<<nitems, PT, sh, st>>>(p); break;
+    case MODE_S3A: k_polar<MODE_S3A><<<nitems, PT, sh, st>>>(p); break;
+    default: k_polar<MODE_EVAL><<<nitems, PT, sh, st>>>(p); break;
+  }
+}
+
 // one fused operator evaluation (+ update / store / dots) of state E
 static int stage(gmd_model *m, int pass, int mode, const State &E, const State *O, double dt, State *N, Tend *T,
                  const Tend *P) {
@@ -600,8 +633,7 @@ static int stage(gmd_model *m, int pass, int mode, const State &E, const State *
     memset(&p, 0, sizeof p);
     p.g = m->geo;
     p.t = m->tab;
-    p.items = m->d_items[li];
-    p.basis = m->d_basis;
+    fill_items(p, m->items[li]);
     p.EU = a.EU; p.EV = a.EV; p.Egd = a.Egd; p.ghs = a.ghs;
     p.OU = a.OU; p.OV = a.OV; p.Ogd = a.Ogd;
     p.NU = a.NU; p.NV = a.NV; p.Ngd = a.Ngd;
@@ -612,13 +644,7 @@ static int stage(gmd_model *m, int pass, int mode, const State &E, const State *
     p.rescale = 1;
     p.radius = m->mesh.radius;
     p.dlat = m->mesh.dlat;
-    const size_t sh = 2 * (size_t)m->geo.nlon * sizeof(double);
-    switch (mode) {
-      case MODE_S1: if (!m->dry) k_polar<MODE_S1><<<m->n_items[li], PT, sh, m->stream>>>(p); break;
-      case MODE_S2: if (!m->dry) k_polar<MODE_S2><<<m->n_items[li], PT, sh, m->stream>>>(p); break;
-      case MODE_S3A: if (!m->dry) k_polar<MODE_S3A><<<m->n_items[li], PT, sh, m->stream>>>(p); break;
-      default: if (!m->dry) k_polar<MODE_EVAL><<<m->n_items[li], PT, sh, m->stream>>>(p); break;
-    }
+    if (!m->dry) launch_polar(m, mode, m->n_items[li], p, m->stream);
     if ((r = post_launch(m))) return r;
   }
   if (mode == MODE_S3A) {
@@ -802,13 +828,11 @@ static int polar_filter_only(gmd_model *m, double *ud, double *vd, double *gdd) 
   memset(&p, 0, sizeof p);
   p.g = m->geo;
   p.t = m->tab;
-  p.items = m->d_items[2];
-  p.basis = m->d_basis;
+  fill_items(p, m->items[2]);
   p.TU = ud; p.TV = vd; p.Tgd = gdd;
   p.rescale = 0;
   p.partials = m->d_partials;
-  const size_t sh = 2 * (size_t)m->geo.nlon * sizeof(double);
-  if (!m->dry) k_polar<MODE_EVAL><<<m->n_items[2], PT, sh, m->stream>>>(p);
+  if (!m->dry) launch_polar(m, MODE_EVAL, m->n_items[2], p, m->stream);
   return post_launch(m);
 }
 
@@ -1066,7 +1090,7 @@ void gmd_destroy(gmd_model *m) {
   for (double *p : m->tab_allocs) cudaFree(p);
   cudaFree(m->d_flags_alloc);
   cudaFree(m->d_basis);
-  for (int k = 0; k < 3; k++) cudaFree(m->d_items[k]);
+  cudaFree(m->d_rot);
   cudaFree(m->d_partials);
   cudaFree(m->d_ip);
   cudaFree(m->d_ring);
@@ -1591,31 +1615,24 @@ int gmd_filter_row(gmd_model *m, int half, int row0, double *x) {
   if (r) return r;
   double *buf = nullptr;
   if ((r = acquire(m, KIND_G, &buf))) return r;
-  PolarItem it = {IT_DGD, m->geo.r0, half ? m->mesh.cut_half[(size_t)row0] : m->mesh.cut_full[(size_t)row0], 0};
-  PolarItem *dit = nullptr;
-  CK(cudaMalloc(&dit, sizeof it));
-  CK(cudaMemcpyAsync(dit, &it, sizeof it, cudaMemcpyHostToDevice, m->stream));
+  const int cutoff = half ? m->mesh.cut_half[(size_t)row0] : m->mesh.cut_full[(size_t)row0];
   CK(cudaMemcpyAsync(buf, x, (size_t)nlon * sizeof(double), cudaMemcpyHostToDevice, m->stream));
   PolarArgs p;
   memset(&p, 0, sizeof p);
   p.g = m->geo;
   p.t = m->tab;
-  p.items = dit;
-  p.basis = m->d_basis;
+  p.items[0] = pack_item(IT_DGD, m->geo.r0, cutoff);
   p.Tgd = buf;
   p.rescale = 0;
   p.partials = m->d_partials;
-  if (2 * (it.cutoff + 1) > m->ncoef_max && it.cutoff >= 0) {
-    cudaFree(dit);
+  if (2 * (cutoff + 1) > m->ncoef_max && cutoff >= 0) {
     release(m, buf);
     return fail(GMD_ERR_STATE, "internal: basis too small");
   }
-  k_polar<MODE_EVAL><<<1, PT, 2 * (size_t)nlon * sizeof(double), m->stream>>>(p);
+  launch_polar(m, MODE_EVAL, 1, p, m->stream);
   if ((r = post_launch(m))) return r;
   CK(cudaMemcpyAsync(x, buf, (size_t)nlon * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
   CK(cudaStreamSynchronize(m->stream));
-  // restore the buffer's zero rows invariant is not needed: row r0 of a G buffer is ordinary data
-  cudaFree(dit);
   release(m, buf);
   return 0;
 }

@@ -14,6 +14,7 @@
 // lets ptxas contract a*b+c into DFMA.
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda_pipeline.h>
 #include <stdint.h>
 
 #ifndef GMD_STRICT
@@ -576,20 +577,25 @@ __global__ void __launch_bounds__(BX, GMD_MINB) k_stage(const StageArgs a) {
 // (2c+2 dot products with a host-precomputed basis + reconstruction): same result to rounding, no
 // butterflies, and the row never leaves shared memory.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int PT = 1024;      // threads per polar-row CTA
-constexpr int PT_EW = 256;   // threads of the small pole-cap kernels
-constexpr int PB = 4;        // row elements per thread per batch (independent loads in flight)
+constexpr int PT = 512;       // threads per polar-row CTA (one CTA per SM: <= 128 registers per thread)
+constexpr int PT_EW = 256;    // threads of the small pole-cap kernels
+constexpr int PB = 4;         // row elements per thread per batch (independent loads in flight)
+constexpr int KF = 6;         // fast projector: wavenumbers 1..KF, i.e. cutoff <= KF-1 ...
+constexpr int PQ = 16;        // ... on rows of up to PT*PQ elements
+constexpr int MAX_ITEMS = 128;
 enum { IT_DU = 0, IT_DV = 1, IT_DGD = 2, IT_POLE_S = 3, IT_POLE_N = 4 };
 
-struct PolarItem {
-  int kind, row, cutoff, pad;
-};
+// one (row, field) work item, packed so that the whole list travels in the kernel parameters (no dependent
+// global load at the head of the latency chain): bits 0-15 row, 16-24 cutoff+1, 28-30 kind
+__host__ __device__ inline unsigned pack_item(int kind, int row, int cutoff) {
+  return (unsigned)row | ((unsigned)(cutoff + 1) << 16) | ((unsigned)kind << 28);
+}
 
 struct PolarArgs {
   Geo g;
   Tab t;
-  const PolarItem *items;
-  const double *basis;  // [2*cmax+2][nlon]: row 0 = 1, 2k-1 = cos(k x_i), 2k = sin(k x_i)
+  const double *basis;  // [2*cmax+3][nlon]: row 0 = 1, 2k-1 = cos(k x_i), 2k = sin(k x_i), x_i = 2 pi i / nlon
+  const double *rot;    // [PQ][KF][2]: cos, sin of 2 pi k (q PT) / nlon  (k = 1..KF): basis(i0 + q PT) from basis(i0)
   const double *EU, *EV, *Egd, *ghs;
   const double *OU, *OV, *Ogd;
   double *NU, *NV, *Ngd;
@@ -598,12 +604,14 @@ struct PolarArgs {
   double dt;
   double *partials;       // [nitems][2]
   int rescale;            // 1: tendency filter with inner-product rescale; 0: plain filter (diffusion)
+  int use_q;              // dynamic shared memory holds a third row (prefetched base-state / previous-tendency row)
   double radius, dlat;
+  unsigned items[MAX_ITEMS];
 };
 
-// Project x[0..n) (shared) onto the kept modes, result overwrites x.  The 2c+2 dot products are spread over
-// the CTA's warps (one (coefficient, segment) item per warp, fixed summation order => deterministic); all
-// basis loads are read-only-path loads that the compiler may hoist and batch.
+// General projector (any cutoff, any row length): project x[0..n) (shared) onto the kept modes, result overwrites
+// x.  The 2c+2 dot products are spread over the CTA's warps (one (coefficient, segment) item per warp, fixed
+// summation order => deterministic) with the basis streamed from L2.
 __device__ inline void project_row(double *x, int n, int cutoff, const double *__restrict__ basis, double *coef,
                                    double *part) {
   const int K = cutoff + 1;  // highest (cosine-only) wavenumber kept
@@ -662,36 +670,44 @@ __device__ inline void project_row(double *x, int n, int cutoff, const double *_
   __syncthreads();
 }
 
+// Latency is what this kernel is about (it sits between two stage launches): the item comes from the kernel
+// parameters, the base-state row is prefetched into shared memory with cp.async while the projection runs, and
+// for the cutoffs the reference ships (<= KF-1) the projector runs on THREAD-OWNED elements: thread t owns
+// i = t + q PT, loads the 2K basis values of i = t once (coalesced, 2K PT doubles per CTA instead of 2K n, twice)
+// and turns them to i = t + q PT by one complex rotation with a tiny host-built table, so the inner product s1
+// and all 2K+1 dot products come out of ONE block reduction and the reconstruction needs no further loads.
 template <int MODE>
-__global__ void __launch_bounds__(PT) k_polar(const PolarArgs a) {
-  extern __shared__ double psm[];  // x[n], w[n]
+__global__ void __launch_bounds__(PT) k_polar(const __grid_constant__ PolarArgs a) {
+  extern __shared__ double psm[];  // x[n], w[n] (, q[n])
   __shared__ double red[32];
   __shared__ double coef[512];
   __shared__ double part[512];
+  __shared__ double rot_s[PQ * KF * 2];
   __shared__ double bc[2];
-  const PolarItem it = a.items[blockIdx.x];
+  const unsigned pk = a.items[blockIdx.x];
+  const int j = (int)(pk & 0xffffu), cutoff = (int)((pk >> 16) & 0x1ffu) - 1, kind = (int)(pk >> 28);
   const int n = a.g.nlon, r0 = a.g.r0;
+  const int tid = threadIdx.x;
   double *x = psm, *w = psm + n;
-  const int j = it.row;
   const ptrdiff_t off = (ptrdiff_t)(j - r0) * (ptrdiff_t)n;
   double ip1 = 0.0, ip2 = 0.0;
 
-  if (it.kind == IT_POLE_S || it.kind == IT_POLE_N) {
+  if (kind == IT_POLE_S || kind == IT_POLE_N) {
     // src/dycore_mod.F90:572-596: zonal sum of the single adjacent flux, broadcast along the pole row
     const double *__restrict__ g0 = a.Egd + off;
-    const double *__restrict__ g1 = (it.kind == IT_POLE_S) ? a.Egd + off + n : a.Egd + off - n;
-    const double *__restrict__ vv = (it.kind == IT_POLE_S) ? a.EV + off : a.EV + off - n;
+    const double *__restrict__ g1 = (kind == IT_POLE_S) ? a.Egd + off + n : a.Egd + off - n;
+    const double *__restrict__ vv = (kind == IT_POLE_S) ? a.EV + off : a.EV + off - n;
     double acc = 0.0;
-    for (int i = threadIdx.x; i < n; i += PT) {
+    for (int i = tid; i < n; i += PT) {
       const double f = (sqrt(__ldg(g0 + i)) + sqrt(__ldg(g1 + i))) * __ldg(vv + i);
-      acc = (it.kind == IT_POLE_S) ? acc + f : acc - f;
+      acc = (kind == IT_POLE_S) ? acc + f : acc - f;
     }
     const double r = block_sum<PT>(acc, red);
-    if (threadIdx.x == 0) bc[0] = -(r * 2.0 / n / a.radius / a.dlat);  // dgd = -mass_div_lon(=0) - mass_div_lat
+    if (tid == 0) bc[0] = -(r * 2.0 / n / a.radius / a.dlat);  // dgd = -mass_div_lon(=0) - mass_div_lat
     __syncthreads();
     const double dG = bc[0];
     const double cw = a.t.cosf[j];
-    for (int i0 = threadIdx.x; i0 < n; i0 += PT * PB) {
+    for (int i0 = tid; i0 < n; i0 += PT * PB) {
       double o[PB], pr[PB];
 #pragma unroll
       for (int q = 0; q < PB; q++) {
@@ -716,10 +732,33 @@ __global__ void __launch_bounds__(PT) k_polar(const PolarArgs a) {
       }
     }
   } else {
-    double *T = (it.kind == IT_DU) ? a.TU : (it.kind == IT_DV) ? a.TV : a.Tgd;
-    const double *__restrict__ W = (it.kind == IT_DU) ? a.EU : (it.kind == IT_DV) ? a.EV : a.Egd;
+    double *T = (kind == IT_DU) ? a.TU : (kind == IT_DV) ? a.TV : a.Tgd;
+    const double *__restrict__ W = (kind == IT_DU) ? a.EU : (kind == IT_DV) ? a.EV : a.Egd;
+    const double *__restrict__ O = (kind == IT_DU) ? a.OU : (kind == IT_DV) ? a.OV : a.Ogd;
+    double *N = (kind == IT_DU) ? a.NU : (kind == IT_DV) ? a.NV : a.Ngd;
+    const double *__restrict__ P = (kind == IT_DU) ? a.PU : (kind == IT_DV) ? a.PV : a.Pgd;
+    const double *__restrict__ Q = (MODE == MODE_S1 || MODE == MODE_S2) ? O : (MODE == MODE_S3A) ? P : nullptr;
+    double *qs = psm + 2 * (size_t)n;
+    const bool useq = (MODE != MODE_EVAL) && a.use_q;
+    if (useq) {  // fire and forget: consumed in the last loop, by the thread that issued it
+      for (int i = tid; i < n; i += PT) __pipeline_memcpy_async(qs + i, Q + off + i, sizeof(double));
+      __pipeline_commit();
+    }
+    const int K = cutoff + 1;
+    const bool fast = (K >= 1) && (K <= KF) && (n <= PT * PQ) && (2 * K < n);
+    double bcv[KF], bsv[KF];
+#pragma unroll
+    for (int k = 0; k < KF; k++) {
+      bcv[k] = bsv[k] = 0.0;
+      if (fast && k < K && tid < n) {
+        bcv[k] = __ldg(a.basis + (size_t)(2 * k + 1) * n + tid);
+        bsv[k] = __ldg(a.basis + (size_t)(2 * k + 2) * n + tid);
+      }
+    }
+    if (fast)
+      for (int k = tid; k < PQ * KF * 2; k += PT) rot_s[k] = __ldg(a.rot + k);
     double s1p = 0.0;
-    for (int i0 = threadIdx.x; i0 < n; i0 += PT * PB) {
+    for (int i0 = tid; i0 < n; i0 += PT * PB) {
       double xv[PB], wv[PB];
 #pragma unroll
       for (int q = 0; q < PB; q++) {
@@ -729,7 +768,7 @@ __global__ void __launch_bounds__(PT) k_polar(const PolarArgs a) {
           xv[q] = T[off + i];
           if (a.rescale) {
             wv[q] = __ldg(W + off + i);
-            if (it.kind == IT_DGD) wv[q] = wv[q] + __ldg(a.ghs + off + i);
+            if (kind == IT_DGD) wv[q] = wv[q] + __ldg(a.ghs + off + i);
           }
         }
       }
@@ -743,55 +782,135 @@ __global__ void __launch_bounds__(PT) k_polar(const PolarArgs a) {
         }
       }
     }
+    __syncthreads();
     bool do_filter = true;
-    double s1 = 0.0;
-    if (a.rescale) {
-      const double r = block_sum<PT>(s1p, red);
-      if (threadIdx.x == 0) bc[0] = r;
+    double s1 = 0.0, s2 = 1.0;
+    if (fast) {
+      // ---- s1 and the 2K+1 dot products in one pass over the thread's own elements ---------------------------
+      double acc0 = 0.0, accC[KF], accS[KF];
+#pragma unroll
+      for (int k = 0; k < KF; k++) accC[k] = accS[k] = 0.0;
+      for (int q = 0, i = tid; i < n; q++, i += PT) {
+        const double xi = x[i];
+        acc0 += xi;
+        const double *__restrict__ e = rot_s + q * (KF * 2);
+#pragma unroll
+        for (int k = 0; k < KF; k++) {
+          if (k < K) {
+            const double ec = e[2 * k], es = e[2 * k + 1];
+            const double cr = bcv[k] * ec - bsv[k] * es;
+            const double sr = bsv[k] * ec + bcv[k] * es;
+            accC[k] += xi * cr;
+            accS[k] += xi * sr;
+          }
+        }
+      }
+      const int warp = tid >> 5, lane = tid & 31;
+      constexpr int NW = PT / 32;
+      {
+        const double r = warp_sum(s1p);
+        if (lane == 0) part[warp] = r;
+        const double r0_ = warp_sum(acc0);
+        if (lane == 0) part[NW + warp] = r0_;
+      }
+#pragma unroll
+      for (int k = 0; k < KF; k++) {
+        if (k < K) {
+          const double rc = warp_sum(accC[k]), rs = warp_sum(accS[k]);
+          if (lane == 0) {
+            part[(2 + 2 * k) * NW + warp] = rc;
+            part[(3 + 2 * k) * NW + warp] = rs;
+          }
+        }
+      }
+      __syncthreads();
+      if (tid < 2 + 2 * K) {
+        double r = 0.0;
+        for (int q = 0; q < NW; q++) r += part[tid * NW + q];
+        if (tid == 0) bc[0] = r;
+        else coef[tid - 1] = r * ((tid == 1) ? 1.0 / n : 2.0 / n);  // rfftf1.f:87-107 normalisation
+      }
       __syncthreads();
       s1 = bc[0];
-      do_filter = fabs(s1) > 1.0e-16;  // filter_inner_product_threshold, src/filter_mod.F90:31
-    } else {
-      __syncthreads();
-    }
-    double s2 = 1.0;
-    if (do_filter) {
-      project_row(x, n, it.cutoff, a.basis, coef, part);
-      if (a.rescale) {
+      if (a.rescale) do_filter = fabs(s1) > 1.0e-16;  // filter_inner_product_threshold, src/filter_mod.F90:31
+      if (do_filter) {
+        // ---- reconstruction from entries 0 .. 2K-1 (sin(K x) is dropped: quirk B3) ---------------------------
+        const double c0 = coef[0];
+        double cc[KF], cs[KF];
+#pragma unroll
+        for (int k = 0; k < KF; k++) {
+          cc[k] = (k < K) ? coef[1 + 2 * k] : 0.0;
+          cs[k] = (k < K - 1) ? coef[2 + 2 * k] : 0.0;
+        }
         double s2p = 0.0;
-        for (int i = threadIdx.x; i < n; i += PT) s2p = s2p + x[i] * w[i];
-        const double r = block_sum<PT>(s2p, red);
-        if (threadIdx.x == 0) bc[1] = r;
+        for (int q = 0, i = tid; i < n; q++, i += PT) {
+          const double *__restrict__ e = rot_s + q * (KF * 2);
+          double y = c0;
+#pragma unroll
+          for (int k = 0; k < KF; k++) {
+            if (k < K) {
+              const double ec = e[2 * k], es = e[2 * k + 1];
+              const double cr = bcv[k] * ec - bsv[k] * es;
+              const double sr = bsv[k] * ec + bcv[k] * es;
+              y += cc[k] * cr + cs[k] * sr;
+            }
+          }
+          x[i] = y;
+          s2p = s2p + y * w[i];
+        }
+        if (a.rescale) {
+          const double r = block_sum<PT>(s2p, red);
+          if (tid == 0) bc[1] = r;
+          __syncthreads();
+          s2 = bc[1];
+        }
+      }
+    } else {
+      if (a.rescale) {
+        const double r = block_sum<PT>(s1p, red);
+        if (tid == 0) bc[0] = r;
         __syncthreads();
-        s2 = bc[1];
+        s1 = bc[0];
+        do_filter = fabs(s1) > 1.0e-16;
+      }
+      if (do_filter) {
+        project_row(x, n, cutoff, a.basis, coef, part);
+        if (a.rescale) {
+          double s2p = 0.0;
+          for (int i = tid; i < n; i += PT) s2p = s2p + x[i] * w[i];
+          const double r = block_sum<PT>(s2p, red);
+          if (tid == 0) bc[1] = r;
+          __syncthreads();
+          s2 = bc[1];
+        }
       }
     }
-    const double *__restrict__ O = (it.kind == IT_DU) ? a.OU : (it.kind == IT_DV) ? a.OV : a.Ogd;
-    double *N = (it.kind == IT_DU) ? a.NU : (it.kind == IT_DV) ? a.NV : a.Ngd;
-    const double *__restrict__ P = (it.kind == IT_DU) ? a.PU : (it.kind == IT_DV) ? a.PV : a.Pgd;
-    const double cw = (it.kind == IT_DV) ? a.t.cosh[j] : a.t.cosf[j];
+    const double cw = (kind == IT_DV) ? a.t.cosh[j] : a.t.cosf[j];
     const bool scale = do_filter && a.rescale;
-    for (int i0 = threadIdx.x; i0 < n; i0 += PT * PB) {
-      double o[PB], pr[PB];
+#ifdef GMD_DEBUG_POLAR
+    if (tid == 0) printf("polar mode %d kind %d row %d cutoff %d fast %d s1 %.17g s2 %.17g coef %g %g %g %g x0 %g\n", MODE, kind, j, cutoff, (int)fast, s1, s2, coef[0], coef[1], coef[2], coef[3], x[0]);
+#endif
+    if (useq) __pipeline_wait_prior(0);
+    for (int i0 = tid; i0 < n; i0 += PT * PB) {
+      double o[PB];
 #pragma unroll
       for (int q = 0; q < PB; q++) {
         const int i = i0 + q * PT;
-        o[q] = pr[q] = 0.0;
-        if (i < n) {
-          if (MODE == MODE_S1 || MODE == MODE_S2) o[q] = __ldg(O + off + i);
-          if (MODE == MODE_S3A) pr[q] = __ldg(P + off + i);
-        }
+        o[q] = 0.0;
+        if (i < n && MODE != MODE_EVAL) o[q] = useq ? qs[i] : __ldg(Q + off + i);
       }
 #pragma unroll
       for (int q = 0; q < PB; q++) {
         const int i = i0 + q * PT;
         if (i < n) {
           double d = x[i];
-          if (scale) d = d * s1 / s2;  // src/dycore_mod.F90:218
+          // src/dycore_mod.F90:218.  s2 == 0 exactly (a row whose filtered inner product cancels to the last bit; the
+          // reference would divide by zero and abort with NaN, quirk B13): the filtered row is left unscaled.
+          if (scale && s2 != 0.0) d = d * s1 / s2;
           if (MODE == MODE_S1 || MODE == MODE_S2) N[off + i] = o[q] + a.dt * d;
           if (MODE != MODE_S1) T[off + i] = d;
           if (MODE == MODE_S3A) {
-            ip1 = ip1 + d * pr[q] * cw;
+            ip1 = ip1 + d * o[q] * cw;
             ip2 = ip2 + d * d * cw;
           }
         }
@@ -801,7 +920,7 @@ __global__ void __launch_bounds__(PT) k_polar(const PolarArgs a) {
   if (MODE == MODE_S3A) {
     const double r1 = block_sum<PT>(ip1, red);
     const double r2 = block_sum<PT>(ip2, red);
-    if (threadIdx.x == 0) {
+    if (tid == 0) {
       a.partials[2 * blockIdx.x] = r1;
       a.partials[2 * blockIdx.x + 1] = r2;
     }
