@@ -628,6 +628,8 @@ static int stage(gmd_model *m, int pass, int mode, const State &E, const State *
   }
 
   const int li = (pass == PASS_SLOW) ? 1 : 0;
+  // timing experiments only: launch the polar-row kernel twice (benign: it re-filters its own output)
+  static const bool double_polar = getenv("GMD_TIMING_DOUBLE_POLAR") != nullptr;
   if (m->n_items[li]) {
     PolarArgs p;
     memset(&p, 0, sizeof p);
@@ -645,6 +647,7 @@ static int stage(gmd_model *m, int pass, int mode, const State &E, const State *
     p.radius = m->mesh.radius;
     p.dlat = m->mesh.dlat;
     if (!m->dry) launch_polar(m, mode, m->n_items[li], p, m->stream);
+    if (!m->dry && double_polar) launch_polar(m, mode, m->n_items[li], p, m->stream);
     if ((r = post_launch(m))) return r;
   }
   if (mode == MODE_S3A) {

@@ -15,6 +15,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_pipeline.h>
+#include <cstdio>
 #include <stdint.h>
 
 #ifndef GMD_STRICT
@@ -670,26 +671,64 @@ __device__ inline void project_row(double *x, int n, int cutoff, const double *_
   __syncthreads();
 }
 
-// Latency is what this kernel is about (it sits between two stage launches): the item comes from the kernel
-// parameters, the base-state row is prefetched into shared memory with cp.async while the projection runs, and
-// for the cutoffs the reference ships (<= KF-1) the projector runs on THREAD-OWNED elements: thread t owns
-// i = t + q PT, loads the 2K basis values of i = t once (coalesced, 2K PT doubles per CTA instead of 2K n, twice)
-// and turns them to i = t + q PT by one complex rotation with a tiny host-built table, so the inner product s1
-// and all 2K+1 dot products come out of ONE block reduction and the reconstruction needs no further loads.
+// Latency is what this kernel is about (it sits between two stage launches, and at one CTA per SM it is a chain
+// of dependent phases, not a throughput problem):
+//  * the work item comes from the kernel parameters (no dependent global load at the head of the chain);
+//  * EVERY global load of a row -- tendency, weight (+ghs), base-state / previous-tendency row, basis -- is issued
+//    before the first use, so the CTA pays one memory round trip (2.5 us behind the stage kernel's write-back);
+//  * for the cutoffs the reference ships (<= KF-1) the projector runs on THREAD-OWNED elements: thread t owns
+//    i = b + q n/4 (q = 0..3) for b = t + g PT.  The basis at b + q n/4 is the basis at b turned by k q 90 degrees --
+//    sign changes and swaps -- so the four elements are folded with additions first and one (cos, sin) pair per
+//    wavenumber serves all four; the pair at b = t + g PT is the pair at t turned by a host-tabulated angle.  The
+//    inner product s1 and all 2K+1 dot products come out of ONE interleaved block reduction, the reconstruction
+//    needs no loads at all.
+template <int NV>
+__device__ __forceinline__ void warp_sum_n(double (&v)[NV]) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int m = 0; m < NV; m++) v[m] += __shfl_xor_sync(0xffffffffu, v[m], o);
+  }
+}
+// deterministic block sum of two values at once; results valid in thread 0; red must hold >= 64 doubles
+template <int NT>
+__device__ __forceinline__ void block_sum2(double &a, double &b, double *red) {
+  double v[2] = {a, b};
+  warp_sum_n<2>(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) {
+    red[w] = v[0];
+    red[32 + w] = v[1];
+  }
+  __syncthreads();
+  if (w == 0) {
+    v[0] = (l < NT / 32) ? red[l] : 0.0;
+    v[1] = (l < NT / 32) ? red[32 + l] : 0.0;
+    warp_sum_n<2>(v);
+  }
+  a = v[0];
+  b = v[1];
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(PT) k_polar(const __grid_constant__ PolarArgs a) {
   extern __shared__ double psm[];  // x[n], w[n] (, q[n])
-  __shared__ double red[32];
+  __shared__ double red[64];
   __shared__ double coef[512];
   __shared__ double part[512];
   __shared__ double rot_s[PQ * KF * 2];
   __shared__ double bc[2];
+  constexpr int NW = PT / 32;
+  constexpr int NV = 2 + 2 * KF;  // s1, <x,1>, <x,cos k>, <x,sin k>
+  static_assert(NV * NW <= 512 && (NV * NW) % 32 == 0, "second reduction stage runs on whole warps");
   const unsigned pk = a.items[blockIdx.x];
   const int j = (int)(pk & 0xffffu), cutoff = (int)((pk >> 16) & 0x1ffu) - 1, kind = (int)(pk >> 28);
   const int n = a.g.nlon, r0 = a.g.r0;
   const int tid = threadIdx.x;
-  double *x = psm, *w = psm + n;
+  double *x = psm, *w = psm + n, *qs = psm + 2 * (size_t)n;
   const ptrdiff_t off = (ptrdiff_t)(j - r0) * (ptrdiff_t)n;
+  const bool useq = (MODE != MODE_EVAL) && a.use_q;
   double ip1 = 0.0, ip2 = 0.0;
 
   if (kind == IT_POLE_S || kind == IT_POLE_N) {
@@ -697,38 +736,42 @@ __global__ void __launch_bounds__(PT) k_polar(const __grid_constant__ PolarArgs 
     const double *__restrict__ g0 = a.Egd + off;
     const double *__restrict__ g1 = (kind == IT_POLE_S) ? a.Egd + off + n : a.Egd + off - n;
     const double *__restrict__ vv = (kind == IT_POLE_S) ? a.EV + off : a.EV + off - n;
+    const double *__restrict__ Q = (MODE == MODE_S3A) ? a.Pgd : a.Ogd;
     double acc = 0.0;
-    for (int i = tid; i < n; i += PT) {
-      const double f = (sqrt(__ldg(g0 + i)) + sqrt(__ldg(g1 + i))) * __ldg(vv + i);
-      acc = (kind == IT_POLE_S) ? acc + f : acc - f;
+    for (int i0 = tid; i0 < n; i0 += PT * 8) {
+      double av[8], bv[8], cv[8], qv[8];
+#pragma unroll
+      for (int e = 0; e < 8; e++) {
+        const int i = i0 + e * PT;
+        const bool ok = i < n;
+        av[e] = ok ? __ldg(g0 + i) : 0.0;
+        bv[e] = ok ? __ldg(g1 + i) : 0.0;
+        cv[e] = ok ? __ldg(vv + i) : 0.0;
+        qv[e] = (ok && useq) ? __ldg(Q + off + i) : 0.0;
+      }
+#pragma unroll
+      for (int e = 0; e < 8; e++) {
+        const int i = i0 + e * PT;
+        if (i < n) {
+          const double f = (sqrt(av[e]) + sqrt(bv[e])) * cv[e];
+          acc = (kind == IT_POLE_S) ? acc + f : acc - f;
+          if (useq) qs[i] = qv[e];
+        }
+      }
     }
     const double r = block_sum<PT>(acc, red);
     if (tid == 0) bc[0] = -(r * 2.0 / n / a.radius / a.dlat);  // dgd = -mass_div_lon(=0) - mass_div_lat
     __syncthreads();
     const double dG = bc[0];
     const double cw = a.t.cosf[j];
-    for (int i0 = tid; i0 < n; i0 += PT * PB) {
-      double o[PB], pr[PB];
-#pragma unroll
-      for (int q = 0; q < PB; q++) {
-        const int i = i0 + q * PT;
-        o[q] = pr[q] = 0.0;
-        if (i < n) {
-          if (MODE == MODE_S1 || MODE == MODE_S2) o[q] = __ldg(a.Ogd + off + i);
-          if (MODE == MODE_S3A) pr[q] = __ldg(a.Pgd + off + i);
-        }
-      }
-#pragma unroll
-      for (int q = 0; q < PB; q++) {
-        const int i = i0 + q * PT;
-        if (i < n) {
-          if (MODE == MODE_S1 || MODE == MODE_S2) a.Ngd[off + i] = o[q] + a.dt * dG;
-          if (MODE != MODE_S1) a.Tgd[off + i] = dG;
-          if (MODE == MODE_S3A) {
-            ip1 = ip1 + dG * pr[q] * cw;
-            ip2 = ip2 + dG * dG * cw;
-          }
-        }
+    for (int i = tid; i < n; i += PT) {
+      double o = 0.0;
+      if (MODE != MODE_EVAL) o = useq ? qs[i] : __ldg(Q + off + i);
+      if (MODE == MODE_S1 || MODE == MODE_S2) a.Ngd[off + i] = o + a.dt * dG;
+      if (MODE != MODE_S1) a.Tgd[off + i] = dG;
+      if (MODE == MODE_S3A) {
+        ip1 = ip1 + dG * o * cw;
+        ip2 = ip2 + dG * dG * cw;
       }
     }
   } else {
@@ -738,97 +781,105 @@ __global__ void __launch_bounds__(PT) k_polar(const __grid_constant__ PolarArgs 
     double *N = (kind == IT_DU) ? a.NU : (kind == IT_DV) ? a.NV : a.Ngd;
     const double *__restrict__ P = (kind == IT_DU) ? a.PU : (kind == IT_DV) ? a.PV : a.Pgd;
     const double *__restrict__ Q = (MODE == MODE_S1 || MODE == MODE_S2) ? O : (MODE == MODE_S3A) ? P : nullptr;
-    double *qs = psm + 2 * (size_t)n;
-    const bool useq = (MODE != MODE_EVAL) && a.use_q;
-    if (useq) {  // fire and forget: consumed in the last loop, by the thread that issued it
-      for (int i = tid; i < n; i += PT) __pipeline_memcpy_async(qs + i, Q + off + i, sizeof(double));
-      __pipeline_commit();
-    }
     const int K = cutoff + 1;
-    const bool fast = (K >= 1) && (K <= KF) && (n <= PT * PQ) && (2 * K < n);
+    const int n4 = n >> 2;
+    const int G = (n4 + PT - 1) / PT;  // element groups per thread on the fast path
+    const bool fast = (K >= 1) && (K <= KF) && ((n & 3) == 0) && (G <= PQ) && (2 * K < n);
+    // element e of a batch of 8: fast path: group g0 + e/4, quarter e%4; general path: i0 + e PT
+    auto elem = [&](int i0, int e) -> int {
+      if (fast) {
+        const int b = tid + (i0 + (e >> 2)) * PT;
+        return (b < n4) ? b + (e & 3) * n4 : n;
+      }
+      return min(i0 + e * PT, n);
+    };
     double bcv[KF], bsv[KF];
 #pragma unroll
     for (int k = 0; k < KF; k++) {
       bcv[k] = bsv[k] = 0.0;
-      if (fast && k < K && tid < n) {
+      if (fast && k < K && tid < n4) {
         bcv[k] = __ldg(a.basis + (size_t)(2 * k + 1) * n + tid);
         bsv[k] = __ldg(a.basis + (size_t)(2 * k + 2) * n + tid);
       }
     }
-    if (fast)
-      for (int k = tid; k < PQ * KF * 2; k += PT) rot_s[k] = __ldg(a.rot + k);
+    double rv = 0.0;
+    if (fast && tid < PQ * KF * 2) rv = __ldg(a.rot + tid);
     double s1p = 0.0;
-    for (int i0 = tid; i0 < n; i0 += PT * PB) {
-      double xv[PB], wv[PB];
+    const int nb = fast ? G : n;           // loop bound / step of the batch loop in its own units
+    const int step = fast ? 2 : PT * 8;
+    for (int i0 = fast ? 0 : tid; i0 < nb; i0 += step) {
+      double xv[8], wv[8], gv[8], qv[8];
 #pragma unroll
-      for (int q = 0; q < PB; q++) {
-        const int i = i0 + q * PT;
-        xv[q] = wv[q] = 0.0;
-        if (i < n) {
-          xv[q] = T[off + i];
-          if (a.rescale) {
-            wv[q] = __ldg(W + off + i);
-            if (kind == IT_DGD) wv[q] = wv[q] + __ldg(a.ghs + off + i);
-          }
-        }
+      for (int e = 0; e < 8; e++) {
+        const int i = elem(i0, e);
+        const bool ok = i < n;
+        xv[e] = ok ? T[off + i] : 0.0;
+        wv[e] = (ok && a.rescale) ? __ldg(W + off + i) : 0.0;
+        gv[e] = (ok && a.rescale && kind == IT_DGD) ? __ldg(a.ghs + off + i) : 0.0;
+        qv[e] = (ok && useq) ? __ldg(Q + off + i) : 0.0;
       }
 #pragma unroll
-      for (int q = 0; q < PB; q++) {
-        const int i = i0 + q * PT;
+      for (int e = 0; e < 8; e++) {
+        const int i = elem(i0, e);
         if (i < n) {
-          x[i] = xv[q];
-          w[i] = wv[q];
-          s1p = s1p + xv[q] * wv[q];
+          const double ww = wv[e] + gv[e];
+          x[i] = xv[e];
+          w[i] = ww;
+          if (useq) qs[i] = qv[e];
+          s1p = s1p + xv[e] * ww;
         }
       }
     }
+    if (fast && tid < PQ * KF * 2) rot_s[tid] = rv;
     __syncthreads();
     bool do_filter = true;
     double s1 = 0.0, s2 = 1.0;
     if (fast) {
       // ---- s1 and the 2K+1 dot products in one pass over the thread's own elements ---------------------------
-      double acc0 = 0.0, accC[KF], accS[KF];
+      double v[NV];
 #pragma unroll
-      for (int k = 0; k < KF; k++) accC[k] = accS[k] = 0.0;
-      for (int q = 0, i = tid; i < n; q++, i += PT) {
-        const double xi = x[i];
-        acc0 += xi;
-        const double *__restrict__ e = rot_s + q * (KF * 2);
+      for (int m = 0; m < NV; m++) v[m] = 0.0;
+      v[0] = s1p;
+      for (int g = 0; g < G; g++) {
+        const int b = tid + g * PT;
+        if (b < n4) {
+          const double x0 = x[b], x1 = x[b + n4], x2 = x[b + 2 * n4], x3 = x[b + 3 * n4];
+          const double e0 = x0 + x2, e1 = x1 + x3, d0 = x0 - x2, d1 = x1 - x3;
+          const double a0 = e0 + e1, a2 = e0 - e1;
+          v[1] += a0;
+          const double *__restrict__ e = rot_s + g * (KF * 2);
 #pragma unroll
-        for (int k = 0; k < KF; k++) {
-          if (k < K) {
-            const double ec = e[2 * k], es = e[2 * k + 1];
-            const double cr = bcv[k] * ec - bsv[k] * es;
-            const double sr = bsv[k] * ec + bcv[k] * es;
-            accC[k] += xi * cr;
-            accS[k] += xi * sr;
+          for (int k = 0; k < KF; k++) {
+            if (k < K) {
+              const double ec = e[2 * k], es = e[2 * k + 1];
+              const double cr = bcv[k] * ec - bsv[k] * es;   // cos, sin of wavenumber k+1 at element b
+              const double sr = bsv[k] * ec + bcv[k] * es;
+              switch ((k + 1) & 3) {                         // quarter turns of the other three elements
+                case 1: v[2 + 2 * k] += cr * d0 - sr * d1; v[3 + 2 * k] += sr * d0 + cr * d1; break;
+                case 2: v[2 + 2 * k] += cr * a2;           v[3 + 2 * k] += sr * a2;           break;
+                case 3: v[2 + 2 * k] += cr * d0 + sr * d1; v[3 + 2 * k] += sr * d0 - cr * d1; break;
+                default: v[2 + 2 * k] += cr * a0;          v[3 + 2 * k] += sr * a0;           break;
+              }
+            }
           }
         }
       }
       const int warp = tid >> 5, lane = tid & 31;
-      constexpr int NW = PT / 32;
-      {
-        const double r = warp_sum(s1p);
-        if (lane == 0) part[warp] = r;
-        const double r0_ = warp_sum(acc0);
-        if (lane == 0) part[NW + warp] = r0_;
-      }
+      warp_sum_n<NV>(v);
+      if (lane == 0) {
 #pragma unroll
-      for (int k = 0; k < KF; k++) {
-        if (k < K) {
-          const double rc = warp_sum(accC[k]), rs = warp_sum(accS[k]);
-          if (lane == 0) {
-            part[(2 + 2 * k) * NW + warp] = rc;
-            part[(3 + 2 * k) * NW + warp] = rs;
-          }
-        }
+        for (int m = 0; m < NV; m++) part[m * NW + warp] = v[m];
       }
       __syncthreads();
-      if (tid < 2 + 2 * K) {
-        double r = 0.0;
-        for (int q = 0; q < NW; q++) r += part[tid * NW + q];
-        if (tid == 0) bc[0] = r;
-        else coef[tid - 1] = r * ((tid == 1) ? 1.0 / n : 2.0 / n);  // rfftf1.f:87-107 normalisation
+      if (tid < NV * NW) {  // NW-lane segments, fixed tree
+        double p = part[tid];
+#pragma unroll
+        for (int o = NW / 2; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+        if ((tid & (NW - 1)) == 0) {
+          const int m = tid / NW;
+          if (m == 0) bc[0] = p;
+          else coef[m - 1] = p * ((m == 1) ? 1.0 / n : 2.0 / n);  // rfftf1.f:87-107 normalisation
+        }
       }
       __syncthreads();
       s1 = bc[0];
@@ -843,20 +894,34 @@ __global__ void __launch_bounds__(PT) k_polar(const __grid_constant__ PolarArgs 
           cs[k] = (k < K - 1) ? coef[2 + 2 * k] : 0.0;
         }
         double s2p = 0.0;
-        for (int q = 0, i = tid; i < n; q++, i += PT) {
-          const double *__restrict__ e = rot_s + q * (KF * 2);
-          double y = c0;
+        for (int g = 0; g < G; g++) {
+          const int b = tid + g * PT;
+          if (b < n4) {
+            const double *__restrict__ e = rot_s + g * (KF * 2);
+            double S0 = c0, Pa = 0.0, Ra = 0.0, P2 = 0.0;
 #pragma unroll
-          for (int k = 0; k < KF; k++) {
-            if (k < K) {
-              const double ec = e[2 * k], es = e[2 * k + 1];
-              const double cr = bcv[k] * ec - bsv[k] * es;
-              const double sr = bsv[k] * ec + bcv[k] * es;
-              y += cc[k] * cr + cs[k] * sr;
+            for (int k = 0; k < KF; k++) {
+              if (k < K) {
+                const double ec = e[2 * k], es = e[2 * k + 1];
+                const double cr = bcv[k] * ec - bsv[k] * es;
+                const double sr = bsv[k] * ec + bcv[k] * es;
+                const double Pk = cc[k] * cr + cs[k] * sr;   // value at b; a quarter turn further: Rk, -Pk, -Rk
+                const double Rk = cs[k] * cr - cc[k] * sr;
+                switch ((k + 1) & 3) {
+                  case 1: Pa += Pk; Ra += Rk; break;
+                  case 2: P2 += Pk; break;
+                  case 3: Pa += Pk; Ra -= Rk; break;
+                  default: S0 += Pk; break;
+                }
+              }
             }
+            const double y0 = (S0 + P2) + Pa, y2 = (S0 + P2) - Pa, y1 = (S0 - P2) + Ra, y3 = (S0 - P2) - Ra;
+            x[b] = y0;
+            x[b + n4] = y1;
+            x[b + 2 * n4] = y2;
+            x[b + 3 * n4] = y3;
+            s2p = s2p + y0 * w[b] + y1 * w[b + n4] + y2 * w[b + 2 * n4] + y3 * w[b + 3 * n4];
           }
-          x[i] = y;
-          s2p = s2p + y * w[i];
         }
         if (a.rescale) {
           const double r = block_sum<PT>(s2p, red);
@@ -886,31 +951,30 @@ __global__ void __launch_bounds__(PT) k_polar(const __grid_constant__ PolarArgs 
       }
     }
     const double cw = (kind == IT_DV) ? a.t.cosh[j] : a.t.cosf[j];
-    const bool scale = do_filter && a.rescale;
-#ifdef GMD_DEBUG_POLAR
-    if (tid == 0) printf("polar mode %d kind %d row %d cutoff %d fast %d s1 %.17g s2 %.17g coef %g %g %g %g x0 %g\n", MODE, kind, j, cutoff, (int)fast, s1, s2, coef[0], coef[1], coef[2], coef[3], x[0]);
+    // src/dycore_mod.F90:218.  s2 == 0 exactly (a row whose filtered inner product cancels to the last bit; the
+    // reference would divide by zero and abort with NaN, quirk B13): the filtered row is left unscaled.
+    const bool scale = do_filter && a.rescale && (s2 != 0.0);
+#if !GMD_STRICT
+    const double ratio = scale ? s1 / s2 : 1.0;
 #endif
-    if (useq) __pipeline_wait_prior(0);
-    for (int i0 = tid; i0 < n; i0 += PT * PB) {
-      double o[PB];
+    // own elements again on the fast path (x and qs of element i were written by this thread)
+    for (int i0 = fast ? 0 : tid; i0 < nb; i0 += step) {
 #pragma unroll
-      for (int q = 0; q < PB; q++) {
-        const int i = i0 + q * PT;
-        o[q] = 0.0;
-        if (i < n && MODE != MODE_EVAL) o[q] = useq ? qs[i] : __ldg(Q + off + i);
-      }
-#pragma unroll
-      for (int q = 0; q < PB; q++) {
-        const int i = i0 + q * PT;
+      for (int e = 0; e < 8; e++) {
+        const int i = elem(i0, e);
         if (i < n) {
+          double o = 0.0;
+          if (MODE != MODE_EVAL) o = useq ? qs[i] : __ldg(Q + off + i);
           double d = x[i];
-          // src/dycore_mod.F90:218.  s2 == 0 exactly (a row whose filtered inner product cancels to the last bit; the
-          // reference would divide by zero and abort with NaN, quirk B13): the filtered row is left unscaled.
-          if (scale && s2 != 0.0) d = d * s1 / s2;
-          if (MODE == MODE_S1 || MODE == MODE_S2) N[off + i] = o[q] + a.dt * d;
+#if GMD_STRICT
+          if (scale) d = d * s1 / s2;
+#else
+          d = d * ratio;
+#endif
+          if (MODE == MODE_S1 || MODE == MODE_S2) N[off + i] = o + a.dt * d;
           if (MODE != MODE_S1) T[off + i] = d;
           if (MODE == MODE_S3A) {
-            ip1 = ip1 + d * o[q] * cw;
+            ip1 = ip1 + d * o * cw;
             ip2 = ip2 + d * d * cw;
           }
         }
@@ -918,11 +982,10 @@ __global__ void __launch_bounds__(PT) k_polar(const __grid_constant__ PolarArgs 
     }
   }
   if (MODE == MODE_S3A) {
-    const double r1 = block_sum<PT>(ip1, red);
-    const double r2 = block_sum<PT>(ip2, red);
+    block_sum2<PT>(ip1, ip2, red);
     if (tid == 0) {
-      a.partials[2 * blockIdx.x] = r1;
-      a.partials[2 * blockIdx.x + 1] = r2;
+      a.partials[2 * blockIdx.x] = ip1;
+      a.partials[2 * blockIdx.x + 1] = ip2;
     }
   }
 }
