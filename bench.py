@@ -16,8 +16,9 @@ for this grid; dt, S and the cutoff vector are builder-chosen and
   roofline  the fused stage kernel (S2 variant) timed alone with CUDA events; algorithmic bytes = 13 words/column
   cpu_baseline  the CPU oracle (-O3 -ffast-math, as the reference's -Ofast), 1 thread (the reference is serial),
             on a bounded sample: the same configuration on a 900x451 grid
-Multi-GPU (torchrun, one rank per GPU): latitude bands, NCCL halo exchange + allreduce inside libgmd;
-fixed global grid => "strong" scaling.
+Multi-GPU (torchrun, one rank per GPU): latitude bands; halo rows are stored into the neighbour's ghost rows over
+NVLink peer memory and the two-scalar all-reduces are one-shot peer exchanges, all inside libgmd (--comm nccl
+selects the ncclSend/Recv + ncclAllReduce path instead); fixed global grid => "strong" scaling.
 """
 import argparse
 import json
@@ -143,13 +144,13 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def config_dict(name, kw, ngpu):
+def config_dict(name, kw, ngpu, comm="peer memory"):
     return {"workload": f"{name}: {WORKLOADS[name][0]} {kw['num_lon']}x{kw['num_lat']}", "dt_s": kw["time_step_size"],
             "split_scheme": kw["split_scheme"], "subcycles": kw["subcycles"], "uv_adv_scheme": kw.get("uv_adv_scheme", "center_diff"),
             "filter_rows_per_pole": sum(1 for c in kw["zonal_tend_filter_cutoff_wavenumber"] if c),
             "filter_cutoff": max(kw["zonal_tend_filter_cutoff_wavenumber"]),
             "use_diffusion": bool(kw.get("use_diffusion", False)),
-            "decomposition": f"{ngpu} latitude band(s)", "l2_policy": "per-step working set (>= 16 fields x 51.9 MB at 0.1 deg) exceeds the 126 MB L2"}
+            "decomposition": f"{ngpu} latitude band(s)" + (f", halo rows and all-reduces over {comm}" if ngpu > 1 else ""), "l2_policy": "per-step working set (>= 16 fields x 51.9 MB at 0.1 deg) exceeds the 126 MB L2"}
 
 
 def main():
@@ -161,6 +162,8 @@ def main():
     ap.add_argument("--workload", default="sg_0.1deg", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--comm", default="peer", choices=["peer", "nccl"],
+                    help="multi-GPU data path: NVLink peer memory (default) or NCCL send/recv + all-reduce")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -187,10 +190,8 @@ def main():
 
     d = gmd.Dycore(gmd.Config(rank=rank, nranks=world, device=local, **kw))
     if world > 1:
-        import torch.distributed as dist
-        uid = [gmd.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        d.comm_init(uid[0])
+        from gamil_dycore_b200 import parallel
+        parallel.connect(d, mode=args.comm)
     if args.no_graph:
         d.set_graph_mode(False)
     stream = torch.cuda.Stream()   # a real (non-legacy) stream: libgmd launches on it, torch events time it
@@ -280,7 +281,7 @@ def main():
                              "(the reference is serial), oracle built with gcc -O3 -ffast-math"}
         line = {"metric": "grid-point-updates/s", "value": value, "unit": "grid-point-updates/s", "n_gpus": world,
                 "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong",
-                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_dict(args.workload, kw, world),
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_dict(args.workload, kw, world, "NVLink peer memory" if args.comm == "peer" else "NCCL"),
                 "sim_days_per_day": kw["time_step_size"] * K / (ms * 1e-3), "clocks": sampler.summary(), "e2e": e2e,
                 "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
                 "conservation": {"mass_rel_drift": abs(m1 / m0 - 1), "energy_rel_drift": abs(e1 / e0 - 1), "beta": beta}}

@@ -116,6 +116,8 @@ def load(kind: str = "fast") -> C.CDLL:
     lib.gmd_last_error.restype = C.c_char_p
     lib.gmd_comm_unique_id.argtypes = [C.c_void_p]
     lib.gmd_comm_init.argtypes = [P, C.c_void_p]
+    lib.gmd_peer_export.argtypes = [P, C.c_void_p]
+    lib.gmd_peer_connect.argtypes = [P, C.c_void_p, C.c_int]
     lib.gmd_get_band.argtypes = [P, I, I]
     lib.gmd_set_state.argtypes = [P, D, D, D, D, C.c_int]
     lib.gmd_run_init.argtypes = [P]
@@ -145,6 +147,9 @@ def load(kind: str = "fast") -> C.CDLL:
     lib.gmd_time_stage_variant.argtypes = [P, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), D]
     _LIBS[kind] = lib
     return lib
+
+
+PEER_BLOB_BYTES = 256   # GMD_PEER_BLOB_BYTES, include/gmd.h
 
 
 def _dp(a: Optional[np.ndarray]):
@@ -201,6 +206,18 @@ class Dycore:
 
     def comm_init(self, uid: bytes):
         self._chk(self.lib.gmd_comm_init(self.h, C.create_string_buffer(uid, 128)))
+
+    def peer_export(self) -> bytes:
+        """this rank's peer blob (CUDA-IPC handles of its field slab and signal page), gmd_peer_export"""
+        buf = C.create_string_buffer(PEER_BLOB_BYTES)
+        self._chk(self.lib.gmd_peer_export(self.h, buf))
+        return buf.raw
+
+    def peer_connect(self, blobs):
+        """`blobs`: the peer blobs of ALL ranks in rank order (list of bytes); switches halo rows and the
+        two-scalar all-reduces to the peer-memory path, gmd_peer_connect"""
+        raw = b"".join(blobs)
+        self._chk(self.lib.gmd_peer_connect(self.h, C.create_string_buffer(raw, len(raw)), len(blobs)))
 
     def band(self):
         a, b = C.c_int(), C.c_int()

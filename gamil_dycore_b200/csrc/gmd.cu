@@ -9,6 +9,7 @@
 #include "gmd_mesh.h"
 
 #include <dlfcn.h>
+#include <unistd.h>
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
@@ -124,9 +125,11 @@ struct gmd_model {
   int n_items[3] = {0, 0, 0};
   double *d_rot = nullptr;         // [PQ][KF][2] rotation table of the fast projector
 
-  // buffers
+  // buffers: every field lives in ONE slab (fixed slots), so that one CUDA-IPC handle maps the whole pool into
+  // the neighbour ranks and "my buffer X" and "the neighbour's buffer X" are the same slot index
   std::vector<double *> free_[3];
-  std::vector<double *> all_allocs;
+  double *slab = nullptr;
+  int slab_cap = 0, slab_next = 0;
   std::map<double *, int> refc;  // base pointer (row r0) -> refcount
   std::map<double *, int> kind_of;
 
@@ -161,8 +164,16 @@ struct gmd_model {
   bool split = true;
   int ew_blocks = 0;  // grid of element-wise kernels
 
-  // comm
+  // comm: NCCL (optional) and the peer-memory path (gmd_peer_connect)
   void *comm = nullptr;
+  u64 *page = nullptr;             // my signal page
+  bool p2p = false;
+  u64 *peer_page[MAXR] = {};       // every rank's signal page as mapped here
+  double *peer_slab[2] = {nullptr, nullptr};   // south / north neighbour's slab as mapped here
+  int peer_r0[2] = {0, 0};
+  size_t peer_fld[2] = {0, 0};
+  std::vector<void *> ipc_opened;
+  unsigned xk = 0, rk = 0, xwaited = 0;  // halo epochs released / reductions done / halo epoch waited for, this unit
 
   // graphs
   bool graph_mode = true;
@@ -202,11 +213,10 @@ static int acquire(gmd_model *m, int kind, double **out) {
     *out = m->free_[kind].back();
     m->free_[kind].pop_back();
   } else {
-    if (m->capturing) return fail(GMD_ERR_STATE, "buffer pool exhausted during graph capture");
-    double *p = nullptr;
-    CK(cudaMalloc(&p, m->fld_elems * sizeof(double)));
-    CK(cudaMemsetAsync(p, 0, m->fld_elems * sizeof(double), m->stream));
-    m->all_allocs.push_back(p);
+    if (m->slab_next >= m->slab_cap)
+      return fail(GMD_ERR_STATE, "field pool exhausted (%d fields of %zu bytes); set GMD_POOL_FIELDS", m->slab_cap,
+                  m->fld_elems * sizeof(double));
+    double *p = m->slab + (size_t)m->slab_next++ * m->fld_elems;  // zero since gmd_create
     *out = p + (size_t)GHOST * m->geo.nlon;
     m->kind_of[*out] = kind;
   }
@@ -446,10 +456,90 @@ static int exchange_field(gmd_model *m, double *f, int ns, int nn) {
   }
   return 0;
 }
+// ---- peer-memory path ------------------------------------------------------------------------------------
+// the neighbour's copy of my buffer `mine` (same slab slot), shifted so that the element offset of (row j, column
+// i) is the one I use: q[(j - r0) nlon + i] is the neighbour's (j, i)
+static double *peer_ptr(const gmd_model *m, int side, const double *mine) {
+  if (!mine || !m->peer_slab[side]) return nullptr;
+  const size_t nlon = (size_t)m->geo.nlon;
+  const size_t slot = (size_t)((mine - (size_t)GHOST * nlon) - m->slab) / m->fld_elems;
+  double *base = m->peer_slab[side] + slot * m->peer_fld[side] + (size_t)GHOST * nlon;  // the neighbour's row r0'
+  return base + (ptrdiff_t)(m->geo.r0 - m->peer_r0[side]) * (ptrdiff_t)nlon;
+}
+static int halo_sides(const gmd_model *m) {
+  return (m->cfg.rank > 0 ? 1 : 0) | (m->cfg.rank + 1 < m->cfg.nranks ? 2 : 0);
+}
+// store halo rows of up to three fields into the neighbours' ghost rows and release halo epoch ++xk
+static int halo_push(gmd_model *m, double *const f[3], const int ns[3], const int nn[3]) {
+  m->xk++;
+  if (m->dry) return 0;
+  PushArgs a;
+  memset(&a, 0, sizeof a);
+  a.g = m->geo;
+  int rows = 0;
+  for (int k = 0; k < 3; k++) {
+    a.src[k] = f[k];
+    a.dstS[k] = peer_ptr(m, 0, f[k]);
+    a.dstN[k] = peer_ptr(m, 1, f[k]);
+    a.ns[k] = ns[k];
+    a.nn[k] = nn[k];
+    if (f[k]) rows += (a.dstS[k] ? nn[k] : 0) + (a.dstN[k] ? ns[k] : 0);
+  }
+  a.page = m->page;
+  a.sigS = (m->cfg.rank > 0) ? m->peer_page[m->cfg.rank - 1] + SP_SIG + 1 : nullptr;
+  a.sigN = (m->cfg.rank + 1 < m->cfg.nranks) ? m->peer_page[m->cfg.rank + 1] + SP_SIG : nullptr;
+  a.k = m->xk;
+  const int units = rows * (m->geo.nlon / 2);
+  const int nb = std::max(1, std::min(64, (units + 255) / 256));
+  k_halo_push<<<nb, 256, 0, m->stream>>>(a);
+  m->launches++;
+  cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) return fail(GMD_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+  return 0;
+}
+// before a launch on the main stream that reads ghost rows and does not wait by itself
+static int halo_wait(gmd_model *m) {
+  if (!m->p2p || m->xwaited == m->xk) return 0;
+  m->xwaited = m->xk;
+  if (m->dry) return 0;
+  k_halo_wait<<<1, 32, 0, m->stream>>>(m->page, m->xk, halo_sides(m));
+  m->launches++;
+  return 0;
+}
+// close a unit of work (k_unit_end): all incoming halo rows have landed, epoch bases advance
+static int unit_end(gmd_model *m) {
+  if (!m->p2p || (m->xk == 0 && m->rk == 0)) return 0;
+  if (!m->dry) {
+    k_unit_end<<<1, 32, 0, m->stream>>>(m->page, m->xk, m->rk, halo_sides(m));
+    m->launches++;
+  }
+  m->xk = m->rk = m->xwaited = 0;
+  return 0;
+}
+static RedArgs red_args(gmd_model *m) {
+  RedArgs r;
+  memset(&r, 0, sizeof r);
+  r.nranks = 1;
+  if (m->p2p) {
+    r.page = m->page;
+    for (int p = 0; p < m->cfg.nranks; p++) r.peer[p] = m->peer_page[p];
+    r.rank = m->cfg.rank;
+    r.nranks = m->cfg.nranks;
+    r.k = ++m->rk;
+  }
+  return r;
+}
+
 // ghosts the stage kernel needs: south U,V,gd row r0-1; north U,V row r1, gd rows r1, r1+1
 static int exchange_state(gmd_model *m, const State &s, bool with_gd) {
-  if (m->cfg.nranks == 1 || m->dry) return 0;
-  if (!m->comm) return fail(GMD_ERR_COMM, "gmd_comm_init has not been called on this rank");
+  if (m->cfg.nranks == 1) return 0;
+  if (m->p2p) {
+    double *const f[3] = {s.U, s.V, with_gd ? s.gd : nullptr};
+    const int ns[3] = {1, 1, 1}, nn[3] = {1, 1, 2};
+    return halo_push(m, f, ns, nn);
+  }
+  if (m->dry) return 0;
+  if (!m->comm) return fail(GMD_ERR_COMM, "neither gmd_peer_connect nor gmd_comm_init has been called on this rank");
   NK(g_nccl.GroupStart());
   int r;
   if ((r = exchange_field(m, s.U, 1, 1))) return r;
@@ -459,8 +549,14 @@ static int exchange_state(gmd_model *m, const State &s, bool with_gd) {
   return 0;
 }
 static int exchange_tend3(gmd_model *m, double *a, double *b, double *c, int ns, int nn) {
-  if (m->cfg.nranks == 1 || m->dry) return 0;
-  if (!m->comm) return fail(GMD_ERR_COMM, "gmd_comm_init has not been called on this rank");
+  if (m->cfg.nranks == 1) return 0;
+  if (m->p2p) {
+    double *const f[3] = {a, b, c};
+    const int nsv[3] = {ns, ns, ns}, nnv[3] = {nn, nn, nn};
+    return halo_push(m, f, nsv, nnv);
+  }
+  if (m->dry) return 0;
+  if (!m->comm) return fail(GMD_ERR_COMM, "neither gmd_peer_connect nor gmd_comm_init has been called on this rank");
   NK(g_nccl.GroupStart());
   int r;
   if (a && (r = exchange_field(m, a, ns, nn))) return r;
@@ -470,8 +566,8 @@ static int exchange_tend3(gmd_model *m, double *a, double *b, double *c, int ns,
   return 0;
 }
 static int allreduce2(gmd_model *m, double *d) {
-  if (m->cfg.nranks == 1 || m->dry) return 0;
-  if (!m->comm) return fail(GMD_ERR_COMM, "gmd_comm_init has not been called on this rank");
+  if (m->cfg.nranks == 1 || m->dry || m->p2p) return 0;  // peer path: done inside k_reduce_pairs
+  if (!m->comm) return fail(GMD_ERR_COMM, "neither gmd_peer_connect nor gmd_comm_init has been called on this rank");
   NK(g_nccl.AllReduce(d, d, 2, NCCL_F64, NCCL_SUM, m->comm, m->stream));
   return 0;
 }
@@ -527,6 +623,7 @@ static int derive_uv(gmd_model *m, const State &s) {
   int r;
   if ((r = ensure_uv(m))) return r;
   if ((r = join(m))) return r;
+  if ((r = halo_wait(m))) return r;
   const int ja = std::max(m->geo.r0 - 1, 0), jb = std::min(m->geo.r1 + 1, m->geo.nlat);
   if (!m->dry) k_derive<<<m->ew_blocks, 256, 0, m->stream>>>(m->geo, ja, jb, s.U, s.V, s.gd, m->w_u, m->w_v, nullptr);
   return post_launch(m);
@@ -604,6 +701,13 @@ static int stage(gmd_model *m, int pass, int mode, const State &E, const State *
     // boundary rows first on the main stream (then polar rows / halo exchange), interior rows on stream2
     if ((r = split_begin(m))) return r;
     StageArgs b = a;
+    if (m->p2p) {  // the boundary CTAs wait for the neighbours' halo rows themselves
+      b.hpage = m->page;
+      b.hwait_k = m->xk;
+      b.hside[0] = halo_sides(m) & 1;
+      b.hside[1] = halo_sides(m) & 2;
+      m->xwaited = m->xk;
+    }
     b.rows_per_cta = m->rows_per_cta_b;
     b.rb[0] = r0; b.re[0] = r0 + m->bs; b.pofs[0] = 0;
     b.rb[1] = r1 - m->bn; b.re[1] = r1; b.pofs[1] = m->nbx * m->nchunks_b;
@@ -619,6 +723,7 @@ static int stage(gmd_model *m, int pass, int mode, const State &E, const State *
     nst = 2 * m->nbx * m->nchunks_b + m->nbx * m->nchunks_i;
   } else {
     if ((r = join(m))) return r;
+    if ((r = halo_wait(m))) return r;
     a.rows_per_cta = m->rows_per_cta;
     a.rb[0] = r0; a.re[0] = r1; a.pofs[0] = 0;
     dim3 grid((unsigned)m->nbx, (unsigned)m->nchunks, 1);
@@ -652,7 +757,10 @@ static int stage(gmd_model *m, int pass, int mode, const State &E, const State *
   }
   if (mode == MODE_S3A) {
     if ((r = join(m))) return r;
-    if (!m->dry) k_reduce_pairs<<<1, 256, 0, m->stream>>>(m->d_partials, nst + m->n_items[li], m->d_ip);
+    {
+      const RedArgs ra = red_args(m);
+      if (!m->dry) k_reduce_pairs<<<1, 256, 0, m->stream>>>(m->d_partials, nst + m->n_items[li], m->d_ip, ra);
+    }
     if ((r = post_launch(m))) return r;
     if ((r = allreduce2(m, m->d_ip))) return r;
   }
@@ -814,7 +922,10 @@ static int isp(gmd_model *m, const State &F, State *out) {
   // ip1 = <R, F> (tend-state product, src/types_mod.F90:373-397), ip2 = <R, R>
   if ((r = dot(m, T2.U, T2.V, T2.gd, F.U, F.V, F.gd, 0))) return r;
   if ((r = dot(m, T2.U, T2.V, T2.gd, T2.U, T2.V, T2.gd, 1))) return r;
-  if (!m->dry) k_reduce_pairs<<<1, 256, 0, m->stream>>>(m->d_partials, m->ew_blocks, m->d_ip);
+  {
+    const RedArgs ra = red_args(m);
+    if (!m->dry) k_reduce_pairs<<<1, 256, 0, m->stream>>>(m->d_partials, m->ew_blocks, m->d_ip, ra);
+  }
   if ((r = post_launch(m))) return r;
   if ((r = allreduce2(m, m->d_ip))) return r;
   if ((r = update(m, F, T2, half_dt, 2, dtm, true, &Q1))) return r;
@@ -856,6 +967,7 @@ static int diffusion(gmd_model *m, double dt, const State &in, State *out) {
   const double *qu = m->w_u, *qv = m->w_v, *qg = in.gd;
   double *ou = m->d_ud, *ov = m->d_vd, *og = m->d_gdd;
   for (int order = 1; order <= norder; order++) {
+    if ((r = halo_wait(m))) return r;
     if (!m->dry) k_laplace<<<m->ew_blocks, 256, 0, m->stream>>>(m->geo, m->tab, qu, qv, qg, ou, ov, og);
     if ((r = post_launch(m))) return r;
     if (south || north) {
@@ -874,6 +986,7 @@ static int diffusion(gmd_model *m, double dt, const State &in, State *out) {
   const double sdc = sign * dt * m->cfg.diffusion_coef;
   State N;
   if ((r = new_state(m, &N, nullptr))) return r;
+  if ((r = halo_wait(m))) return r;
   if (!m->dry) k_diff_update<<<m->ew_blocks, 256, 0, m->stream>>>(m->geo, m->w_u, m->w_v, in.gd, ou, ov, og, sdc, N.U, N.V, N.gd);
   if ((r = post_launch(m))) return r;
   if ((r = exchange_state(m, N, true))) return r;
@@ -888,11 +1001,15 @@ static int diag(gmd_model *m, const State &s, int advance) {
   if (!m->dry) k_diag<<<m->ew_blocks, 256, 0, m->stream>>>(m->geo, m->tab, s.U, s.V, s.gd, m->ghs, m->mesh.dlon, m->mesh.dlat,
                                              m->d_partials);
   if ((r = post_launch(m))) return r;
-  if (!m->dry) k_reduce_pairs<<<1, 256, 0, m->stream>>>(m->d_partials, m->ew_blocks, m->d_sums);
+  {
+    const RedArgs ra = red_args(m);
+    if (!m->dry) k_reduce_pairs<<<1, 256, 0, m->stream>>>(m->d_partials, m->ew_blocks, m->d_sums, ra);
+  }
   if ((r = post_launch(m))) return r;
   if ((r = allreduce2(m, m->d_sums))) return r;
   if (!m->dry) k_diag_store<<<1, 32, 0, m->stream>>>(m->d_sums, m->d_beta, m->mesh.radius, m->d_ring, m->d_ctr, advance, gmd_model::RING);
-  return post_launch(m);
+  if ((r = post_launch(m))) return r;
+  return unit_end(m);
 }
 
 // time_integrate (src/dycore_mod.F90:654-669) + time_advance + diag_run for ONE step; consumes m->cur
@@ -1089,7 +1206,9 @@ void gmd_destroy(gmd_model *m) {
   if (m->stream) cudaStreamSynchronize(m->stream);
   for (auto &g : m->graphs) cudaGraphExecDestroy(g.exec);
   if (m->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(m->comm);
-  for (double *p : m->all_allocs) cudaFree(p);
+  for (void *p : m->ipc_opened) cudaIpcCloseMemHandle(p);
+  cudaFree(m->slab);
+  cudaFree(m->page);
   for (double *p : m->tab_allocs) cudaFree(p);
   cudaFree(m->d_flags_alloc);
   cudaFree(m->d_basis);
@@ -1165,6 +1284,18 @@ int gmd_create(const gmd_config *cfg, gmd_model **out) {
   m->geo.r1 = m->geo.r0 + base + (cfg->rank < rem ? 1 : 0);
   m->nr = m->geo.r1 - m->geo.r0;
   m->fld_elems = (size_t)(m->nr + 2 * GHOST) * nlon;
+  {
+    // field pool: csp2 needs 22 fields (state 3 + ghs + 2 tendencies + 2 stage states + 1 substep state), isp 6
+    // more, WENO 12, diffusion 8, the get_* calls 2
+    m->slab_cap = 56;
+    if (const char *ev = getenv("GMD_POOL_FIELDS")) m->slab_cap = std::max(24, atoi(ev));
+    const size_t bytes = (size_t)m->slab_cap * m->fld_elems * sizeof(double);
+    CKD(cudaMalloc(&m->slab, bytes));
+    CKD(cudaMemset(m->slab, 0, bytes));
+    CKD(cudaMalloc(&m->page, SP_WORDS * sizeof(u64)));
+    CKD(cudaMemset(m->page, 0, SP_WORDS * sizeof(u64)));
+    m->peer_page[cfg->rank < MAXR ? cfg->rank : 0] = m->page;
+  }
   int r = build_tables(m);
   if (r) { gmd_destroy(m); return r; }
   // stage grid: ~6 CTAs per SM
@@ -1258,6 +1389,103 @@ int gmd_comm_init(gmd_model *m, const void *id128) {
   NcclId128 id;
   memcpy(id.b, id128, 128);
   NK(g_nccl.CommInitRank(&m->comm, m->cfg.nranks, id, m->cfg.rank));
+  return 0;
+}
+
+struct PeerBlob {  // what gmd_peer_export hands to the host program (<= GMD_PEER_BLOB_BYTES)
+  unsigned magic;
+  int rank, nranks, r0, r1, dev, cap, pad;
+  long long pid;
+  unsigned long long fld_elems;
+  void *slab, *page;
+  cudaIpcMemHandle_t hslab, hpage;
+};
+static_assert(sizeof(PeerBlob) <= GMD_PEER_BLOB_BYTES, "blob size");
+static const unsigned PEER_MAGIC = 0x676d6431u;
+
+int gmd_peer_export(gmd_model *m, void *blob) {
+  if (!m || !blob) return fail(GMD_ERR_ARG, "null argument");
+  int r = set_dev(m);
+  if (r) return r;
+  PeerBlob b;
+  memset(&b, 0, sizeof b);
+  b.magic = PEER_MAGIC;
+  b.rank = m->cfg.rank;
+  b.nranks = m->cfg.nranks;
+  b.r0 = m->geo.r0;
+  b.r1 = m->geo.r1;
+  b.dev = m->dev;
+  b.cap = m->slab_cap;
+  b.pid = (long long)getpid();
+  b.fld_elems = m->fld_elems;
+  b.slab = m->slab;
+  b.page = m->page;
+  CK(cudaIpcGetMemHandle(&b.hslab, m->slab));
+  CK(cudaIpcGetMemHandle(&b.hpage, m->page));
+  memset(blob, 0, GMD_PEER_BLOB_BYTES);
+  memcpy(blob, &b, sizeof b);
+  return 0;
+}
+
+// map one peer allocation: CUDA IPC across processes, the pointer itself (with peer access) inside one process
+static int peer_map(gmd_model *m, const PeerBlob &b, bool want_slab, void **out) {
+  if (b.pid == (long long)getpid()) {
+    if (b.dev != m->dev) {
+      cudaError_t e = cudaDeviceEnablePeerAccess(b.dev, 0);
+      if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+      else if (e != cudaSuccess) return fail(GMD_ERR_COMM, "no peer access from device %d to %d: %s", m->dev, b.dev, cudaGetErrorString(e));
+    }
+    *out = want_slab ? b.slab : b.page;
+    return 0;
+  }
+  cudaError_t e = cudaIpcOpenMemHandle(out, want_slab ? b.hslab : b.hpage, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess)
+    return fail(GMD_ERR_COMM, "cudaIpcOpenMemHandle of rank %d's %s failed: %s", b.rank, want_slab ? "field slab" : "signal page",
+                cudaGetErrorString(e));
+  m->ipc_opened.push_back(*out);
+  return 0;
+}
+
+int gmd_peer_connect(gmd_model *m, const void *blobs, int nblobs) {
+  if (!m || !blobs) return fail(GMD_ERR_ARG, "null argument");
+  const int np = m->cfg.nranks, rank = m->cfg.rank;
+  if (np == 1) return 0;
+  if (nblobs != np) return fail(GMD_ERR_ARG, "%d blobs for %d ranks", nblobs, np);
+  if (np > MAXR) return fail(GMD_ERR_ARG, "the peer-memory path serves up to %d ranks (one node); use gmd_comm_init", MAXR);
+  if (m->p2p) return fail(GMD_ERR_STATE, "gmd_peer_connect called twice");
+  int r = set_dev(m);
+  if (r) return r;
+  if ((r = join(m))) return r;
+  CK(cudaStreamSynchronize(m->stream));
+  std::vector<PeerBlob> B((size_t)np);
+  for (int p = 0; p < np; p++) {
+    memcpy(&B[(size_t)p], (const char *)blobs + (size_t)p * GMD_PEER_BLOB_BYTES, sizeof(PeerBlob));
+    const PeerBlob &b = B[(size_t)p];
+    if (b.magic != PEER_MAGIC || b.rank != p || b.nranks != np) return fail(GMD_ERR_ARG, "blob %d is not rank %d's export", p, p);
+    if (b.cap != m->slab_cap) return fail(GMD_ERR_ARG, "rank %d has a field pool of %d slots, this rank %d", p, b.cap, m->slab_cap);
+  }
+  if (rank > 0 && B[(size_t)rank - 1].r1 != m->geo.r0) return fail(GMD_ERR_ARG, "rank %d's band does not end where this one starts", rank - 1);
+  if (rank + 1 < np && B[(size_t)rank + 1].r0 != m->geo.r1) return fail(GMD_ERR_ARG, "rank %d's band does not start where this one ends", rank + 1);
+  for (int p = 0; p < np; p++) {
+    if (p == rank) {
+      m->peer_page[p] = m->page;
+      continue;
+    }
+    void *q = nullptr;
+    if ((r = peer_map(m, B[(size_t)p], false, &q))) return r;
+    m->peer_page[p] = (u64 *)q;
+    if (p == rank - 1 || p == rank + 1) {
+      const int side = (p == rank - 1) ? 0 : 1;
+      if ((r = peer_map(m, B[(size_t)p], true, &q))) return r;
+      m->peer_slab[side] = (double *)q;
+      m->peer_r0[side] = B[(size_t)p].r0;
+      m->peer_fld[side] = (size_t)B[(size_t)p].fld_elems;
+    }
+  }
+  m->p2p = true;
+  m->xk = m->rk = m->xwaited = 0;
+  for (auto &g : m->graphs) cudaGraphExecDestroy(g.exec);
+  m->graphs.clear();
   return 0;
 }
 
@@ -1449,6 +1677,11 @@ int gmd_sync(gmd_model *m) {
   }
   const int n = m->pending_steps;
   m->pending_steps = 0;
+  if (m->p2p) {
+    u64 err = 0;
+    CK(cudaMemcpy(&err, m->page + SP_ERR, sizeof err, cudaMemcpyDeviceToHost));
+    if (err) return fail(GMD_ERR_COMM, "a wait for a neighbour rank's halo rows or partial sums timed out");
+  }
   return check_nan_last(m, std::max(n, 1));
 }
 
@@ -1592,6 +1825,7 @@ int gmd_predict_correct(gmd_model *m, double dt, int pass) {
   release_state(m, &m->cur);
   m->cur = out;
   if ((r = join(m))) return r;
+  if ((r = unit_end(m))) return r;
   CK(cudaStreamSynchronize(m->stream));
   return 0;
 }
@@ -1606,6 +1840,7 @@ int gmd_ordinary_diffusion(gmd_model *m, double dt) {
   release_state(m, &m->cur);
   m->cur = out;
   if ((r = join(m))) return r;
+  if ((r = unit_end(m))) return r;
   CK(cudaStreamSynchronize(m->stream));
   return 0;
 }
@@ -1727,6 +1962,7 @@ static int time_stage(gmd_model *m, int pass, int mode, int reps, float *ms_per_
   cudaEventDestroy(e1);
   CK(cudaGetLastError());
   *ms_per_launch = ms / reps;
+  if ((r = unit_end(m))) return r;
   release_state(m, &A);
   release_state(m, &B);
   return 0;

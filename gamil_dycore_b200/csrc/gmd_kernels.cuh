@@ -25,6 +25,7 @@
 namespace gmd {
 
 constexpr int GHOST = 2;      // ghost rows on each side of a band
+typedef unsigned long long u64;
 
 enum { PASS_ALL = 0, PASS_FAST = 1, PASS_SLOW = 2 };
 enum { ADV_CENTER = 0, ADV_UPWIND = 1, ADV_WENO = 2 };
@@ -76,12 +77,54 @@ struct StageArgs {
   // row ranges of this launch, selected by blockIdx.z (boundary launches cover two disjoint ranges)
   int rb[2], re[2];
   int pofs[2];       // first partial slot of each range
+  // peer halo: the CTAs of range z wait for halo epoch page[SP_XBASE] + hwait_k from the south (hside[z] & 1) /
+  // north (hside[z] & 2) neighbour before their first load (their rows read ghost rows)
+  u64 *hpage;
+  unsigned hwait_k;
+  int hside[2];
 };
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Peer-memory signalling (latitude bands on the GPUs of one NVLink / NVSwitch node, one process per GPU).
+// Every rank owns a SIGNAL PAGE (device memory, CUDA-IPC mapped by all ranks), 8-byte words:
+// ---------------------------------------------------------------------------------------------------------
+constexpr int MAXR = 8;   // ranks of one node
+enum { SP_SIG = 0,                       // [2] halo epoch released by the south / north neighbour
+       SP_XBASE = 2,                     // local: halo epochs completed before the current unit of work
+       SP_RBASE = 3,                     // local: reductions completed before the current unit of work
+       SP_TICKET = 4,                    // local: CTA ticket of the halo-push kernel
+       SP_ERR = 5,                       // local: set when a wait timed out (reported by gmd_sync)
+       SP_RFLAG = 8,                     // [2][MAXR] reduction epoch released by every rank (parity double buffer)
+       SP_RSLOT = 8 + 2 * MAXR,          // [2][MAXR][2] doubles: the two partial sums of every rank
+       SP_WORDS = 8 + 2 * MAXR + 4 * MAXR };
+
+__device__ __forceinline__ u64 ld_acquire_sys(const u64 *p) {
+  u64 v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(u64 *p, u64 v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// spin until *p >= want; a peer that never arrives (a bug, a dead rank) must not hang the GPU: give up after
+// ~20 s (once: later waits return at once), flag the page, carry on with whatever is there; gmd_sync turns the
+// flag into GMD_ERR_COMM
+__device__ __forceinline__ void spin_until(const u64 *p, u64 want, u64 *page) {
+  if (ld_acquire_sys(p) >= want) return;
+  if (*reinterpret_cast<volatile u64 *>(page + SP_ERR)) return;
+  const long long t0 = clock64();
+  while (ld_acquire_sys(p) < want) {
+    if (clock64() - t0 > 40000000000LL) {
+      *reinterpret_cast<volatile u64 *>(page + SP_ERR) = 1;
+      return;
+    }
+  }
 }
 
 // deterministic block sum (fixed tree); result valid in thread 0; red must hold >= 32 doubles
@@ -311,6 +354,14 @@ __global__ void __launch_bounds__(BX, GMD_MINB) k_stage(const StageArgs a) {
     const int nrec = (jb - ja + 2) * RC_N;
     const double *__restrict__ src = a.t.rowrec + (ptrdiff_t)(ja - 1) * RC_N;
     for (int k = threadIdx.x; k < nrec; k += BX) srow[k] = __ldg(src + k);
+  }
+  if (a.hpage != nullptr && threadIdx.x == 0) {
+    const int hs = a.hside[blockIdx.z];
+    if (hs) {
+      const u64 want = a.hpage[SP_XBASE] + a.hwait_k;
+      if (hs & 1) spin_until(a.hpage + SP_SIG, want, a.hpage);
+      if (hs & 2) spin_until(a.hpage + SP_SIG + 1, want, a.hpage);
+    }
   }
   __syncthreads();
 
@@ -990,9 +1041,19 @@ __global__ void __launch_bounds__(PT) k_polar(const __grid_constant__ PolarArgs 
   }
 }
 
-// sum `n` pairs of partials in index order (deterministic) -> out[0], out[1]
-__global__ void __launch_bounds__(256) k_reduce_pairs(const double *__restrict__ partials, int n, double *out) {
+// sum `n` pairs of partials in index order (deterministic) -> out[0], out[1]; with nranks > 1 the pair is then
+// all-reduced over peer memory in the same launch: every rank stores its pair into every rank's signal page,
+// releases a flag, acquires the flags of all ranks and sums the pairs in rank order (same bits on every rank).
+struct RedArgs {
+  u64 *page;          // my signal page
+  u64 *peer[MAXR];    // every rank's signal page (peer[rank] == page)
+  int rank, nranks;
+  unsigned k;         // reduction epoch = page[SP_RBASE] + k
+};
+__global__ void __launch_bounds__(256) k_reduce_pairs(const double *__restrict__ partials, int n, double *out,
+                                                      const RedArgs r) {
   __shared__ double red[32];
+  __shared__ double gath[2 * MAXR + 2];
   double a0 = 0.0, a1 = 0.0;
   for (int k = threadIdx.x; k < n; k += 256) {
     a0 += partials[2 * k];
@@ -1000,9 +1061,112 @@ __global__ void __launch_bounds__(256) k_reduce_pairs(const double *__restrict__
   }
   const double r0 = block_sum<256>(a0, red);
   const double r1 = block_sum<256>(a1, red);
+  if (r.nranks <= 1) {
+    if (threadIdx.x == 0) {
+      out[0] = r0;
+      out[1] = r1;
+    }
+    return;
+  }
   if (threadIdx.x == 0) {
-    out[0] = r0;
-    out[1] = r1;
+    gath[2 * MAXR] = r0;
+    gath[2 * MAXR + 1] = r1;
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < r.nranks) {
+    const int p = threadIdx.x;
+    const u64 ep = r.page[SP_RBASE] + r.k;
+    const int par = (int)(ep & 1);
+    u64 *pp = r.peer[p];
+    volatile double *slot = reinterpret_cast<volatile double *>(pp + SP_RSLOT) + (par * MAXR + r.rank) * 2;
+    slot[0] = gath[2 * MAXR];
+    slot[1] = gath[2 * MAXR + 1];
+    __threadfence_system();
+    st_release_sys(pp + SP_RFLAG + par * MAXR + r.rank, ep);
+    spin_until(r.page + SP_RFLAG + par * MAXR + p, ep, r.page);
+    const volatile double *mine = reinterpret_cast<const volatile double *>(r.page + SP_RSLOT) + (par * MAXR + p) * 2;
+    gath[2 * p] = mine[0];
+    gath[2 * p + 1] = mine[1];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s0 = 0.0, s1 = 0.0;
+    for (int p = 0; p < r.nranks; p++) {
+      s0 += gath[2 * p];
+      s1 += gath[2 * p + 1];
+    }
+    out[0] = s0;
+    out[1] = s1;
+  }
+}
+
+// Halo rows of up to three fields stored straight into the neighbours' ghost rows, then one release per
+// neighbour.  dstS / dstN are the neighbour's copies of the same buffers, already shifted so that the element
+// offset of (row j, column i) is the one of `src` (gmd.cu: peer_ptr).
+struct PushArgs {
+  Geo g;
+  const double *src[3];
+  double *dstS[3], *dstN[3];
+  int ns[3], nn[3];   // my top `ns` rows go north, my bottom `nn` rows go south
+  u64 *page;          // my signal page
+  u64 *sigS, *sigN;   // the word each neighbour waits on (its SP_SIG+1 / SP_SIG+0), or null
+  unsigned k;         // halo epoch = page[SP_XBASE] + k
+};
+__global__ void __launch_bounds__(256) k_halo_push(const PushArgs a) {
+  const int nlon = a.g.nlon, nr = a.g.r1 - a.g.r0;
+  const int n2 = nlon >> 1;  // 16-byte units per row
+  int first[7];              // prefix of rows: (f0 S, f0 N, f1 S, f1 N, f2 S, f2 N)
+  first[0] = 0;
+#pragma unroll
+  for (int f = 0; f < 3; f++) {
+    first[2 * f + 1] = first[2 * f] + ((a.src[f] && a.dstS[f]) ? a.nn[f] : 0);
+    first[2 * f + 2] = first[2 * f + 1] + ((a.src[f] && a.dstN[f]) ? a.ns[f] : 0);
+  }
+  const int total = first[6] * n2;
+  for (int idx = blockIdx.x * 256 + threadIdx.x; idx < total; idx += gridDim.x * 256) {
+    const int row = idx / n2, c = idx - row * n2;
+    int seg = 0;
+#pragma unroll
+    for (int q = 1; q < 6; q++) seg += (row >= first[q]) ? 1 : 0;
+    const int f = seg >> 1, north = seg & 1, r = row - first[seg];
+    const int lj = north ? nr - a.ns[f] + r : r;
+    const ptrdiff_t o = (ptrdiff_t)lj * nlon + 2 * c;
+    const double2 v = *reinterpret_cast<const double2 *>(a.src[f] + o);
+    double *d = north ? a.dstN[f] : a.dstS[f];
+    *reinterpret_cast<double2 *>(d + o) = v;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    unsigned *ticket = reinterpret_cast<unsigned *>(a.page + SP_TICKET);
+    const unsigned t = atomicAdd(ticket, 1u);
+    if (t == gridDim.x - 1) {  // every CTA's rows are on their way: release both neighbours
+      *ticket = 0;
+      __threadfence_system();
+      const u64 ep = a.page[SP_XBASE] + a.k;
+      if (a.sigS) st_release_sys(a.sigS, ep);
+      if (a.sigN) st_release_sys(a.sigN, ep);
+    }
+  }
+}
+// consumers that are not the stage kernel: block the stream until halo epoch page[SP_XBASE] + k has arrived
+__global__ void k_halo_wait(u64 *page, unsigned k, int sides) {
+  if (threadIdx.x == 0) {
+    const u64 want = page[SP_XBASE] + k;
+    if (sides & 1) spin_until(page + SP_SIG, want, page);
+    if (sides & 2) spin_until(page + SP_SIG + 1, want, page);
+  }
+}
+// end of a unit of work (one model step, one direct API call): all incoming halos of the unit have landed (so the
+// host may touch the ghost rows, and a neighbour may free its slab), then the epoch bases advance.  The epochs
+// inside a unit are base + k with k baked into the launches, which is what makes a captured step replayable.
+__global__ void k_unit_end(u64 *page, unsigned nx, unsigned nred, int sides) {
+  if (threadIdx.x == 0) {
+    const u64 want = page[SP_XBASE] + nx;
+    if (sides & 1) spin_until(page + SP_SIG, want, page);
+    if (sides & 2) spin_until(page + SP_SIG + 1, want, page);
+    page[SP_XBASE] = want;
+    page[SP_RBASE] = page[SP_RBASE] + nred;
   }
 }
 

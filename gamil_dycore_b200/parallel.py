@@ -24,6 +24,28 @@ def halo_rows(rank: int, nranks: int, num_lat: int):
     return south, north
 
 
+def connect(d, group=None, mode: str = "peer"):
+    """wire the ranks of one node together.  mode "peer" (default): all-gather the CUDA-IPC blobs and call
+    gmd_peer_connect (halo rows and all-reduces over NVLink peer memory, no NCCL on the step path);
+    mode "nccl": broadcast an NCCL unique id and call gmd_comm_init (ncclSend/Recv + ncclAllReduce)."""
+    import torch.distributed as dist
+    from . import comm_unique_id
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    if world == 1:
+        return
+    if mode == "peer":
+        blobs = [None] * world
+        dist.all_gather_object(blobs, d.peer_export(), group=group)
+        d.peer_connect(blobs)
+        dist.barrier(group=group)   # nobody stores into a neighbour before every rank has mapped it
+    elif mode == "nccl":
+        uid = [comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0, group=group)
+        d.comm_init(uid[0])
+    else:
+        raise ValueError(mode)
+
+
 def gather_field(local: np.ndarray, num_lat: int, group=None) -> np.ndarray:
     """`local` is a global-shaped array ([num_lat][num_lon] or, for half-latitude fields, [num_lat-1][num_lon]) in
     which only this rank's band rows are filled (what Dycore.state() returns); all ranks receive the assembled

@@ -88,6 +88,16 @@ int gmd_version(void);
    counterpart (parallel_init, src/parallel_mod.F90:75-113, is serial). */
 int gmd_comm_unique_id(void *id128);
 int gmd_comm_init(gmd_model *m, const void *id128);
+
+/* Peer-memory data path for nranks > 1 (one process per GPU on one NVLink / NVSwitch node): every rank exports a
+   blob describing its field slab and its signal page (CUDA IPC handles), the host program gathers the blobs of
+   all ranks in rank order (MPI_Allgather / torch.distributed) and every rank calls gmd_peer_connect.  From then
+   on halo rows are stored straight into the neighbour's ghost rows by this rank's kernels, the neighbour's next
+   boundary launch spins on a release/acquire flag, and the two-scalar all-reduces are one-shot peer exchanges --
+   NCCL is no longer on the step path (gmd_comm_init becomes optional).  No reference counterpart. */
+#define GMD_PEER_BLOB_BYTES 256
+int gmd_peer_export(gmd_model *m, void *blob);
+int gmd_peer_connect(gmd_model *m, const void *blobs, int nblobs);
 /* full-latitude rows [row_begin, row_end) (0-based) owned by this rank */
 int gmd_get_band(const gmd_model *m, int *row_begin, int *row_end);
 

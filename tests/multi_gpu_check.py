@@ -3,7 +3,8 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         tests/multi_gpu_check.py
 
-Every rank builds its latitude band of the same global problem, the bands exchange halos over NCCL inside libgmd,
+Every rank builds its latitude band of the same global problem, the bands exchange halos inside libgmd (argument
+"peer": NVLink peer memory, the default; "nccl": ncclSend/Recv),
 and the gathered result is compared with the CPU oracle.  Exit code 0 = pass.
 """
 import os
@@ -16,6 +17,7 @@ import torch.distributed as dist
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import gamil_dycore_b200 as gmd  # noqa: E402
+from gamil_dycore_b200 import parallel  # noqa: E402
 from oracle.oracle import Oracle, OracleConfig  # noqa: E402
 
 
@@ -40,6 +42,7 @@ def main():
                                      zonal_tend_filter_cutoff_wavenumber=[4, 4]), 3),
     ]
     ok = True
+    mode = sys.argv[1] if len(sys.argv) > 1 else "peer"   # "peer" (NVLink peer memory) or "nccl"
     for tc, kw, nsteps in cases:
         o = Oracle(OracleConfig(**kw))
         o.set_initial_condition(tc)
@@ -49,9 +52,7 @@ def main():
         m0 = o.diag()
         o.step(nsteps)
         d = gmd.Dycore(gmd.Config(rank=rank, nranks=world, device=local, **kw))
-        uid = [gmd.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        d.comm_init(uid[0])
+        parallel.connect(d, mode=mode)
         d.set_state(u, v, gd, ghs)
         d.run_init()
         md0 = d.diag()
@@ -74,7 +75,7 @@ def main():
                 errs[0] < 1e-10 and errs[2] < 1e-11 and (errs[1] < 1e-9))
         ok = ok and good
         if rank == 0:
-            print(f"[{world} ranks] {tc} {kw['num_lon']}x{nlat} {kw['split_scheme']}: rel-L2 u,v,gd = {errs}, "
+            print(f"[{world} ranks, {mode}] {tc} {kw['num_lon']}x{nlat} {kw['split_scheme']}: rel-L2 u,v,gd = {errs}, "
                   f"mass {abs(m / mo - 1):.1e} energy {abs(e / eo - 1):.1e} beta {abs(beta - bo):.1e} -> {'ok' if good else 'FAIL'}",
                   flush=True)
         d.close()

@@ -334,8 +334,10 @@ def test_error_behaviour():
         d.run_init()
 
 
-def test_two_band_decomposition_matches_oracle():
-    """N>1 path on real GPUs: 2 latitude bands over NCCL == oracle (skipped on a single-GPU box)"""
+@pytest.mark.parametrize("mode", ["peer", "nccl"])
+def test_two_band_decomposition_matches_oracle(mode):
+    """N>1 path on real GPUs: 2 latitude bands, halo rows over NVLink peer memory (the product path) or NCCL, ==
+    oracle (skipped on a single-GPU box)"""
     import subprocess
     import sys
     import torch
@@ -344,7 +346,7 @@ def test_two_band_decomposition_matches_oracle():
     import os
     here = os.path.dirname(os.path.abspath(__file__))
     res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-                          "--master-addr", "127.0.0.1", "--master-port", "29531", os.path.join(here, "multi_gpu_check.py")],
+                          "--master-addr", "127.0.0.1", "--master-port", "29531", os.path.join(here, "multi_gpu_check.py"), mode],
                          capture_output=True, text=True, timeout=600)
     print(res.stdout[-3000:], res.stderr[-3000:])
     assert res.returncode == 0
