@@ -35,6 +35,11 @@ WORKLOADS = {
     "sg_0.1deg": ("steady_geostrophic_flow",
                   dict(num_lon=3600, num_lat=1801, time_step_size=10.0, subcycles=10, split_scheme="csp2",
                        zonal_tend_filter_cutoff_wavenumber=[4] * 20)),
+    # one eighth of the 0.1 degree rows: with --gpus 2 each rank holds what an edge rank of the 8-GPU run holds
+    # (development aid for the small-band regime; not a BASELINE configuration)
+    "sg_band8": ("steady_geostrophic_flow",
+                 dict(num_lon=3600, num_lat=451, time_step_size=10.0, subcycles=10, split_scheme="csp2",
+                      zonal_tend_filter_cutoff_wavenumber=[4] * 20)),
     "rh_0.05deg": ("rossby_haurwitz_wave",
                    dict(num_lon=7200, num_lat=3601, time_step_size=2.0, subcycles=10, split_scheme="csp2",
                         zonal_tend_filter_cutoff_wavenumber=[4] * 20)),

@@ -434,6 +434,19 @@ static stage_fn pick_stage(int pass, int adv, int mode) {
   }
 }
 
+// MODE_S1 with the previous predict_correct's update folded in (k_stage LAZY = 1 / 2); never with WENO (its
+// advection terms come from separate sweeps over a stored state)
+static stage_fn pick_stage_lazy(int pass, int adv, int lazy) {
+  if (lazy == 1) {
+    if (pass == PASS_FAST) return k_stage<PASS_FAST, ADV_CENTER, MODE_S1, 1>;
+    if (pass == PASS_ALL) return adv == ADV_UPWIND ? k_stage<PASS_ALL, ADV_UPWIND, MODE_S1, 1> : k_stage<PASS_ALL, ADV_CENTER, MODE_S1, 1>;
+    return adv == ADV_UPWIND ? k_stage<PASS_SLOW, ADV_UPWIND, MODE_S1, 1> : k_stage<PASS_SLOW, ADV_CENTER, MODE_S1, 1>;
+  }
+  if (pass == PASS_FAST) return k_stage<PASS_FAST, ADV_CENTER, MODE_S1, 2>;
+  if (pass == PASS_ALL) return adv == ADV_UPWIND ? k_stage<PASS_ALL, ADV_UPWIND, MODE_S1, 2> : k_stage<PASS_ALL, ADV_CENTER, MODE_S1, 2>;
+  return adv == ADV_UPWIND ? k_stage<PASS_SLOW, ADV_UPWIND, MODE_S1, 2> : k_stage<PASS_SLOW, ADV_CENTER, MODE_S1, 2>;
+}
+
 static int post_launch(gmd_model *m) {
   m->launches++;
   if (m->dry) return 0;
@@ -676,8 +689,16 @@ static void launch_polar(gmd_model *m, int mode, int nitems, PolarArgs &p, cudaS
 }
 
 // one fused operator evaluation (+ update / store / dots) of state E
+// A deferred update handed to the next MODE_S1 launch: E = base + beta ldt L, written out to M
+struct LazyIn {
+  const Tend *L;
+  double ldt;
+  State *M;
+  int kind;   // 1: U, V and gd carry a tendency; 2: U, V only (previous pass was slow)
+};
+
 static int stage(gmd_model *m, int pass, int mode, const State &E, const State *O, double dt, State *N, Tend *T,
-                 const Tend *P) {
+                 const Tend *P, const LazyIn *lz = nullptr) {
   int r;
   const int adv = m->cfg.uv_adv_scheme;
   if (pass != PASS_FAST && adv == ADV_WENO && (r = weno_terms(m, E))) return r;
@@ -695,6 +716,16 @@ static int stage(gmd_model *m, int pass, int mode, const State &E, const State *
   a.beta_lon = m->cfg.uv_adv_upwind_lon_beta;
   a.beta_lat = m->cfg.uv_adv_upwind_lat_beta;
   a.partials = m->d_partials;
+  stage_fn fn = pick_stage(pass, adv, mode);
+  if (lz) {
+    a.LU = lz->L->U; a.LV = lz->L->V; a.Lgd = lz->L->gd;
+    a.MU = lz->M->U; a.MV = lz->M->V; a.Mgd = lz->M->gd;
+    a.OU = lz->M->U; a.OV = lz->M->V; a.Ogd = lz->M->gd;   // for the polar-row kernel: old state == evaluated state
+    a.lip = m->d_ip;
+    a.ldt = lz->ldt;
+    a.lqcon = m->cfg.qcon_modified;
+    fn = pick_stage_lazy(pass, adv, lz->kind);
+  }
   const int r0 = m->geo.r0, r1 = m->geo.r1;
   int nst;
   if (use_split(m)) {
@@ -712,12 +743,12 @@ static int stage(gmd_model *m, int pass, int mode, const State &E, const State *
     b.rb[0] = r0; b.re[0] = r0 + m->bs; b.pofs[0] = 0;
     b.rb[1] = r1 - m->bn; b.re[1] = r1; b.pofs[1] = m->nbx * m->nchunks_b;
     dim3 gb((unsigned)m->nbx, (unsigned)m->nchunks_b, 2);
-    if (!m->dry) pick_stage(pass, adv, mode)<<<gb, BX, m->stage_smem_b, m->stream>>>(b);
+    if (!m->dry) fn<<<gb, BX, m->stage_smem_b, m->stream>>>(b);
     if ((r = post_launch(m))) return r;
     a.rows_per_cta = m->rows_per_cta;
     a.rb[0] = r0 + m->bs; a.re[0] = r1 - m->bn; a.pofs[0] = 2 * m->nbx * m->nchunks_b;
     dim3 gi((unsigned)m->nbx, (unsigned)m->nchunks_i, 1);
-    if (!m->dry) pick_stage(pass, adv, mode)<<<gi, BX, m->stage_smem, m->stream2>>>(a);
+    if (!m->dry) fn<<<gi, BX, m->stage_smem, m->stream2>>>(a);
     if ((r = post_launch(m))) return r;
     if ((r = split_end(m))) return r;
     nst = 2 * m->nbx * m->nchunks_b + m->nbx * m->nchunks_i;
@@ -727,7 +758,7 @@ static int stage(gmd_model *m, int pass, int mode, const State &E, const State *
     a.rows_per_cta = m->rows_per_cta;
     a.rb[0] = r0; a.re[0] = r1; a.pofs[0] = 0;
     dim3 grid((unsigned)m->nbx, (unsigned)m->nchunks, 1);
-    if (!m->dry) pick_stage(pass, adv, mode)<<<grid, BX, m->stage_smem, m->stream>>>(a);
+    if (!m->dry) fn<<<grid, BX, m->stage_smem, m->stream>>>(a);
     if ((r = post_launch(m))) return r;
     nst = m->nbx * m->nchunks;
   }
@@ -741,7 +772,7 @@ static int stage(gmd_model *m, int pass, int mode, const State &E, const State *
     p.g = m->geo;
     p.t = m->tab;
     fill_items(p, m->items[li]);
-    p.EU = a.EU; p.EV = a.EV; p.Egd = a.Egd; p.ghs = a.ghs;
+    p.EU = lz ? a.MU : a.EU; p.EV = lz ? a.MV : a.EV; p.Egd = lz ? a.Mgd : a.Egd; p.ghs = a.ghs;
     p.OU = a.OU; p.OV = a.OV; p.Ogd = a.Ogd;
     p.NU = a.NU; p.NV = a.NV; p.Ngd = a.Ngd;
     p.TU = a.TU; p.TV = a.TV; p.Tgd = a.Tgd;
@@ -802,27 +833,69 @@ static int update(gmd_model *m, const State &O, const Tend &T, double dt, int be
   return post_launch(m);
 }
 
-// predict_correct(dt, O -> *out, pass), src/dycore_mod.F90:754-792.  *out is a fresh state; O is kept.
-static int predict_correct(gmd_model *m, double dts, const State &O, int pass, State *out) {
+// A state handed from one predict_correct to the next.  `deferred`: the value is base + beta dts tendNew with beta
+// from the inner products still on the device -- the last update_state of predict_correct (src/dycore_mod.F90:
+// 786-790) has not been run; the next predict_correct folds it into its first operator sweep (k_stage LAZY), which
+// saves one full sweep over the state (9 words per column) and one launch + halo exchange per predict_correct.
+struct Carry {
+  State base;
+  bool deferred = false;
+  double dts = 0.0;
+  bool with_gd = false;   // tendNew.gd takes part (the pass that produced it was not slow)
+};
+
+// predict_correct(dt, in -> *out, pass), src/dycore_mod.F90:754-792.  `in.base` is kept (the caller releases it);
+// with `defer_out` the result is returned deferred (out->base = the old state of THIS call, retained once more).
+static int predict_correct(gmd_model *m, double dts, const Carry &in, int pass, bool defer_out, Carry *out) {
   int r;
   const bool slow = (pass == PASS_SLOW);
   const double dt = dts * 0.5;
-  State A, B;
+  State O = in.base, M, A, B;
+  bool ownO = false;
+  if (in.deferred) {
+    // old state of this call = in.base + beta in.dts tendNew, materialised by the first sweep
+    if ((r = new_state(m, &M, in.with_gd ? nullptr : in.base.gd))) return r;
+    O = M;
+    ownO = true;
+  }
   if ((r = new_state(m, &A, slow ? O.gd : nullptr))) return r;
   if ((r = new_state(m, &B, slow ? O.gd : nullptr))) return r;
   // tend(old) = L(old); new = old + dt/2 tend(old)
-  if ((r = stage(m, pass, MODE_S1, O, &O, dt, &A, &m->tendOld, nullptr))) return r;
+  if (in.deferred) {
+    LazyIn lz = {&m->tendNew, in.dts, &M, in.with_gd ? 1 : 2};
+    if ((r = stage(m, pass, MODE_S1, in.base, nullptr, dt, &A, &m->tendOld, nullptr, &lz))) return r;
+  } else {
+    if ((r = stage(m, pass, MODE_S1, O, &O, dt, &A, &m->tendOld, nullptr))) return r;
+  }
   if ((r = exchange_state(m, A, !slow))) return r;
   // tend(old) = L(new); new = old + dt/2 tend(old)
   if ((r = stage(m, pass, MODE_S2, A, &O, dt, &B, &m->tendOld, nullptr))) return r;
   if ((r = exchange_state(m, B, !slow))) return r;
   // tend(new) = L(new); ip1 = <tend(old), tend(new)>, ip2 = <tend(new), tend(new)>
   if ((r = stage(m, pass, MODE_S3A, B, nullptr, 0.0, nullptr, &m->tendNew, &m->tendOld))) return r;
+  release_state(m, &B);
+  if (defer_out) {
+    // new = old + dt beta tend(new) is left to the next call: it needs the ghost rows of tend(new)
+    const State tv = {m->tendNew.U, m->tendNew.V, m->tendNew.gd};
+    if ((r = exchange_state(m, tv, !slow))) return r;
+    release_state(m, &A);
+    out->base = O;
+    if (!ownO) {  // the caller still owns in.base: take our own references
+      retain(m, O.U);
+      retain(m, O.V);
+      retain(m, O.gd);
+    }
+    out->deferred = true;
+    out->dts = dts;
+    out->with_gd = !slow;
+    return 0;
+  }
   // new = old + dt beta tend(new)
   if ((r = update(m, O, m->tendNew, dts, 1, 0.0, !slow, &A))) return r;
   if ((r = exchange_state(m, A, !slow))) return r;
-  release_state(m, &B);
-  *out = A;
+  if (ownO) release_state(m, &M);
+  out->base = A;
+  out->deferred = false;
   return 0;
 }
 
@@ -831,16 +904,21 @@ static int csp2(gmd_model *m, const State &in, State *out) {
   int r;
   const double dtm = m->cfg.time_step_size;
   const double fast_dt = dtm / m->cfg.subcycles;
-  State s0, s1;
-  if ((r = predict_correct(m, 0.5 * dtm, in, PASS_SLOW, &s0))) return r;
+  static const bool no_lazy = getenv("GMD_NO_LAZY") != nullptr;
+  const bool lazy = !no_lazy && m->cfg.uv_adv_scheme != ADV_WENO;
+  Carry c0, c1;
+  c0.base = in;
+  if ((r = predict_correct(m, 0.5 * dtm, c0, PASS_SLOW, lazy, &c1))) return r;
   for (int k = 0; k < m->cfg.subcycles; k++) {
-    if ((r = predict_correct(m, fast_dt, s0, PASS_FAST, &s1))) return r;
-    release_state(m, &s0);
-    s0 = s1;
+    Carry c2;
+    if ((r = predict_correct(m, fast_dt, c1, PASS_FAST, lazy, &c2))) return r;
+    release_state(m, &c1.base);
+    c1 = c2;
   }
-  if ((r = predict_correct(m, 0.5 * dtm, s0, PASS_SLOW, &s1))) return r;
-  release_state(m, &s0);
-  *out = s1;
+  Carry c3;
+  if ((r = predict_correct(m, 0.5 * dtm, c1, PASS_SLOW, false, &c3))) return r;
+  release_state(m, &c1.base);
+  *out = c3.base;
   return 0;
 }
 
@@ -1019,7 +1097,12 @@ static int one_step(gmd_model *m) {
   switch (m->cfg.split_scheme) {
     case GMD_SPLIT_CSP2: r = csp2(m, m->cur, &next); break;
     case GMD_SPLIT_ISP: r = isp(m, m->cur, &next); break;
-    default: r = predict_correct(m, m->cfg.time_step_size, m->cur, PASS_ALL, &next);
+    default: {
+      Carry ci, co;
+      ci.base = m->cur;
+      r = predict_correct(m, m->cfg.time_step_size, ci, PASS_ALL, false, &co);
+      next = co.base;
+    }
   }
   if (r) return r;
   release_state(m, &m->cur);
@@ -1820,8 +1903,10 @@ int gmd_predict_correct(gmd_model *m, double dt, int pass) {
   if (pass < 0 || pass > 2) return fail(GMD_ERR_ARG, "bad pass %d", pass);
   int r = set_dev(m);
   if (r) return r;
-  State out;
-  if ((r = predict_correct(m, dt, m->cur, pass, &out))) return r;
+  Carry ci, co;
+  ci.base = m->cur;
+  if ((r = predict_correct(m, dt, ci, pass, false, &co))) return r;
+  const State out = co.base;
   release_state(m, &m->cur);
   m->cur = out;
   if ((r = join(m))) return r;
@@ -1946,6 +2031,13 @@ static int time_stage(gmd_model *m, int pass, int mode, int reps, float *ms_per_
   if ((r = join(m))) return r;
   dim3 grid((unsigned)m->nbx, (unsigned)m->nchunks, 1);
   stage_fn fn = pick_stage(pass, m->cfg.uv_adv_scheme, mode);
+  if (mode == 4) {  // MODE_S1 with the deferred update folded in: E = cur + beta dt tendNew -> A (= M), N = B
+    a.LU = m->tendNew.U; a.LV = m->tendNew.V; a.Lgd = m->tendNew.gd;
+    a.MU = A.U; a.MV = A.V; a.Mgd = A.gd;
+    a.EU = m->cur.U; a.EV = m->cur.V; a.Egd = m->cur.gd;
+    a.lip = m->d_ip; a.ldt = dt; a.lqcon = m->cfg.qcon_modified;
+    fn = pick_stage_lazy(pass, m->cfg.uv_adv_scheme == ADV_WENO ? ADV_CENTER : m->cfg.uv_adv_scheme, slow ? 2 : 1);
+  }
   cudaEvent_t e0, e1;
   CK(cudaEventCreate(&e0));
   CK(cudaEventCreate(&e1));
@@ -1987,12 +2079,12 @@ int gmd_time_stage_kernel(gmd_model *m, int reps, float *ms_per_launch, double *
 int gmd_time_stage_variant(gmd_model *m, int pass, int mode, int reps, float *ms_per_launch, double *alg_bytes) {
   if (!m || !ms_per_launch) return fail(GMD_ERR_ARG, "null argument");
   if (!m->run_inited) return fail(GMD_ERR_STATE, "gmd_run_init has not been called");
-  if (reps < 1 || pass < 0 || pass > 2 || mode < 0 || mode > 3) return fail(GMD_ERR_ARG, "bad argument");
+  if (reps < 1 || pass < 0 || pass > 2 || mode < 0 || mode > 4) return fail(GMD_ERR_ARG, "bad argument");
   int r = set_dev(m);
   if (r) return r;
   if ((r = time_stage(m, pass, mode, reps, ms_per_launch))) return r;
   // words per column: fast/all S1 7, S2 13, S3a 10; slow S1 5, S2 9, S3a 7; EVAL = reads + 3 (2) writes
-  static const double words[2][4] = {{7, 13, 10, 7}, {5, 9, 7, 5}};
+  static const double words[2][5] = {{7, 13, 10, 7, 13}, {5, 9, 7, 5, 9}};
   if (alg_bytes) *alg_bytes = words[pass == PASS_SLOW ? 1 : 0][mode] * 8.0 * (double)m->nr * (double)m->geo.nlon;
   return 0;
 }

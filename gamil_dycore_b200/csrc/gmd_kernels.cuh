@@ -82,7 +82,21 @@ struct StageArgs {
   u64 *hpage;
   unsigned hwait_k;
   int hside[2];
+  // deferred update (LAZY variants of MODE_S1): the evaluated state is E = (EU,EV,Egd) + beta ldt (LU,LV,Lgd), the
+  // last update_state of the previous predict_correct (src/dycore_mod.F90:786-790) folded into this sweep; E is
+  // also written out to (MU,MV,Mgd) on the rows of this CTA (and on the band's ghost rows by the edge CTAs)
+  const double *LU, *LV, *Lgd;
+  double *MU, *MV, *Mgd;
+  const double *lip;
+  double ldt;
+  int lqcon;
 };
+
+// beta of predict_correct (src/dycore_mod.F90:784-785) from the device-resident inner products
+__device__ __forceinline__ double beta_from_ip(const double *ip, int qcon) {
+  const double ip1 = ip[0], ip2 = ip[1];
+  return (qcon && ip1 != 0.0 && ip2 != 0.0) ? ip1 / ip2 : 1.0;
+}
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -176,6 +190,12 @@ __device__ __forceinline__ void st2(double *p, double x, double y) {
 #endif
 #ifndef GMD_MINB
 #define GMD_MINB 4   // 4 CTAs x 128 threads per SM => <= 128 registers (measured best, profiles/r1_c_stage_tuning.txt)
+#endif
+#ifndef GMD_LAZY_UNROLL
+#define GMD_LAZY_UNROLL 1
+#endif
+#ifndef GMD_LAZY_MINB
+#define GMD_LAZY_MINB GMD_MINB
 #endif
 #define GMD_PRAGMA_(x) _Pragma(#x)
 #define GMD_UNROLL_PRAGMA(n) GMD_PRAGMA_(unroll n)
@@ -329,8 +349,10 @@ constexpr int WOUT = 60;  // output columns per warp strip (64 held)
 constexpr int SW = 4;     // warps per CTA
 constexpr int BX = SW * 32;
 
-template <int PASS, int ADV, int MODE>
-__global__ void __launch_bounds__(BX, GMD_MINB) k_stage(const StageArgs a) {
+// LAZY: 0 = E is read as stored; 1 = E = base + beta ldt L (U, V and gd); 2 = the same for U, V only (the previous
+// predict_correct was a slow pass: gd unchanged)
+template <int PASS, int ADV, int MODE, int LAZY = 0>
+__global__ void __launch_bounds__(BX, (LAZY ? GMD_LAZY_MINB : GMD_MINB)) k_stage(const StageArgs a) {
   __shared__ double red[2 * SW];
   extern __shared__ double srow[];  // row records of rows ja-1 .. jb: [(jb - ja + 2)][RC_N]
   const int nlon = a.g.nlon, nlat = a.g.nlat, r0 = a.g.r0;
@@ -376,22 +398,71 @@ __global__ void __launch_bounds__(BX, GMD_MINB) k_stage(const StageArgs a) {
 #define ATK(p, k) ((p) + (off + (ptrdiff_t)(k) * nl))
 #define AT(p, jj) ATK(p, (jj) - j)
     const D2 zero2 = {0.0, 0.0};
+    // ---- deferred update: E(row r) = base + bdt * L on the rows where update_state applies, stored to M on the rows
+    //      this CTA is responsible for (its own rows; the band's ghost rows for the CTAs at the band edges)
+    double bdt = 0.0;
+    if (LAZY) bdt = a.ldt * beta_from_ip(a.lip, a.lqcon);
+    const bool edgeS = LAZY && (ja == r0) && (r0 > 0), edgeN = LAZY && (jb == a.g.r1) && (a.g.r1 < nlat);
+    auto mineUV = [&](int r) { return (r >= ja && r < jb) || (edgeS && r == ja - 1) || (edgeN && r == jb); };
+    auto mineG = [&](int r) { return (r >= ja && r < jb) || (edgeS && r == ja - 1) || (edgeN && (r == jb || r == jb + 1)); };
+    auto combU = [&](D2 b, D2 t, int r) -> D2 {
+      if (r >= 1 && r <= nlat - 2) { b.x = fma(bdt, t.x, b.x); b.y = fma(bdt, t.y, b.y); }
+      return b;
+    };
+    auto combV = [&](D2 b, D2 t, int r) -> D2 {
+      if (r >= 0 && r <= nlat - 2) { b.x = fma(bdt, t.x, b.x); b.y = fma(bdt, t.y, b.y); }
+      return b;
+    };
+    auto combG = [&](D2 b, D2 t, int r) -> D2 {
+      if (r >= 0 && r <= nlat - 1) { b.x = fma(bdt, t.x, b.x); b.y = fma(bdt, t.y, b.y); }
+      return b;
+    };
     // ---- prologue: rows ja-1, ja, ja+1 of sqrt(gd); rows ja-1, ja of U, V; gh row ja --------------------
     D2 sm_, s0, sp, sq, u0, up, vm, v0, vp, Um, U0, Up, Vm, V0, Vp;
     D2 g0 = zero2, gp = zero2;
+    D2 graw = zero2;   // LAZY: gd of row j (the base of this row's update)
+    D2 a2keep = zero2;
 #if GMD_STRICT
     D2 h0 = zero2, hp = zero2;  // ghs rows j, j+1 (g0/gp then hold gd alone)
 #endif
     {
       const int j = ja;
-      const D2 a0 = ld2(AT(a.Egd, ja - 1)), a1 = ld2(AT(a.Egd, ja)), a2 = ld2(AT(a.Egd, ja + 1));
-      sm_.x = fast_sqrt(a0.x); sm_.y = fast_sqrt(a0.y);
-      s0.x = fast_sqrt(a1.x); s0.y = fast_sqrt(a1.y);
-      sp.x = fast_sqrt(a2.x); sp.y = fast_sqrt(a2.y);
+      D2 a0 = ld2(AT(a.Egd, ja - 1)), a1 = ld2(AT(a.Egd, ja)), a2 = ld2(AT(a.Egd, ja + 1));
       Um = ld2(AT(a.EU, ja - 1));
       U0 = ld2(AT(a.EU, ja));
       Vm = ld2(AT(a.EV, ja - 1));
       V0 = ld2(AT(a.EV, ja));
+      if (LAZY) {
+        const D2 tUm = ld2(AT(a.LU, ja - 1)), tU0 = ld2(AT(a.LU, ja)), tVm = ld2(AT(a.LV, ja - 1)), tV0 = ld2(AT(a.LV, ja));
+        if (LAZY == 1) {
+          const D2 t0 = ld2(AT(a.Lgd, ja - 1)), t1 = ld2(AT(a.Lgd, ja)), t2 = ld2(AT(a.Lgd, ja + 1));
+          a0 = combG(a0, t0, ja - 1);
+          a1 = combG(a1, t1, ja);
+          a2 = combG(a2, t2, ja + 1);
+          if (out) {
+            if (mineG(ja - 1)) st2(AT(a.Mgd, ja - 1), a0.x, a0.y);
+            st2(AT(a.Mgd, ja), a1.x, a1.y);
+            if (mineG(ja + 1)) st2(AT(a.Mgd, ja + 1), a2.x, a2.y);
+          }
+        }
+        Um = combU(Um, tUm, ja - 1);
+        U0 = combU(U0, tU0, ja);
+        Vm = combV(Vm, tVm, ja - 1);
+        V0 = combV(V0, tV0, ja);
+        if (out) {
+          if (mineUV(ja - 1)) {
+            st2(AT(a.MU, ja - 1), Um.x, Um.y);
+            st2(AT(a.MV, ja - 1), Vm.x, Vm.y);
+          }
+          st2(AT(a.MU, ja), U0.x, U0.y);
+          st2(AT(a.MV, ja), V0.x, V0.y);
+        }
+        graw = a1;
+        a2keep = a2;
+      }
+      sm_.x = fast_sqrt(a0.x); sm_.y = fast_sqrt(a0.y);
+      s0.x = fast_sqrt(a1.x); s0.y = fast_sqrt(a1.y);
+      sp.x = fast_sqrt(a2.x); sp.y = fast_sqrt(a2.y);
       if (need_gh) {
         const D2 hs = ld2(AT(a.ghs, ja));
 #if GMD_STRICT
@@ -423,23 +494,51 @@ __global__ void __launch_bounds__(BX, GMD_MINB) k_stage(const StageArgs a) {
     D2 n_U = ld2(ATK(a.EU, 1));
     D2 n_V = ld2(ATK(a.EV, 1));
     D2 n_gd1 = zero2, n_hs = zero2;
+    D2 n_tg = zero2, n_tU = zero2, n_tV = zero2;   // LAZY: the tendency rows travelling with n_gd2, n_U, n_V
+    if (LAZY) {
+      if (LAZY == 1) n_tg = ld2(ATK(a.Lgd, 2));
+      n_tU = ld2(ATK(a.LU, 1));
+      n_tV = ld2(ATK(a.LV, 1));
+    }
     if (need_gh) {
-      n_gd1 = ld2(ATK(a.Egd, 1));
+      n_gd1 = LAZY ? a2keep : ld2(ATK(a.Egd, 1));
       n_hs = ld2(ATK(a.ghs, 1));
     }
 
-    GMD_UNROLL_PRAGMA(GMD_UNROLL)
+    // measured on B200 (tools/tune_stage.py): the deferred-update variants and S2 are fastest without unrolling (no
+    // spills at the 128-register cap), S1 / S3a with two rows per trip
+    constexpr int kUnroll = LAZY ? GMD_LAZY_UNROLL : (MODE == MODE_S2 ? 1 : GMD_UNROLL);
+#pragma unroll kUnroll
     for (int j = ja; j < jb; j++) {
       // ---- issue every load of this iteration first: the next row of the evaluated state (consumed one
       //      iteration later) and the operands of this row's update (consumed at the end of this iteration) ---
-      const D2 c_gd2 = n_gd2, c_U = n_U, c_V = n_V, c_gd1 = n_gd1, c_hs = n_hs;
-      if (need_gh) n_gd1 = c_gd2;  // gd(j+2) is next iteration's gd(j'+1)
+      D2 c_gd2 = n_gd2, c_U = n_U, c_V = n_V;
+      const D2 c_gd1 = n_gd1, c_hs = n_hs;
+      const D2 c_tg = n_tg, c_tU = n_tU, c_tV = n_tV;
       if (j + 1 < jb) {
         n_gd2 = ld2(AT(a.Egd, j + 3));
         n_U = ld2(AT(a.EU, j + 2));
         n_V = ld2(AT(a.EV, j + 2));
         if (need_gh) n_hs = ld2(AT(a.ghs, j + 2));
+        if (LAZY) {
+          if (LAZY == 1) n_tg = ld2(AT(a.Lgd, j + 3));
+          n_tU = ld2(AT(a.LU, j + 2));
+          n_tV = ld2(AT(a.LV, j + 2));
+        }
       }
+      if (LAZY) {
+        if (LAZY == 1) {
+          c_gd2 = combG(c_gd2, c_tg, j + 2);
+          if (out && mineG(j + 2)) st2(AT(a.Mgd, j + 2), c_gd2.x, c_gd2.y);
+        }
+        c_U = combU(c_U, c_tU, j + 1);
+        c_V = combV(c_V, c_tV, j + 1);
+        if (out && mineUV(j + 1)) {
+          st2(AT(a.MU, j + 1), c_U.x, c_U.y);
+          st2(AT(a.MV, j + 1), c_V.x, c_V.y);
+        }
+      }
+      if (need_gh) n_gd1 = c_gd2;  // gd(j+2) is next iteration's gd(j'+1)
       const double *__restrict__ rc = srow + (j - ja + 1) * RC_N;
       const unsigned fl = (unsigned)rc[RC_FLAGS];
       const bool rowU = (j >= 1 && j <= nlat - 2);
@@ -448,10 +547,15 @@ __global__ void __launch_bounds__(BX, GMD_MINB) k_stage(const StageArgs a) {
       D2 oU = zero2, oV = zero2, oG = zero2, pU = zero2, pV = zero2, pG = zero2;
       D2 wul = zero2, wut = zero2, wvl = zero2, wvt = zero2;
       if (out) {
-        if (upd) {
+        if (upd && !LAZY) {
           oU = ld2(AT(a.OU, j));
           if (rowV) oV = ld2(AT(a.OV, j));
           if (rowG) oG = ld2(AT(a.Ogd, j));
+        }
+        if (upd && LAZY) {  // old state == evaluated state, already on chip
+          oU = U0;
+          oV = V0;
+          oG = graw;
         }
         if (MODE == MODE_S3A) {
           if (rowU) pU = ld2(AT(a.PU, j));
@@ -589,6 +693,7 @@ __global__ void __launch_bounds__(BX, GMD_MINB) k_stage(const StageArgs a) {
 #if GMD_STRICT
       h0 = hp;
 #endif
+      if (LAZY) graw = c_gd1;
       uw_a = unw_a;
       Uw_a = Unw_a;
       Vse_b = Ve_b;
@@ -1187,10 +1292,6 @@ struct UpdateArgs {
   int rb[2], re[2];   // up to two row ranges handled by this launch (empty when rb >= re)
 };
 
-__device__ __forceinline__ double beta_from_ip(const double *ip, int qcon) {
-  const double ip1 = ip[0], ip2 = ip[1];
-  return (qcon && ip1 != 0.0 && ip2 != 0.0) ? ip1 / ip2 : 1.0;
-}
 
 // update_state on stored tendencies (src/dycore_mod.F90:600-652), U/V/gd only: new = old + dt' * tend
 __global__ void __launch_bounds__(256) k_update(const UpdateArgs a) {

@@ -22,7 +22,7 @@ for lib in libs:
     d.run_init()
     out = {}
     for p in ("fast", "slow"):
-        for mode, nm in ((0, "S1"), (1, "S2"), (2, "S3a")):
+        for mode, nm in ((0, "S1"), (1, "S2"), (2, "S3a"), (4, "S1lazy")):
             d.time_stage_variant(p, mode, 3)
             ms, nb = d.time_stage_variant(p, mode, 20)
             out[f"{p}.{nm}"] = (round(ms * 1e3, 1), round(nb / ms / 1e6))
