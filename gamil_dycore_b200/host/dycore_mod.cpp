@@ -8,6 +8,7 @@
 #include "../../include/gmd.h"
 #include "history.h"
 #include "log.h"
+#include "restart.h"
 
 namespace host {
 
@@ -41,6 +42,11 @@ void dycore_init() {
     log_notice("Create output dataset " + params.case_name + ".h0.");
     log_notice("Create output dataset " + params.case_name + ".debug.");
     log_notice("History module is initialized.");
+    // restart_init, src/restart_mod.F90:22-35
+    if (!TimeManager::parse_period(params.restart_period, period))
+      log_error("Invalid IO period " + params.restart_period + "!");
+    timer.add_alert("restart.output", period);
+    log_notice("Create output dataset " + params.case_name + ".r.");
   }
   log_notice("Data module is initialized.");
   log_notice("Filter module is initialized.");
@@ -76,22 +82,33 @@ void dycore_init() {
   log_notice("Dycore module is initialized.");
 }
 
-void dycore_restart() {
-  log_error("restart runs are not supported by this build (the reference's restart_mod writes shifted data, "
-            "see DESIGN.md)");
+void dycore_restart() {  // restart_read, src/restart_mod.F90:39-56
+  log_notice("Create input dataset " + params.restart_file + ".");
+  std::string when, err;
+  if (!restart_read(params.restart_file, params.num_lon, params.num_lat, state_ic.u, state_ic.v, state_ic.gd,
+                    state_ic.ghs, when, err))
+    log_error(err);
+  DateTime t;
+  if (!parse_time_format(when, t)) log_error("Invalid restart_time " + when + "!");
+  timer.reset_start_time(t);   // time_reset_start_time, src/time_mod.F90:81-91
+  log_notice("Reset time to " + timer.curr_time_format + ".");
 }
 
 static void output() {  // src/dycore_mod.F90:175-182
-  if (!timer.is_alerted("hist0.output")) return;
+  const bool hist = timer.is_alerted("hist0.output"), rst = timer.is_alerted("restart.output");
+  if (!hist && !rst) return;
   const int nlon = params.num_lon, nlat = params.num_lat;
   const size_t nf = (size_t)nlon * nlat, nh = (size_t)nlon * (nlat - 1);
   std::vector<double> u(nf), v(nh), gd(nf), vor(nh), div(nf);
   check(gmd_get_state(model, u.data(), v.data(), gd.data(), GMD_LAYOUT_COMPACT));
-  check(gmd_get_vor_div(model, vor.data(), div.data(), GMD_LAYOUT_COMPACT));
-  double m = 0, e = 0, b = 0;
-  check(gmd_get_diag(model, &m, &e, &b));
   std::string path, err;
-  if (!history_write(params, timer, u, v, gd, state_ic.ghs, vor, div, e, m, path, err)) log_error(err);
+  if (hist) {
+    check(gmd_get_vor_div(model, vor.data(), div.data(), GMD_LAYOUT_COMPACT));
+    double m = 0, e = 0, b = 0;
+    check(gmd_get_diag(model, &m, &e, &b));
+    if (!history_write(params, timer, u, v, gd, state_ic.ghs, vor, div, e, m, path, err)) log_error(err);
+  }
+  if (rst && !restart_write(params, timer, u, v, gd, state_ic.ghs, path, err)) log_error(err);
 }
 
 void dycore_run() {
@@ -106,7 +123,8 @@ void dycore_run() {
   std::vector<double> ms, es, bs;
   while (!timer.is_finished()) {
     // steps are batched up to the next output alert: one launch sequence, one sync, one read of the diag series
-    long n = std::min(timer.steps_until_alert("hist0.output"), timer.steps_until_end());
+    long n = std::min(std::min(timer.steps_until_alert("hist0.output"), timer.steps_until_alert("restart.output")),
+                      timer.steps_until_end());
     n = std::max(1L, std::min(n, 2048L));
     check(gmd_step(model, (int)n));
     ms.assign((size_t)n, 0.0); es.assign((size_t)n, 0.0); bs.assign((size_t)n, 0.0);

@@ -14,7 +14,7 @@ extern Fields state_ic;    // state(old)%{u,v,gd}, static%ghs as filled by the I
 extern TimeManager timer;  // time_mod globals
 
 void dycore_init();     // src/dycore_mod.F90:60-111
-void dycore_restart();  // :113-117 (restart_read) -- not supported: the reference's restart I/O is broken as shipped
+void dycore_restart();  // :113-117 (restart_read): state + clock from a `<case>.r.<time>.nc` file (host/restart.h)
 void dycore_run();      // :119-142
 void dycore_final();    // :144-157
 

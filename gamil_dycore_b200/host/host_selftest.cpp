@@ -10,6 +10,7 @@
 #include <string>
 
 #include "history.h"
+#include "restart.h"
 #include "log.h"
 #include "params.h"
 #include "test_cases.h"
@@ -74,6 +75,22 @@ int main(int argc, char **argv) {
     if (!history_write(p, tm, f.u, f.v, f.gd, f.ghs, vor, div, 2.5, 1.5, path, err)) { printf("ERROR: %s\n", err.c_str()); return 2; }
     printf("%s\n", path.c_str());
     return 0;
+  }
+  if (cmd == "restart" && argc >= 4) {
+    // write a restart file from the analytic initial condition after argv[3] clock steps, read it back, compare bits
+    Fields f, g;
+    std::string notice, err, path, when;
+    if (!set_initial_condition(p, f, notice, err)) { printf("ERROR: %s\n", err.c_str()); return 2; }
+    TimeManager tm;
+    tm.init(p);
+    for (int k = 0; k < atoi(argv[3]); k++) tm.advance();
+    if (!restart_write(p, tm, f.u, f.v, f.gd, f.ghs, path, err)) { printf("ERROR: %s\n", err.c_str()); return 2; }
+    if (!restart_read(path, p.num_lon, p.num_lat, g.u, g.v, g.gd, g.ghs, when, err)) { printf("ERROR: %s\n", err.c_str()); return 2; }
+    DateTime t;
+    if (!parse_time_format(when, t)) { printf("ERROR: bad restart_time %s\n", when.c_str()); return 2; }
+    const bool same = f.u == g.u && f.v == g.v && f.gd == g.gd && f.ghs == g.ghs && t.sec == tm.curr_time.sec;
+    printf("%s\n%s\n%s\n", path.c_str(), when.c_str(), same ? "identical" : "DIFFERENT");
+    return same ? 0 : 4;
   }
   if (cmd == "clock" && argc >= 4) {
     TimeManager tm;

@@ -87,6 +87,12 @@ struct TimeManager {
     start_time_format = start_time.format(false);
     curr_time_format = curr_time.format(false);
   }
+  void reset_start_time(const DateTime &t) {  // time_reset_start_time, src/time_mod.F90:81-91
+    start_time = t;
+    curr_time = t;
+    start_time_format = start_time.format(false);
+    curr_time_format = curr_time.format(false);
+  }
   // "<value> <units>" as in history_periods (src/io_mod.F90:202-222)
   static bool parse_period(const std::string &s, double &seconds) {
     double v = 0;

@@ -379,7 +379,9 @@ def test_dycore_test_driver_end_to_end(tmp_path):
     m0, e0, _ = o.diag()
     # the log prints 14 significant digits (E20.14); the oracle sums serially, the GPU in a fixed tree
     assert abs(float(steps[0].split()[2]) / m0 - 1) < 3e-13 and abs(float(steps[0].split()[3]) / e0 - 1) < 3e-13
-    frames = sorted(p for p in os.listdir(tmp_path) if p.endswith(".nc"))
+    restarts = sorted(p for p in os.listdir(tmp_path) if ".r." in p and p.endswith(".nc"))
+    assert restarts == []   # restart_period = '10 days' in this namelist, the run lasts 2
+    frames = sorted(p for p in os.listdir(tmp_path) if ".h0." in p and p.endswith(".nc"))
     assert frames == ["mz_c_u_01.180x90.dt720.h0.0001-01-02T00:00:00Z.nc", "mz_c_u_01.180x90.dt720.h0.0001-01-03T00:00:00Z.nc"]
     for k, name in enumerate(frames):
         o.step(120)
@@ -395,3 +397,57 @@ def test_dycore_test_driver_end_to_end(tmp_path):
         last = steps[120 * (k + 1)].split()
         # the log prints 14 significant digits (E20.14)
         assert abs(float(last[2]) / m - 1) < 3e-13 and abs(float(last[3]) / e - 1) < 3e-13
+
+
+def test_restart_run_reproduces_the_continuous_run(tmp_path):
+    """dycore_restart (src/dycore_mod.F90:113-117, src/restart_mod.F90:39-56): a run restarted from the 6-hour restart
+    file reaches hour 12 with the fields of the uninterrupted run (to rounding: like the reference, a restart goes
+    through u, v, gd and iap_transform, not through the IAP variables) and with the same clock and file names."""
+    import os
+    import shutil
+    import subprocess
+    from scipy.io import netcdf_file
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "gamil_dycore_b200", "dycore_test")
+    base = """&dycore_params
+ num_lon = 120
+ num_lat = 61
+ case_name = 'rs'
+ test_case = 'rossby_haurwitz_wave'
+ run_hours = 12
+ time_step_size = 300
+ subcycles = 4
+ time_scheme = 'predict_correct'
+ split_scheme = 'csp2'
+ history_periods = '6 hours'
+ zonal_tend_filter_cutoff_wavenumber = 4, 4, 4
+%s/
+"""
+    a, b = tmp_path / "a", tmp_path / "b"
+    a.mkdir()
+    b.mkdir()
+    (a / "namelist").write_text(base % "")
+    res = subprocess.run([exe, "namelist"], capture_output=True, text=True, cwd=str(a), timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    assert sorted(os.listdir(a)) == ["namelist", "rs.h0.0001-01-01T06:00:00Z.nc", "rs.h0.0001-01-01T12:00:00Z.nc",
+                                     "rs.r.0001-01-01T06:00:00Z.nc", "rs.r.0001-01-01T12:00:00Z.nc"]
+    shutil.copy(a / "rs.r.0001-01-01T06:00:00Z.nc", b / "restart.nc")
+    (b / "namelist").write_text(base % " restart_file = 'restart.nc'\n")
+    res2 = subprocess.run([exe, "namelist"], capture_output=True, text=True, cwd=str(b), timeout=600)
+    assert res2.returncode == 0, res2.stdout[-2000:] + res2.stderr[-2000:]
+    lines = res2.stdout.splitlines()
+    assert " [Notice]: Reset time to 0001-01-01T06_00_00." in lines
+    steps = [l for l in lines if l.startswith(" => ")]
+    assert len(steps) == 73 and steps[0].startswith(" => 0001-01-01T06:00:00Z ") and steps[-1].startswith(" => 0001-01-01T12:00:00Z ")
+    fa = netcdf_file(str(a / "rs.r.0001-01-01T12:00:00Z.nc"), "r", mmap=False)
+    fb = netcdf_file(str(b / "rs.r.0001-01-01T12:00:00Z.nc"), "r", mmap=False)
+    for name in ("u", "v", "gd"):
+        assert rel(fb.variables[name][0], fa.variables[name][0]) < 1e-11, name
+    assert np.array_equal(fb.variables["ghs"][0], fa.variables["ghs"][0])
+    assert fb.restart_time == fa.restart_time
+    ha = netcdf_file(str(a / "rs.h0.0001-01-01T12:00:00Z.nc"), "r", mmap=False)
+    hb = netcdf_file(str(b / "rs.h0.0001-01-01T12:00:00Z.nc"), "r", mmap=False)
+    assert abs(hb.variables["tm"][0] / ha.variables["tm"][0] - 1) < 1e-13
+    assert abs(hb.variables["te"][0] / ha.variables["te"][0] - 1) < 1e-13
+    # the restarted clock starts at the restart time (time_reset_start_time, src/time_mod.F90:81-91)
+    assert hb.variables["time"].units == b"days since 0001-01-01T06_00_00" and hb.variables["time"][0] == 0.25

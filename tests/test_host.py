@@ -155,6 +155,31 @@ def test_unknown_test_case_message(tmp_path):
     assert rc == 2 and "Unknown test case nope!" in out   # src/dycore_test.F90:41
 
 
+# ------------------------------------------------------------------------------------------------ restart file
+def test_restart_file_schema_and_round_trip(tmp_path):
+    """restart_write / restart_read (src/restart_mod.F90:22-75): schema of the reference, interior data, bit-exact
+    round trip through the host's own classic-netCDF reader"""
+    from scipy.io import netcdf_file
+    nml = os.path.join(ROOT, "run", "namelist.mz_test")
+    rc, out = selftest("restart", nml, 120, cwd=str(tmp_path))
+    assert rc == 0, out
+    name, when, verdict = out.strip().splitlines()
+    assert name == "mz_c_u_01.180x90.dt720.r.0001-01-02T00:00:00Z.nc" and when == "0001-01-02T00:00:00Z" and verdict == "identical"
+    f = netcdf_file(str(tmp_path / name), "r", mmap=False)
+    assert list(f.dimensions.items()) == [("time", None), ("lon", 180), ("lat", 90), ("ilon", 180), ("ilat", 89)]
+    assert list(f.variables) == ["time", "lon", "lat", "ilon", "ilat", "u", "v", "gd", "ghs"]
+    assert list(f._attributes) == ["dataset", "desc", "author", "restart_time", "elapsed_seconds"]
+    assert f.dataset.decode().rstrip() == "restart" and f.desc.decode().rstrip() == "Restart file"
+    assert f.restart_time.decode().rstrip() == "0001-01-02T00:00:00Z" and f.elapsed_seconds == 86400.0
+    assert f.variables["u"].dimensions == ("time", "lat", "ilon") and f.variables["v"].dimensions == ("time", "ilat", "lon")
+    assert f.variables["gd"].long_name == b"geopotential depth" and f.variables["gd"].units == b"m2 s-2"
+    o = Oracle(OracleConfig(num_lon=180, num_lat=90, time_step_size=720.0))
+    o.set_initial_condition("mountain_zonal_flow")
+    u, v, gd = o.state()
+    assert np.allclose(f.variables["u"][0], u, rtol=0, atol=1e-12) and np.allclose(f.variables["gd"][0], gd, rtol=1e-15)
+    assert np.array_equal(f.variables["ghs"][0], o.ghs())
+
+
 # ------------------------------------------------------------------------------------------------ history file
 def test_history_file_schema(tmp_path):
     from scipy.io import netcdf_file
