@@ -108,6 +108,29 @@ module gmd_c
       integer(c_int), value :: layout
     end function
 
+    ! latitude bands over the GPUs of one node, one MPI rank per GPU (cfg%rank, cfg%nranks): every rank exports a
+    ! 256-byte blob (CUDA-IPC handles of its field slab and signal page), the blobs are gathered in rank order
+    ! (MPI_Allgather on character(256) buffers) and handed to gmd_peer_connect; halo rows and the two-scalar
+    ! all-reduces then travel over NVLink peer memory inside gmd_step
+    integer(c_int) function gmd_peer_export(model, blob) bind(c, name='gmd_peer_export')
+      import c_ptr, c_int, c_char
+      type(c_ptr), value :: model
+      character(kind=c_char), intent(out) :: blob(256)
+    end function
+
+    integer(c_int) function gmd_peer_connect(model, blobs, nblobs) bind(c, name='gmd_peer_connect')
+      import c_ptr, c_int, c_char
+      type(c_ptr), value :: model
+      character(kind=c_char), intent(in) :: blobs(*)
+      integer(c_int), value :: nblobs
+    end function
+
+    integer(c_int) function gmd_get_band(model, row_begin, row_end) bind(c, name='gmd_get_band')
+      import c_ptr, c_int
+      type(c_ptr), value :: model
+      integer(c_int), intent(out) :: row_begin, row_end
+    end function
+
   end interface
 
 contains

@@ -174,6 +174,8 @@ struct gmd_model {
   size_t peer_fld[2] = {0, 0};
   std::vector<void *> ipc_opened;
   unsigned xk = 0, rk = 0, xwaited = 0;  // halo epochs released / reductions done / halo epoch waited for, this unit
+  bool fuse_push = false;     // band-edge rows are stored to the neighbours by the boundary stage launch itself
+  bool stage_pushed = false;  // the last stage() call did so: the exchange that follows is already done
 
   // graphs
   bool graph_mode = true;
@@ -413,38 +415,50 @@ static int build_tables(gmd_model *m) {
 // launchers
 // ---------------------------------------------------------------------------------------------------------
 typedef void (*stage_fn)(const StageArgs);
-template <int MODE>
+// PUSH instantiations exist for the schemes a multi-rank run supports (not WENO) and the modes that produce rows
+template <int MODE, bool PUSH>
 static stage_fn pick_stage_mode(int pass, int adv) {
-  if (pass == PASS_FAST) return k_stage<PASS_FAST, ADV_CENTER, MODE>;
+  if (pass == PASS_FAST) return k_stage<PASS_FAST, ADV_CENTER, MODE, 0, PUSH>;
   if (pass == PASS_ALL) {
-    if (adv == ADV_CENTER) return k_stage<PASS_ALL, ADV_CENTER, MODE>;
-    if (adv == ADV_UPWIND) return k_stage<PASS_ALL, ADV_UPWIND, MODE>;
-    return k_stage<PASS_ALL, ADV_WENO, MODE>;
+    if (adv == ADV_CENTER) return k_stage<PASS_ALL, ADV_CENTER, MODE, 0, PUSH>;
+    if (adv == ADV_UPWIND) return k_stage<PASS_ALL, ADV_UPWIND, MODE, 0, PUSH>;
+    if constexpr (PUSH) return nullptr;
+    else return k_stage<PASS_ALL, ADV_WENO, MODE, 0, false>;
   }
-  if (adv == ADV_CENTER) return k_stage<PASS_SLOW, ADV_CENTER, MODE>;
-  if (adv == ADV_UPWIND) return k_stage<PASS_SLOW, ADV_UPWIND, MODE>;
-  return k_stage<PASS_SLOW, ADV_WENO, MODE>;
+  if (adv == ADV_CENTER) return k_stage<PASS_SLOW, ADV_CENTER, MODE, 0, PUSH>;
+  if (adv == ADV_UPWIND) return k_stage<PASS_SLOW, ADV_UPWIND, MODE, 0, PUSH>;
+  if constexpr (PUSH) return nullptr;
+  else return k_stage<PASS_SLOW, ADV_WENO, MODE, 0, false>;
 }
-static stage_fn pick_stage(int pass, int adv, int mode) {
+static stage_fn pick_stage(int pass, int adv, int mode, bool push = false) {
+  if (push) {
+    switch (mode) {
+      case MODE_S1: return pick_stage_mode<MODE_S1, true>(pass, adv);
+      case MODE_S2: return pick_stage_mode<MODE_S2, true>(pass, adv);
+      case MODE_S3A: return pick_stage_mode<MODE_S3A, true>(pass, adv);
+      default: return nullptr;
+    }
+  }
   switch (mode) {
-    case MODE_S1: return pick_stage_mode<MODE_S1>(pass, adv);
-    case MODE_S2: return pick_stage_mode<MODE_S2>(pass, adv);
-    case MODE_S3A: return pick_stage_mode<MODE_S3A>(pass, adv);
-    default: return pick_stage_mode<MODE_EVAL>(pass, adv);
+    case MODE_S1: return pick_stage_mode<MODE_S1, false>(pass, adv);
+    case MODE_S2: return pick_stage_mode<MODE_S2, false>(pass, adv);
+    case MODE_S3A: return pick_stage_mode<MODE_S3A, false>(pass, adv);
+    default: return pick_stage_mode<MODE_EVAL, false>(pass, adv);
   }
 }
 
 // MODE_S1 with the previous predict_correct's update folded in (k_stage LAZY = 1 / 2); never with WENO (its
 // advection terms come from separate sweeps over a stored state)
-static stage_fn pick_stage_lazy(int pass, int adv, int lazy) {
-  if (lazy == 1) {
-    if (pass == PASS_FAST) return k_stage<PASS_FAST, ADV_CENTER, MODE_S1, 1>;
-    if (pass == PASS_ALL) return adv == ADV_UPWIND ? k_stage<PASS_ALL, ADV_UPWIND, MODE_S1, 1> : k_stage<PASS_ALL, ADV_CENTER, MODE_S1, 1>;
-    return adv == ADV_UPWIND ? k_stage<PASS_SLOW, ADV_UPWIND, MODE_S1, 1> : k_stage<PASS_SLOW, ADV_CENTER, MODE_S1, 1>;
-  }
-  if (pass == PASS_FAST) return k_stage<PASS_FAST, ADV_CENTER, MODE_S1, 2>;
-  if (pass == PASS_ALL) return adv == ADV_UPWIND ? k_stage<PASS_ALL, ADV_UPWIND, MODE_S1, 2> : k_stage<PASS_ALL, ADV_CENTER, MODE_S1, 2>;
-  return adv == ADV_UPWIND ? k_stage<PASS_SLOW, ADV_UPWIND, MODE_S1, 2> : k_stage<PASS_SLOW, ADV_CENTER, MODE_S1, 2>;
+template <int LZ, bool PUSH>
+static stage_fn pick_stage_lazy_t(int pass, int adv) {
+  if (pass == PASS_FAST) return k_stage<PASS_FAST, ADV_CENTER, MODE_S1, LZ, PUSH>;
+  if (pass == PASS_ALL)
+    return adv == ADV_UPWIND ? k_stage<PASS_ALL, ADV_UPWIND, MODE_S1, LZ, PUSH> : k_stage<PASS_ALL, ADV_CENTER, MODE_S1, LZ, PUSH>;
+  return adv == ADV_UPWIND ? k_stage<PASS_SLOW, ADV_UPWIND, MODE_S1, LZ, PUSH> : k_stage<PASS_SLOW, ADV_CENTER, MODE_S1, LZ, PUSH>;
+}
+static stage_fn pick_stage_lazy(int pass, int adv, int lazy, bool push = false) {
+  if (lazy == 1) return push ? pick_stage_lazy_t<1, true>(pass, adv) : pick_stage_lazy_t<1, false>(pass, adv);
+  return push ? pick_stage_lazy_t<2, true>(pass, adv) : pick_stage_lazy_t<2, false>(pass, adv);
 }
 
 static int post_launch(gmd_model *m) {
@@ -485,6 +499,7 @@ static int halo_sides(const gmd_model *m) {
 // store halo rows of up to three fields into the neighbours' ghost rows and release halo epoch ++xk
 static int halo_push(gmd_model *m, double *const f[3], const int ns[3], const int nn[3]) {
   m->xk++;
+  m->launches++;
   if (m->dry) return 0;
   PushArgs a;
   memset(&a, 0, sizeof a);
@@ -505,7 +520,6 @@ static int halo_push(gmd_model *m, double *const f[3], const int ns[3], const in
   const int units = rows * (m->geo.nlon / 2);
   const int nb = std::max(1, std::min(64, (units + 255) / 256));
   k_halo_push<<<nb, 256, 0, m->stream>>>(a);
-  m->launches++;
   cudaError_t e = cudaPeekAtLastError();
   if (e != cudaSuccess) return fail(GMD_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
   return 0;
@@ -514,18 +528,16 @@ static int halo_push(gmd_model *m, double *const f[3], const int ns[3], const in
 static int halo_wait(gmd_model *m) {
   if (!m->p2p || m->xwaited == m->xk) return 0;
   m->xwaited = m->xk;
+  m->launches++;
   if (m->dry) return 0;
   k_halo_wait<<<1, 32, 0, m->stream>>>(m->page, m->xk, halo_sides(m));
-  m->launches++;
   return 0;
 }
 // close a unit of work (k_unit_end): all incoming halo rows have landed, epoch bases advance
 static int unit_end(gmd_model *m) {
   if (!m->p2p || (m->xk == 0 && m->rk == 0)) return 0;
-  if (!m->dry) {
-    k_unit_end<<<1, 32, 0, m->stream>>>(m->page, m->xk, m->rk, halo_sides(m));
-    m->launches++;
-  }
+  if (!m->dry) k_unit_end<<<1, 32, 0, m->stream>>>(m->page, m->xk, m->rk, halo_sides(m));
+  m->launches++;
   m->xk = m->rk = m->xwaited = 0;
   return 0;
 }
@@ -698,9 +710,10 @@ struct LazyIn {
 };
 
 static int stage(gmd_model *m, int pass, int mode, const State &E, const State *O, double dt, State *N, Tend *T,
-                 const Tend *P, const LazyIn *lz = nullptr) {
+                 const Tend *P, const LazyIn *lz = nullptr, bool want_push = false) {
   int r;
   const int adv = m->cfg.uv_adv_scheme;
+  m->stage_pushed = false;
   if (pass != PASS_FAST && adv == ADV_WENO && (r = weno_terms(m, E))) return r;
   StageArgs a;
   memset(&a, 0, sizeof a);
@@ -732,18 +745,34 @@ static int stage(gmd_model *m, int pass, int mode, const State &E, const State *
     // boundary rows first on the main stream (then polar rows / halo exchange), interior rows on stream2
     if ((r = split_begin(m))) return r;
     StageArgs b = a;
+    stage_fn fnb = fn;
     if (m->p2p) {  // the boundary CTAs wait for the neighbours' halo rows themselves
       b.hpage = m->page;
       b.hwait_k = m->xk;
       b.hside[0] = halo_sides(m) & 1;
       b.hside[1] = halo_sides(m) & 2;
       m->xwaited = m->xk;
+      stage_fn pf = nullptr;
+      if (want_push && m->fuse_push && mode != MODE_EVAL)
+        pf = lz ? pick_stage_lazy(pass, adv, lz->kind, true) : pick_stage(pass, adv, mode, true);
+      if (pf) {
+        // the rows the neighbours need: new state (S1, S2) or tendency (S3A)
+        double *fu = (mode == MODE_S3A) ? T->U : N->U, *fv = (mode == MODE_S3A) ? T->V : N->V;
+        double *fg = (pass == PASS_SLOW) ? nullptr : ((mode == MODE_S3A) ? T->gd : N->gd);
+        fnb = pf;
+        b.hsig_k = ++m->xk;
+        b.hpS_U = peer_ptr(m, 0, fu); b.hpS_V = peer_ptr(m, 0, fv); b.hpS_G = peer_ptr(m, 0, fg);
+        b.hpN_U = peer_ptr(m, 1, fu); b.hpN_V = peer_ptr(m, 1, fv); b.hpN_G = peer_ptr(m, 1, fg);
+        b.hsigS = (m->cfg.rank > 0) ? m->peer_page[m->cfg.rank - 1] + SP_SIG + 1 : nullptr;
+        b.hsigN = (m->cfg.rank + 1 < m->cfg.nranks) ? m->peer_page[m->cfg.rank + 1] + SP_SIG : nullptr;
+        m->stage_pushed = true;
+      }
     }
     b.rows_per_cta = m->rows_per_cta_b;
     b.rb[0] = r0; b.re[0] = r0 + m->bs; b.pofs[0] = 0;
     b.rb[1] = r1 - m->bn; b.re[1] = r1; b.pofs[1] = m->nbx * m->nchunks_b;
     dim3 gb((unsigned)m->nbx, (unsigned)m->nchunks_b, 2);
-    if (!m->dry) fn<<<gb, BX, m->stage_smem_b, m->stream>>>(b);
+    if (!m->dry) fnb<<<gb, BX, m->stage_smem_b, m->stream>>>(b);
     if ((r = post_launch(m))) return r;
     a.rows_per_cta = m->rows_per_cta;
     a.rb[0] = r0 + m->bs; a.re[0] = r1 - m->bn; a.pofs[0] = 2 * m->nbx * m->nchunks_b;
@@ -863,21 +892,21 @@ static int predict_correct(gmd_model *m, double dts, const Carry &in, int pass, 
   // tend(old) = L(old); new = old + dt/2 tend(old)
   if (in.deferred) {
     LazyIn lz = {&m->tendNew, in.dts, &M, in.with_gd ? 1 : 2};
-    if ((r = stage(m, pass, MODE_S1, in.base, nullptr, dt, &A, &m->tendOld, nullptr, &lz))) return r;
+    if ((r = stage(m, pass, MODE_S1, in.base, nullptr, dt, &A, &m->tendOld, nullptr, &lz, true))) return r;
   } else {
-    if ((r = stage(m, pass, MODE_S1, O, &O, dt, &A, &m->tendOld, nullptr))) return r;
+    if ((r = stage(m, pass, MODE_S1, O, &O, dt, &A, &m->tendOld, nullptr, nullptr, true))) return r;
   }
-  if ((r = exchange_state(m, A, !slow))) return r;
+  if (!m->stage_pushed && (r = exchange_state(m, A, !slow))) return r;
   // tend(old) = L(new); new = old + dt/2 tend(old)
-  if ((r = stage(m, pass, MODE_S2, A, &O, dt, &B, &m->tendOld, nullptr))) return r;
-  if ((r = exchange_state(m, B, !slow))) return r;
+  if ((r = stage(m, pass, MODE_S2, A, &O, dt, &B, &m->tendOld, nullptr, nullptr, true))) return r;
+  if (!m->stage_pushed && (r = exchange_state(m, B, !slow))) return r;
   // tend(new) = L(new); ip1 = <tend(old), tend(new)>, ip2 = <tend(new), tend(new)>
-  if ((r = stage(m, pass, MODE_S3A, B, nullptr, 0.0, nullptr, &m->tendNew, &m->tendOld))) return r;
+  if ((r = stage(m, pass, MODE_S3A, B, nullptr, 0.0, nullptr, &m->tendNew, &m->tendOld, nullptr, defer_out))) return r;
   release_state(m, &B);
   if (defer_out) {
     // new = old + dt beta tend(new) is left to the next call: it needs the ghost rows of tend(new)
     const State tv = {m->tendNew.U, m->tendNew.V, m->tendNew.gd};
-    if ((r = exchange_state(m, tv, !slow))) return r;
+    if (!m->stage_pushed && (r = exchange_state(m, tv, !slow))) return r;
     release_state(m, &A);
     out->base = O;
     if (!ownO) {  // the caller still owns in.base: take our own references
@@ -1567,6 +1596,18 @@ int gmd_peer_connect(gmd_model *m, const void *blobs, int nblobs) {
   }
   m->p2p = true;
   m->xk = m->rk = m->xwaited = 0;
+  {
+    // the boundary stage launch may push the band-edge rows itself if none of them is a filtered row (those get
+    // their final values from the polar-row kernel, which runs after it)
+    auto plain = [&](int j) {
+      return j >= 1 && j <= m->geo.nlat - 2 && !m->mesh.flag_full[(size_t)j] && !m->mesh.flag_half[(size_t)j];
+    };
+    bool ok = m->split;
+    if (rank > 0) ok = ok && plain(m->geo.r0) && plain(m->geo.r0 + 1);
+    if (rank + 1 < np) ok = ok && plain(m->geo.r1 - 1);
+    if (getenv("GMD_NO_FUSED_PUSH")) ok = false;
+    m->fuse_push = ok;
+  }
   for (auto &g : m->graphs) cudaGraphExecDestroy(g.exec);
   m->graphs.clear();
   return 0;

@@ -82,6 +82,13 @@ struct StageArgs {
   u64 *hpage;
   unsigned hwait_k;
   int hside[2];
+  // ... and, in the PUSH instantiations (boundary launches that produce the rows a neighbour needs), store the band-edge rows
+  // of the new state (S1, S2) or of the tendency (S3A) straight into the neighbours' ghost rows (pointers already
+  // shifted to this rank's row coordinates) and release halo epoch page[SP_XBASE] + hsig_k when the last CTA is done
+  // (PUSH instantiations only)
+  unsigned hsig_k;
+  double *hpS_U, *hpS_V, *hpS_G, *hpN_U, *hpN_V, *hpN_G;
+  u64 *hsigS, *hsigN;
   // deferred update (LAZY variants of MODE_S1): the evaluated state is E = (EU,EV,Egd) + beta ldt (LU,LV,Lgd), the
   // last update_state of the previous predict_correct (src/dycore_mod.F90:786-790) folded into this sweep; E is
   // also written out to (MU,MV,Mgd) on the rows of this CTA (and on the band's ghost rows by the edge CTAs)
@@ -349,9 +356,28 @@ constexpr int WOUT = 60;  // output columns per warp strip (64 held)
 constexpr int SW = 4;     // warps per CTA
 constexpr int BX = SW * 32;
 
+// end of a boundary launch that pushed halo rows: the last CTA to get here releases both neighbours
+__device__ __forceinline__ void stage_signal(const StageArgs &a) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    unsigned *ticket = reinterpret_cast<unsigned *>(a.hpage + SP_TICKET) + 1;  // slot 0 belongs to k_halo_push
+    const unsigned total = gridDim.x * gridDim.y * gridDim.z;
+    if (atomicAdd(ticket, 1u) == total - 1) {
+      *ticket = 0;
+      __threadfence_system();
+      const u64 ep = a.hpage[SP_XBASE] + a.hsig_k;
+      if (a.hsigS) st_release_sys(a.hsigS, ep);
+      if (a.hsigN) st_release_sys(a.hsigN, ep);
+    }
+  }
+}
+
 // LAZY: 0 = E is read as stored; 1 = E = base + beta ldt L (U, V and gd); 2 = the same for U, V only (the previous
 // predict_correct was a slow pass: gd unchanged)
-template <int PASS, int ADV, int MODE, int LAZY = 0>
+// PUSH: the boundary launches of a multi-rank run that produce rows a neighbour needs (a separate instantiation, so
+// that the row loop of the interior / single-GPU kernels keeps all of its registers)
+template <int PASS, int ADV, int MODE, int LAZY = 0, bool PUSH = false>
 __global__ void __launch_bounds__(BX, (LAZY ? GMD_LAZY_MINB : GMD_MINB)) k_stage(const StageArgs a) {
   __shared__ double red[2 * SW];
   extern __shared__ double srow[];  // row records of rows ja-1 .. jb: [(jb - ja + 2)][RC_N]
@@ -367,6 +393,7 @@ __global__ void __launch_bounds__(BX, (LAZY ? GMD_LAZY_MINB : GMD_MINB)) k_stage
       a.partials[2 * b] = 0.0;
       a.partials[2 * b + 1] = 0.0;
     }
+    if (PUSH) stage_signal(a);
     return;
   }
   const bool need_gh = (PASS != PASS_SLOW);
@@ -683,6 +710,30 @@ __global__ void __launch_bounds__(BX, (LAZY ? GMD_LAZY_MINB : GMD_MINB)) k_stage
           }
         }
       }
+      // ---- band-edge rows straight into the neighbours' ghost rows (south: U, V, gd of row r0 and gd of row r0+1;
+      //      north: U, V, gd of row r1-1); these rows are never filtered rows (checked by gmd_peer_connect)
+      if (PUSH && MODE != MODE_EVAL && out) {
+        const bool ps0 = (j == r0) && (a.hpS_U != nullptr), ps1 = (j == r0 + 1) && (a.hpS_U != nullptr);
+        const bool pn0 = (j == a.g.r1 - 1) && (a.hpN_U != nullptr);
+        if (ps0 || ps1 || pn0) {
+          const bool tend = (MODE == MODE_S3A);
+          const double xu0 = tend ? dUa : oU.x + a.dt * dUa, xu1 = tend ? dUb : oU.y + a.dt * dUb;
+          const double xv0 = tend ? dVa : oV.x + a.dt * dVa, xv1 = tend ? dVb : oV.y + a.dt * dVb;
+          const double xg0 = tend ? dGa : oG.x + a.dt * dGa, xg1 = tend ? dGb : oG.y + a.dt * dGb;
+          if (ps0) {
+            st2(AT(a.hpS_U, j), xu0, xu1);
+            st2(AT(a.hpS_V, j), xv0, xv1);
+          }
+          if (pn0) {
+            st2(AT(a.hpN_U, j), xu0, xu1);
+            st2(AT(a.hpN_V, j), xv0, xv1);
+          }
+          if (rowG) {
+            if (ps0 || ps1) st2(AT(a.hpS_G, j), xg0, xg1);
+            if (pn0) st2(AT(a.hpN_G, j), xg0, xg1);
+          }
+        }
+      }
       // ---- rotate the window ------------------------------------------------------------------------------
       sm_ = s0; s0 = sp; sp = sq;
       u0 = up;
@@ -722,6 +773,7 @@ __global__ void __launch_bounds__(BX, (LAZY ? GMD_LAZY_MINB : GMD_MINB)) k_stage
       a.partials[2 * b + 1] = q2;
     }
   }
+  if (PUSH) stage_signal(a);
 }
 
 // ---------------------------------------------------------------------------------------------------------
