@@ -1445,7 +1445,9 @@ int gmd_create(const gmd_config *cfg, gmd_model **out) {
     m->nchunks = (m->nr + m->rows_per_cta - 1) / m->rows_per_cta;
     m->nchunks_i = (rows_i + m->rows_per_cta - 1) / m->rows_per_cta;
     m->stage_smem = (size_t)(m->rows_per_cta + 2) * RC_N * sizeof(double);
-    m->rows_per_cta_b = 6;
+    // boundary chunks: long while the interior launch hides them, short once the boundary -> polar rows -> next
+    // boundary chain is what a phase waits for (measured at 900 and 225 rows per rank)
+    m->rows_per_cta_b = (m->nr >= 600) ? 6 : 3;
     if (const char *ev = getenv("GMD_ROWS_PER_CTA_B")) m->rows_per_cta_b = std::max(1, atoi(ev));
     m->nchunks_b = (std::max(m->bs, m->bn) + m->rows_per_cta_b - 1) / m->rows_per_cta_b;
     m->stage_smem_b = (size_t)(m->rows_per_cta_b + 2) * RC_N * sizeof(double);
