@@ -196,7 +196,7 @@ def main():
     d = gmd.Dycore(gmd.Config(rank=rank, nranks=world, device=local, **kw))
     if world > 1:
         from gamil_dycore_b200 import parallel
-        parallel.connect(d, mode=args.comm)
+        args.comm = parallel.connect(d, mode=args.comm)   # "peer" falls back to "nccl" if CUDA IPC is not available
     if args.no_graph:
         d.set_graph_mode(False)
     stream = torch.cuda.Stream()   # a real (non-legacy) stream: libgmd launches on it, torch events time it

@@ -125,6 +125,11 @@ module gmd_c
       integer(c_int), value :: nblobs
     end function
 
+    integer(c_int) function gmd_peer_disconnect(model) bind(c, name='gmd_peer_disconnect')
+      import c_ptr, c_int
+      type(c_ptr), value :: model
+    end function
+
     integer(c_int) function gmd_get_band(model, row_begin, row_end) bind(c, name='gmd_get_band')
       import c_ptr, c_int
       type(c_ptr), value :: model

@@ -118,6 +118,7 @@ def load(kind: str = "fast") -> C.CDLL:
     lib.gmd_comm_init.argtypes = [P, C.c_void_p]
     lib.gmd_peer_export.argtypes = [P, C.c_void_p]
     lib.gmd_peer_connect.argtypes = [P, C.c_void_p, C.c_int]
+    lib.gmd_peer_disconnect.argtypes = [P]
     lib.gmd_get_band.argtypes = [P, I, I]
     lib.gmd_set_state.argtypes = [P, D, D, D, D, C.c_int]
     lib.gmd_run_init.argtypes = [P]
@@ -218,6 +219,9 @@ class Dycore:
         two-scalar all-reduces to the peer-memory path, gmd_peer_connect"""
         raw = b"".join(blobs)
         self._chk(self.lib.gmd_peer_connect(self.h, C.create_string_buffer(raw, len(raw)), len(blobs)))
+
+    def peer_disconnect(self):
+        self._chk(self.lib.gmd_peer_disconnect(self.h))
 
     def band(self):
         a, b = C.c_int(), C.c_int()

@@ -1615,6 +1615,26 @@ int gmd_peer_connect(gmd_model *m, const void *blobs, int nblobs) {
   return 0;
 }
 
+int gmd_peer_disconnect(gmd_model *m) {
+  if (!m) return fail(GMD_ERR_ARG, "null model");
+  int r = set_dev(m);
+  if (r) return r;
+  if ((r = join(m))) return r;
+  CK(cudaStreamSynchronize(m->stream));
+  for (void *p : m->ipc_opened) cudaIpcCloseMemHandle(p);
+  m->ipc_opened.clear();
+  for (int p = 0; p < MAXR; p++) m->peer_page[p] = nullptr;
+  if (m->cfg.rank < MAXR) m->peer_page[m->cfg.rank] = m->page;
+  m->peer_slab[0] = m->peer_slab[1] = nullptr;
+  m->p2p = false;
+  m->fuse_push = false;
+  m->xk = m->rk = m->xwaited = 0;
+  CK(cudaMemset(m->page, 0, SP_WORDS * sizeof(u64)));
+  for (auto &g : m->graphs) cudaGraphExecDestroy(g.exec);
+  m->graphs.clear();
+  return 0;
+}
+
 int gmd_get_band(const gmd_model *m, int *b, int *e) {
   if (!m) return fail(GMD_ERR_ARG, "null model");
   if (b) *b = m->geo.r0;

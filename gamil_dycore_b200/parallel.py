@@ -24,10 +24,12 @@ def halo_rows(rank: int, nranks: int, num_lat: int):
     return south, north
 
 
-def connect(d, group=None, mode: str = "peer"):
+def connect(d, group=None, mode: str = "peer", fallback: bool = True):
     """wire the ranks of one node together.  mode "peer" (default): all-gather the CUDA-IPC blobs and call
     gmd_peer_connect (halo rows and all-reduces over NVLink peer memory, no NCCL on the step path);
-    mode "nccl": broadcast an NCCL unique id and call gmd_comm_init (ncclSend/Recv + ncclAllReduce)."""
+    mode "nccl": broadcast an NCCL unique id and call gmd_comm_init (ncclSend/Recv + ncclAllReduce).
+    If the peer mapping fails on any rank and `fallback` is set, every rank drops back to "nccl".  Returns the
+    mode in use."""
     import torch.distributed as dist
     from . import comm_unique_id
     rank, world = dist.get_rank(group), dist.get_world_size(group)
@@ -36,12 +38,24 @@ def connect(d, group=None, mode: str = "peer"):
     if mode == "peer":
         blobs = [None] * world
         dist.all_gather_object(blobs, d.peer_export(), group=group)
-        d.peer_connect(blobs)
-        dist.barrier(group=group)   # nobody stores into a neighbour before every rank has mapped it
+        err = None
+        try:
+            d.peer_connect(blobs)
+        except Exception as e:   # e.g. CUDA IPC not permitted between the ranks' processes
+            err = str(e)
+        errs = [None] * world
+        dist.all_gather_object(errs, err, group=group)   # doubles as the barrier: nobody stores into a neighbour
+        if any(errs):                                    # before every rank has mapped it
+            if not fallback:
+                raise RuntimeError(f"gmd_peer_connect failed: {[e for e in errs if e]}")
+            d.peer_disconnect()
+            return connect(d, group=group, mode="nccl")
+        return "peer"
     elif mode == "nccl":
         uid = [comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0, group=group)
         d.comm_init(uid[0])
+        return "nccl"
     else:
         raise ValueError(mode)
 

@@ -98,6 +98,9 @@ int gmd_comm_init(gmd_model *m, const void *id128);
 #define GMD_PEER_BLOB_BYTES 256
 int gmd_peer_export(gmd_model *m, void *blob);
 int gmd_peer_connect(gmd_model *m, const void *blobs, int nblobs);
+/* back to "not connected" (unmaps the neighbours): for a host program that wants to fall back to gmd_comm_init
+   when gmd_peer_connect failed on some rank.  Collective in the same sense as gmd_peer_connect. */
+int gmd_peer_disconnect(gmd_model *m);
 /* full-latitude rows [row_begin, row_end) (0-based) owned by this rank */
 int gmd_get_band(const gmd_model *m, int *row_begin, int *row_end);
 
