@@ -547,7 +547,6 @@ static RedArgs red_args(gmd_model *m) {
   r.nranks = 1;
   if (m->p2p) {
     r.page = m->page;
-    for (int p = 0; p < m->cfg.nranks; p++) r.peer[p] = m->peer_page[p];
     r.rank = m->cfg.rank;
     r.nranks = m->cfg.nranks;
     r.k = ++m->rk;
@@ -729,6 +728,12 @@ static int stage(gmd_model *m, int pass, int mode, const State &E, const State *
   a.beta_lon = m->cfg.uv_adv_upwind_lon_beta;
   a.beta_lat = m->cfg.uv_adv_upwind_lat_beta;
   a.partials = m->d_partials;
+  // the inner products are finalised (and all-reduced over peer memory) by the last CTA of the S3a launches; over
+  // NCCL the all-reduce is a library call, so the partials are reduced by a launch of their own
+  // (worth it once a band is short -- measured: 3.6 % at 225 rows per rank, nothing at 900 and above, where the
+  // extra ticket per CTA costs as much as the launch it saves)
+  static const int fold_env = getenv("GMD_FOLD") ? atoi(getenv("GMD_FOLD")) : -1;
+  const bool fold = (mode == MODE_S3A) && (m->cfg.nranks == 1 || m->p2p) && (fold_env >= 0 ? fold_env != 0 : m->nr < 600);
   stage_fn fn = pick_stage(pass, adv, mode);
   if (lz) {
     a.LU = lz->L->U; a.LV = lz->L->V; a.Lgd = lz->L->gd;
@@ -741,6 +746,15 @@ static int stage(gmd_model *m, int pass, int mode, const State &E, const State *
   }
   const int r0 = m->geo.r0, r1 = m->geo.r1;
   int nst;
+  const int li = (pass == PASS_SLOW) ? 1 : 0;
+  if (fold) {  // one partial pair and one ticket per CTA of the stage launch(es) and of the polar-row launch
+    const int ncta = use_split(m) ? 2 * m->nbx * m->nchunks_b + m->nbx * m->nchunks_i : m->nbx * m->nchunks;
+    a.fold.ticket = reinterpret_cast<unsigned *>(m->d_ip + 7);
+    a.fold.total = (unsigned)(ncta + m->n_items[li]);
+    a.fold.n = ncta + m->n_items[li];
+    a.fold.out = m->d_ip;
+    a.fold.r = red_args(m);
+  }
   if (use_split(m)) {
     // boundary rows first on the main stream (then polar rows / halo exchange), interior rows on stream2
     if ((r = split_begin(m))) return r;
@@ -792,9 +806,6 @@ static int stage(gmd_model *m, int pass, int mode, const State &E, const State *
     nst = m->nbx * m->nchunks;
   }
 
-  const int li = (pass == PASS_SLOW) ? 1 : 0;
-  // timing experiments only: launch the polar-row kernel twice (benign: it re-filters its own output)
-  static const bool double_polar = getenv("GMD_TIMING_DOUBLE_POLAR") != nullptr;
   if (m->n_items[li]) {
     PolarArgs p;
     memset(&p, 0, sizeof p);
@@ -811,11 +822,12 @@ static int stage(gmd_model *m, int pass, int mode, const State &E, const State *
     p.rescale = 1;
     p.radius = m->mesh.radius;
     p.dlat = m->mesh.dlat;
+    p.fold = a.fold;
+    p.fold_partials = m->d_partials;
     if (!m->dry) launch_polar(m, mode, m->n_items[li], p, m->stream);
-    if (!m->dry && double_polar) launch_polar(m, mode, m->n_items[li], p, m->stream);
     if ((r = post_launch(m))) return r;
   }
-  if (mode == MODE_S3A) {
+  if (mode == MODE_S3A && !fold) {
     if ((r = join(m))) return r;
     {
       const RedArgs ra = red_args(m);
@@ -1595,6 +1607,11 @@ int gmd_peer_connect(gmd_model *m, const void *blobs, int nblobs) {
       m->peer_r0[side] = B[(size_t)p].r0;
       m->peer_fld[side] = (size_t)B[(size_t)p].fld_elems;
     }
+  }
+  {
+    u64 tab[MAXR] = {};
+    for (int p = 0; p < np; p++) tab[p] = (u64)(uintptr_t)m->peer_page[p];
+    CK(cudaMemcpy(m->page + SP_PEERTAB, tab, sizeof tab, cudaMemcpyHostToDevice));
   }
   m->p2p = true;
   m->xk = m->rk = m->xwaited = 0;

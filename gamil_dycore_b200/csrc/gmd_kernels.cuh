@@ -62,6 +62,21 @@ struct Geo {
   int r0, r1;  // this rank owns full rows [r0, r1)
 };
 
+// arguments of the peer all-reduce of one partial pair (reduce_pairs_body below)
+struct RedArgs {
+  u64 *page;          // my signal page (page[SP_PEERTAB + p] = rank p's page as mapped here)
+  int rank, nranks;
+  unsigned k;         // reduction epoch = page[SP_RBASE] + k
+};
+// the inner-product finalisation folded into the launches that produce the partials (fold_tail below)
+struct Fold {
+  unsigned *ticket;   // null: the partials are reduced by a k_reduce_pairs launch instead
+  unsigned total;     // CTAs of all launches that contribute
+  int n;              // partial pairs
+  double *out;
+  RedArgs r;
+};
+
 struct StageArgs {
   Geo g;
   Tab t;
@@ -97,6 +112,7 @@ struct StageArgs {
   const double *lip;
   double ldt;
   int lqcon;
+  Fold fold;   // MODE_S3A
 };
 
 // beta of predict_correct (src/dycore_mod.F90:784-785) from the device-resident inner products
@@ -123,7 +139,8 @@ enum { SP_SIG = 0,                       // [2] halo epoch released by the south
        SP_ERR = 5,                       // local: set when a wait timed out (reported by gmd_sync)
        SP_RFLAG = 8,                     // [2][MAXR] reduction epoch released by every rank (parity double buffer)
        SP_RSLOT = 8 + 2 * MAXR,          // [2][MAXR][2] doubles: the two partial sums of every rank
-       SP_WORDS = 8 + 2 * MAXR + 4 * MAXR };
+       SP_PEERTAB = 8 + 2 * MAXR + 4 * MAXR,  // [MAXR] local: every rank's signal page as mapped here (pointers)
+       SP_WORDS = 8 + 2 * MAXR + 4 * MAXR + MAXR };
 
 __device__ __forceinline__ u64 ld_acquire_sys(const u64 *p) {
   u64 v;
@@ -162,6 +179,78 @@ __device__ __forceinline__ double block_sum(double v, double *red) {
     r = warp_sum(r);
   }
   return r;
+}
+
+// sum `n` pairs of partials in index order (deterministic) -> out[0], out[1]; with nranks > 1 the pair is then
+// all-reduced over peer memory by the same CTA: every rank stores its pair into every rank's signal page,
+// releases a flag, acquires the flags of all ranks and sums the pairs in rank order (same bits on every rank).
+template <int NT>
+__device__ __forceinline__ void reduce_pairs_body(const double *partials, int n, double *out, u64 *page, int rank,
+                                                  int nranks, unsigned k, double *red, double *gath) {
+  double a0 = 0.0, a1 = 0.0;
+  for (int q = threadIdx.x; q < n; q += NT) {
+    a0 += __ldcg(partials + 2 * q);
+    a1 += __ldcg(partials + 2 * q + 1);
+  }
+  const double r0 = block_sum<NT>(a0, red);
+  const double r1 = block_sum<NT>(a1, red);
+  if (nranks <= 1) {
+    if (threadIdx.x == 0) {
+      out[0] = r0;
+      out[1] = r1;
+    }
+    return;
+  }
+  if (threadIdx.x == 0) {
+    gath[2 * MAXR] = r0;
+    gath[2 * MAXR + 1] = r1;
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < nranks) {
+    const int p = threadIdx.x;
+    const u64 ep = page[SP_RBASE] + k;
+    const int par = (int)(ep & 1);
+    u64 *pp = reinterpret_cast<u64 *>(page[SP_PEERTAB + p]);
+    volatile double *slot = reinterpret_cast<volatile double *>(pp + SP_RSLOT) + (par * MAXR + rank) * 2;
+    slot[0] = gath[2 * MAXR];
+    slot[1] = gath[2 * MAXR + 1];
+    __threadfence_system();
+    st_release_sys(pp + SP_RFLAG + par * MAXR + rank, ep);
+    spin_until(page + SP_RFLAG + par * MAXR + p, ep, page);
+    const volatile double *mine = reinterpret_cast<const volatile double *>(page + SP_RSLOT) + (par * MAXR + p) * 2;
+    gath[2 * p] = mine[0];
+    gath[2 * p + 1] = mine[1];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s0 = 0.0, s1 = 0.0;
+    for (int p = 0; p < nranks; p++) {
+      s0 += gath[2 * p];
+      s1 += gath[2 * p + 1];
+    }
+    out[0] = s0;
+    out[1] = s1;
+  }
+}
+// The inner products of predict_correct folded into the launches that produce their partial sums: every CTA of the
+// S3a launches (boundary, interior, polar rows) takes a ticket after storing its partial pair; the last one sums all
+// pairs in index order (so the result does not depend on which CTA that is) and runs the peer all-reduce.  Not
+// inlined and fed by scalars only: the row loop of k_stage keeps its registers.
+template <int NT>
+__device__ __noinline__ void fold_tail(unsigned *ticket, unsigned total, const double *partials, int n, double *out,
+                                       u64 *page, int rank, int nranks, unsigned k) {
+  __shared__ double red[32];
+  __shared__ double gath[2 * MAXR + 2];
+  __shared__ int last;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    last = (atomicAdd(ticket, 1u) == total - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  reduce_pairs_body<NT>(partials, n, out, page, rank, nranks, k, red, gath);
+  if (threadIdx.x == 0) *ticket = 0;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -393,6 +482,9 @@ __global__ void __launch_bounds__(BX, (LAZY ? GMD_LAZY_MINB : GMD_MINB)) k_stage
       a.partials[2 * b] = 0.0;
       a.partials[2 * b + 1] = 0.0;
     }
+    if (MODE == MODE_S3A && a.fold.ticket)
+      fold_tail<BX>(a.fold.ticket, a.fold.total, a.partials, a.fold.n, a.fold.out, a.fold.r.page, a.fold.r.rank, a.fold.r.nranks,
+                    a.fold.r.k);
     if (PUSH) stage_signal(a);
     return;
   }
@@ -772,6 +864,9 @@ __global__ void __launch_bounds__(BX, (LAZY ? GMD_LAZY_MINB : GMD_MINB)) k_stage
       a.partials[2 * b] = q1;
       a.partials[2 * b + 1] = q2;
     }
+    if (a.fold.ticket)
+      fold_tail<BX>(a.fold.ticket, a.fold.total, a.partials, a.fold.n, a.fold.out, a.fold.r.page, a.fold.r.rank, a.fold.r.nranks,
+                    a.fold.r.k);
   }
   if (PUSH) stage_signal(a);
 }
@@ -815,6 +910,8 @@ struct PolarArgs {
   int rescale;            // 1: tendency filter with inner-product rescale; 0: plain filter (diffusion)
   int use_q;              // dynamic shared memory holds a third row (prefetched base-state / previous-tendency row)
   double radius, dlat;
+  Fold fold;              // MODE_S3A: see k_stage
+  const double *fold_partials;   // start of the whole partials array (this kernel's own pairs start at `partials`)
   unsigned items[MAX_ITEMS];
 };
 
@@ -1195,66 +1292,17 @@ __global__ void __launch_bounds__(PT) k_polar(const __grid_constant__ PolarArgs 
       a.partials[2 * blockIdx.x] = ip1;
       a.partials[2 * blockIdx.x + 1] = ip2;
     }
+    if (a.fold.ticket)
+      fold_tail<PT>(a.fold.ticket, a.fold.total, a.fold_partials, a.fold.n, a.fold.out, a.fold.r.page, a.fold.r.rank,
+                    a.fold.r.nranks, a.fold.r.k);
   }
 }
 
-// sum `n` pairs of partials in index order (deterministic) -> out[0], out[1]; with nranks > 1 the pair is then
-// all-reduced over peer memory in the same launch: every rank stores its pair into every rank's signal page,
-// releases a flag, acquires the flags of all ranks and sums the pairs in rank order (same bits on every rank).
-struct RedArgs {
-  u64 *page;          // my signal page
-  u64 *peer[MAXR];    // every rank's signal page (peer[rank] == page)
-  int rank, nranks;
-  unsigned k;         // reduction epoch = page[SP_RBASE] + k
-};
 __global__ void __launch_bounds__(256) k_reduce_pairs(const double *__restrict__ partials, int n, double *out,
                                                       const RedArgs r) {
   __shared__ double red[32];
   __shared__ double gath[2 * MAXR + 2];
-  double a0 = 0.0, a1 = 0.0;
-  for (int k = threadIdx.x; k < n; k += 256) {
-    a0 += partials[2 * k];
-    a1 += partials[2 * k + 1];
-  }
-  const double r0 = block_sum<256>(a0, red);
-  const double r1 = block_sum<256>(a1, red);
-  if (r.nranks <= 1) {
-    if (threadIdx.x == 0) {
-      out[0] = r0;
-      out[1] = r1;
-    }
-    return;
-  }
-  if (threadIdx.x == 0) {
-    gath[2 * MAXR] = r0;
-    gath[2 * MAXR + 1] = r1;
-  }
-  __syncthreads();
-  if ((int)threadIdx.x < r.nranks) {
-    const int p = threadIdx.x;
-    const u64 ep = r.page[SP_RBASE] + r.k;
-    const int par = (int)(ep & 1);
-    u64 *pp = r.peer[p];
-    volatile double *slot = reinterpret_cast<volatile double *>(pp + SP_RSLOT) + (par * MAXR + r.rank) * 2;
-    slot[0] = gath[2 * MAXR];
-    slot[1] = gath[2 * MAXR + 1];
-    __threadfence_system();
-    st_release_sys(pp + SP_RFLAG + par * MAXR + r.rank, ep);
-    spin_until(r.page + SP_RFLAG + par * MAXR + p, ep, r.page);
-    const volatile double *mine = reinterpret_cast<const volatile double *>(r.page + SP_RSLOT) + (par * MAXR + p) * 2;
-    gath[2 * p] = mine[0];
-    gath[2 * p + 1] = mine[1];
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double s0 = 0.0, s1 = 0.0;
-    for (int p = 0; p < r.nranks; p++) {
-      s0 += gath[2 * p];
-      s1 += gath[2 * p + 1];
-    }
-    out[0] = s0;
-    out[1] = s1;
-  }
+  reduce_pairs_body<256>(partials, n, out, r.page, r.rank, r.nranks, r.k, red, gath);
 }
 
 // Halo rows of up to three fields stored straight into the neighbours' ghost rows, then one release per
