@@ -167,6 +167,9 @@ def main():
     ap.add_argument("--workload", default="sg_0.1deg", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--polar-band-rows", type=int, default=-1,
+                    help="rows of the first and last latitude band for >= 3 GPUs (0: even bands; default: balanced "
+                         "against the polar-row work, gamil_dycore_b200.parallel.polar_band_rows_for)")
     ap.add_argument("--comm", default="peer", choices=["peer", "nccl"],
                     help="multi-GPU data path: NVLink peer memory (default) or NCCL send/recv + all-reduce")
     args = ap.parse_args()
@@ -193,9 +196,11 @@ def main():
     u, v, gd, ghs = initial_condition(test_case, kw)
     ncol = kw["num_lon"] * kw["num_lat"]
 
-    d = gmd.Dycore(gmd.Config(rank=rank, nranks=world, device=local, **kw))
+    from gamil_dycore_b200 import parallel
+    pbr = args.polar_band_rows if args.polar_band_rows >= 0 else parallel.polar_band_rows_for(
+        world, kw["num_lon"], kw["num_lat"], any(kw["zonal_tend_filter_cutoff_wavenumber"]))
+    d = gmd.Dycore(gmd.Config(rank=rank, nranks=world, device=local, polar_band_rows=pbr, **kw))
     if world > 1:
-        from gamil_dycore_b200 import parallel
         args.comm = parallel.connect(d, mode=args.comm)   # "peer" falls back to "nccl" if CUDA IPC is not available
     if args.no_graph:
         d.set_graph_mode(False)
@@ -286,7 +291,8 @@ def main():
                              "(the reference is serial), oracle built with gcc -O3 -ffast-math"}
         line = {"metric": "grid-point-updates/s", "value": value, "unit": "grid-point-updates/s", "n_gpus": world,
                 "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong",
-                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_dict(args.workload, kw, world, "NVLink peer memory" if args.comm == "peer" else "NCCL"),
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": dict(config_dict(args.workload, kw, world, "NVLink peer memory" if args.comm == "peer" else "NCCL"),
+                               polar_band_rows=pbr),
                 "sim_days_per_day": kw["time_step_size"] * K / (ms * 1e-3), "clocks": sampler.summary(), "e2e": e2e,
                 "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
                 "conservation": {"mass_rel_drift": abs(m1 / m0 - 1), "energy_rel_drift": abs(e1 / e0 - 1), "beta": beta}}

@@ -34,6 +34,7 @@ module gmd_c
     integer(c_int) rank
     integer(c_int) nranks
     integer(c_int) device
+    integer(c_int) polar_band_rows
   end type gmd_config
 
   interface

@@ -33,6 +33,7 @@ class _Cfg(C.Structure):
         ("uv_adv_upwind_lat_beta", C.c_double), ("use_zonal_tend_filter", C.c_int),
         ("cutoff", C.c_int * 20), ("use_diffusion", C.c_int), ("diffusion_order", C.c_int),
         ("diffusion_coef", C.c_double), ("rank", C.c_int), ("nranks", C.c_int), ("device", C.c_int),
+        ("polar_band_rows", C.c_int),
     ]
 
 
@@ -56,6 +57,7 @@ class Config:
     rank: int = 0
     nranks: int = 1
     device: int = -1
+    polar_band_rows: int = 0
 
     def to_c(self) -> _Cfg:
         c = _Cfg()
@@ -74,6 +76,7 @@ class Config:
         c.diffusion_order = self.diffusion_order
         c.diffusion_coef = self.diffusion_coef
         c.rank, c.nranks, c.device = self.rank, self.nranks, self.device
+        c.polar_band_rows = self.polar_band_rows
         return c
 
 

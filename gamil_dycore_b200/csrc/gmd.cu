@@ -209,6 +209,23 @@ static int set_dev(gmd_model *m) {
   return 0;
 }
 
+// rows [r0, r1) of band `rank` (mirrored by gamil_dycore_b200/parallel.py: band)
+static void band_rows(int nlat, int nranks, int polar_rows, int rank, int *r0, int *r1) {
+  if (nranks >= 3 && polar_rows > 0 && 2 * polar_rows < nlat) {
+    const int mid = nlat - 2 * polar_rows, nm = nranks - 2;
+    const int base = mid / nm, rem = mid % nm;
+    if (rank == 0) { *r0 = 0; *r1 = polar_rows; return; }
+    if (rank == nranks - 1) { *r0 = nlat - polar_rows; *r1 = nlat; return; }
+    const int q = rank - 1;
+    *r0 = polar_rows + q * base + std::min(q, rem);
+    *r1 = *r0 + base + (q < rem ? 1 : 0);
+    return;
+  }
+  const int base = nlat / nranks, rem = nlat % nranks;
+  *r0 = rank * base + std::min(rank, rem);
+  *r1 = *r0 + base + (rank < rem ? 1 : 0);
+}
+
 // ---- buffer pool --------------------------------------------------------------------------------------
 static int acquire(gmd_model *m, int kind, double **out) {
   if (!m->free_[kind].empty()) {
@@ -1373,6 +1390,8 @@ int gmd_create(const gmd_config *cfg, gmd_model **out) {
     }
   }
   if (cfg->num_lat / cfg->nranks < 4) return fail(GMD_ERR_ARG, "fewer than 4 latitude rows per rank");
+  if (cfg->polar_band_rows < 0 || (cfg->polar_band_rows > 0 && cfg->polar_band_rows < 4))
+    return fail(GMD_ERR_ARG, "polar_band_rows must be 0 or >= 4");
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0)
@@ -1400,12 +1419,10 @@ int gmd_create(const gmd_config *cfg, gmd_model **out) {
   const int nlon = cfg->num_lon, nlat = cfg->num_lat;
   m->mesh.init(nlon, nlat, /*reset_poles=*/true);
   m->mesh.filter_init(cfg->use_zonal_tend_filter != 0, cfg->zonal_tend_filter_cutoff_wavenumber);
-  // latitude bands: rows split as evenly as possible
-  const int base = nlat / cfg->nranks, rem = nlat % cfg->nranks;
+  // latitude bands: rows split as evenly as possible, or (polar_band_rows) shorter first and last bands
   m->geo.nlon = nlon;
   m->geo.nlat = nlat;
-  m->geo.r0 = cfg->rank * base + std::min(cfg->rank, rem);
-  m->geo.r1 = m->geo.r0 + base + (cfg->rank < rem ? 1 : 0);
+  band_rows(nlat, cfg->nranks, cfg->polar_band_rows, cfg->rank, &m->geo.r0, &m->geo.r1);
   m->nr = m->geo.r1 - m->geo.r0;
   m->fld_elems = (size_t)(m->nr + 2 * GHOST) * nlon;
   {

@@ -67,6 +67,9 @@ typedef struct gmd_config {
   int rank;                        /* 0 .. nranks-1 */
   int nranks;                      /* latitude bands; 1 = whole globe */
   int device;                      /* CUDA device ordinal, -1 = current device */
+  int polar_band_rows;             /* nranks >= 3: rows of the first and the last band (they also carry the polar
+                                      filter rows and pole caps, whose cost does not shrink with the band), the
+                                      other ranks share the rest evenly; 0 = all bands even (default) */
 } gmd_config;
 
 typedef struct gmd_model gmd_model;

@@ -51,7 +51,10 @@ def main():
         o.run_init()
         m0 = o.diag()
         o.step(nsteps)
-        d = gmd.Dycore(gmd.Config(rank=rank, nranks=world, device=local, **kw))
+        # >= 3 ranks: shorter first and last bands (gmd_config.polar_band_rows), as bench.py uses them
+        pbr = max(kw["num_lat"] // world - 3, 8) if world >= 3 else 0
+        d = gmd.Dycore(gmd.Config(rank=rank, nranks=world, device=local, polar_band_rows=pbr, **kw))
+        assert d.band() == parallel.band(rank, world, kw["num_lat"], pbr)
         parallel.connect(d, mode=mode)
         d.set_state(u, v, gd, ghs)
         d.run_init()

@@ -225,6 +225,16 @@ def test_band_arithmetic():
         sizes = [b - a for a, b in rows]
         assert max(sizes) - min(sizes) <= 1
     assert parallel.halo_rows(0, 2, 181) == ([], [91, 92]) and parallel.halo_rows(1, 2, 181) == ([90], [])
+    # shorter polar bands (gmd_config.polar_band_rows): contiguous cover, the middle ranks even
+    for nlat, n, pbr in ((1801, 8, 113), (1801, 4, 350), (3601, 8, 300), (181, 3, 40)):
+        rows = [parallel.band(r, n, nlat, pbr) for r in range(n)]
+        assert rows[0] == (0, pbr) and rows[-1] == (nlat - pbr, nlat)
+        assert all(a[1] == b[0] for a, b in zip(rows, rows[1:]))
+        mid = [b - a for a, b in rows[1:-1]]
+        assert max(mid) - min(mid) <= 1 and sum(mid) == nlat - 2 * pbr
+    assert parallel.band(1, 2, 181, 40) == parallel.band(1, 2, 181)      # ignored below 3 ranks
+    assert parallel.polar_band_rows_for(2, 3600, 1801) == 0
+    assert parallel.polar_band_rows_for(4, 3600, 1801) == 400 and 112 <= parallel.polar_band_rows_for(8, 3600, 1801) < 225
 
 
 def _gloo_worker(rank, world, port, nlat, nlon, q):
