@@ -1596,6 +1596,11 @@ int gmd_peer_connect(gmd_model *m, const void *blobs, int nblobs) {
   if (nblobs != np) return fail(GMD_ERR_ARG, "%d blobs for %d ranks", nblobs, np);
   if (np > MAXR) return fail(GMD_ERR_ARG, "the peer-memory path serves up to %d ranks (one node); use gmd_comm_init", MAXR);
   if (m->p2p) return fail(GMD_ERR_STATE, "gmd_peer_connect called twice");
+  // A boundary CTA reads the neighbour-written ghost rows through the read-only path after acquiring the epoch, while
+  // interior CTAs of the same phase may already have read the last owned row: the two must never share a 32-byte L1
+  // sector, i.e. a row must be a whole number of sectors.
+  if (m->geo.nlon % 4)
+    return fail(GMD_ERR_ARG, "the peer-memory path needs num_lon to be a multiple of 4 (got %d); use gmd_comm_init", m->geo.nlon);
   int r = set_dev(m);
   if (r) return r;
   if ((r = join(m))) return r;
