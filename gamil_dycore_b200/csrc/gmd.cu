@@ -491,12 +491,12 @@ static int exchange_field(gmd_model *m, double *f, int ns, int nn) {
   const int nlon = m->geo.nlon, nr = m->nr;
   const int rank = m->cfg.rank, np = m->cfg.nranks;
   if (rank + 1 < np) {
-    NK(g_nccl.Send(f + (size_t)(nr - ns) * nlon, (size_t)ns * nlon, NCCL_F64, rank + 1, m->comm, m->stream));
-    NK(g_nccl.Recv(f + (size_t)nr * nlon, (size_t)nn * nlon, NCCL_F64, rank + 1, m->comm, m->stream));
+    if (ns) NK(g_nccl.Send(f + (size_t)(nr - ns) * nlon, (size_t)ns * nlon, NCCL_F64, rank + 1, m->comm, m->stream));
+    if (nn) NK(g_nccl.Recv(f + (size_t)nr * nlon, (size_t)nn * nlon, NCCL_F64, rank + 1, m->comm, m->stream));
   }
   if (rank > 0) {
-    NK(g_nccl.Send(f, (size_t)nn * nlon, NCCL_F64, rank - 1, m->comm, m->stream));
-    NK(g_nccl.Recv(f - (ptrdiff_t)ns * nlon, (size_t)ns * nlon, NCCL_F64, rank - 1, m->comm, m->stream));
+    if (nn) NK(g_nccl.Send(f, (size_t)nn * nlon, NCCL_F64, rank - 1, m->comm, m->stream));
+    if (ns) NK(g_nccl.Recv(f - (ptrdiff_t)ns * nlon, (size_t)ns * nlon, NCCL_F64, rank - 1, m->comm, m->stream));
   }
   return 0;
 }
@@ -673,7 +673,6 @@ static int derive_uv(gmd_model *m, const State &s) {
 // WENO advection terms of state E into w_alon_u .. (src/weno_mod.F90:69-233)
 static int weno_terms(gmd_model *m, const State &E) {
   int r;
-  if (m->cfg.nranks > 1) return fail(GMD_ERR_ARG, "uv_adv_scheme='weno' is single-GPU only in this build");
   if ((r = ensure_weno(m))) return r;
   if ((r = derive_uv(m, E))) return r;
   WenoArgs a;
@@ -687,8 +686,20 @@ static int weno_terms(gmd_model *m, const State &E) {
     a.dir = dir;
     if (!m->dry) k_weno_split<<<m->ew_blocks, 256, 0, m->stream>>>(a);
     if ((r = post_launch(m))) return r;
+    if (dir == 1) {
+      // the meridional reconstruction reads the split fluxes on rows j-1 .. j+2 (src/weno_mod.F90:186-217): one row
+      // from the south, two from the north
+      if ((r = exchange_tend3(m, a.fpu, a.fnu, a.fpv, 1, 2))) return r;
+      if ((r = exchange_tend3(m, a.fnv, nullptr, nullptr, 1, 2))) return r;
+      if ((r = halo_wait(m))) return r;
+    }
     if (!m->dry) k_weno_flux<<<m->ew_blocks, 256, 0, m->stream>>>(a);
     if ((r = post_launch(m))) return r;
+    if (dir == 1) {
+      // the flux difference reads the reconstructed flux of row j-1 (:219-233)
+      if ((r = exchange_tend3(m, a.fu, a.fv, nullptr, 1, 0))) return r;
+      if ((r = halo_wait(m))) return r;
+    }
     if (!m->dry) k_weno_adv<<<m->ew_blocks, 256, 0, m->stream>>>(a);
     if ((r = post_launch(m))) return r;
   }

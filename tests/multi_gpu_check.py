@@ -40,6 +40,8 @@ def main():
         ("mountain_zonal_flow", dict(num_lon=96, num_lat=50, time_step_size=600.0, split_scheme="none",
                                      use_diffusion=True, diffusion_order=4, diffusion_coef=1.0e14,
                                      zonal_tend_filter_cutoff_wavenumber=[4, 4]), 3),
+        ("mountain_zonal_flow", dict(num_lon=96, num_lat=49, time_step_size=600.0, subcycles=4, split_scheme="csp2",
+                                     uv_adv_scheme="weno", zonal_tend_filter_cutoff_wavenumber=[4, 4]), 3),
     ]
     ok = True
     mode = sys.argv[1] if len(sys.argv) > 1 else "peer"   # "peer" (NVLink peer memory) or "nccl"
@@ -78,7 +80,7 @@ def main():
                 errs[0] < 1e-10 and errs[2] < 1e-11 and (errs[1] < 1e-9))
         ok = ok and good
         if rank == 0:
-            print(f"[{world} ranks, {mode}] {tc} {kw['num_lon']}x{nlat} {kw['split_scheme']}: rel-L2 u,v,gd = {errs}, "
+            print(f"[{world} ranks, {mode}] {tc} {kw['num_lon']}x{nlat} {kw['split_scheme']} {kw.get('uv_adv_scheme', 'center_diff')}: rel-L2 u,v,gd = {errs}, "
                   f"mass {abs(m / mo - 1):.1e} energy {abs(e / eo - 1):.1e} beta {abs(beta - bo):.1e} -> {'ok' if good else 'FAIL'}",
                   flush=True)
         d.close()
