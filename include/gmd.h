@@ -97,7 +97,10 @@ int gmd_comm_init(gmd_model *m, const void *id128);
    all ranks in rank order (MPI_Allgather / torch.distributed) and every rank calls gmd_peer_connect.  From then
    on halo rows are stored straight into the neighbour's ghost rows by this rank's kernels, the neighbour's next
    boundary launch spins on a release/acquire flag, and the two-scalar all-reduces are one-shot peer exchanges --
-   NCCL is no longer on the step path (gmd_comm_init becomes optional).  No reference counterpart. */
+   NCCL is no longer on the step path (gmd_comm_init becomes optional).  No reference counterpart.
+   All ranks must issue the same sequence of gmd_* calls after connecting (the slot index of a buffer is what
+   identifies "the same buffer" on a neighbour, and gmd_step / gmd_predict_correct / gmd_ordinary_diffusion wait for
+   the neighbours inside their kernels). */
 #define GMD_PEER_BLOB_BYTES 256
 int gmd_peer_export(gmd_model *m, void *blob);
 int gmd_peer_connect(gmd_model *m, const void *blobs, int nblobs);
