@@ -264,3 +264,65 @@ def test_gather_bands_over_gloo_world_size_2():
     for p in procs:
         p.join(timeout=60)
     assert res == [(0, True), (1, True)]
+
+
+class _FakeDycore:
+    """stands in for gamil_dycore_b200.Dycore in the wiring test below: records the calls parallel.connect makes"""
+
+    def __init__(self, rank, fail_connect):
+        self.rank, self.fail_connect, self.calls = rank, fail_connect, []
+
+    def peer_export(self):
+        self.calls.append("export")
+        return bytes([self.rank]) * 256
+
+    def peer_connect(self, blobs):
+        self.calls.append(("connect", [b[0] for b in blobs]))
+        if self.fail_connect:
+            raise RuntimeError("cudaIpcOpenMemHandle failed (simulated)")
+
+    def peer_disconnect(self):
+        self.calls.append("disconnect")
+
+    def comm_init(self, uid):
+        self.calls.append(("comm_init", len(uid)))
+
+
+def _connect_worker(rank, world, port, fail_rank, q):
+    import torch.distributed as dist
+    import gamil_dycore_b200 as pkg
+    from gamil_dycore_b200 import parallel
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    pkg.comm_unique_id = lambda kind="fast": b"\x07" * 128     # no NCCL on the CPU box
+    d = _FakeDycore(rank, fail_connect=(rank == fail_rank))
+    mode = parallel.connect(d)
+    strict = None
+    if fail_rank >= 0:
+        try:
+            parallel.connect(_FakeDycore(rank, fail_connect=(rank == fail_rank)), fallback=False)
+        except RuntimeError as e:
+            strict = "gmd_peer_connect failed" in str(e)
+    q.put((rank, mode, d.calls, strict))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("fail_rank", [-1, 1])
+def test_connect_wiring_and_nccl_fallback_over_gloo_world_size_2(fail_rank):
+    """parallel.connect: blobs gathered in rank order; if the peer mapping fails on ANY rank, EVERY rank disconnects and
+    falls back to the NCCL bootstrap (or raises with fallback=False)"""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_connect_worker, args=(r, 2, 29579 + fail_rank, fail_rank, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    for rank, mode, calls, strict in res:
+        assert calls[0] == "export" and calls[1] == ("connect", [0, 1])
+        if fail_rank < 0:
+            assert mode == "peer" and len(calls) == 2
+        else:
+            assert mode == "nccl" and calls[2] == "disconnect" and calls[3] == ("comm_init", 128) and strict is True
