@@ -86,7 +86,7 @@ class GmdError(RuntimeError):
         self.code = code
 
 
-LIB_NAMES = {"fast": "libgmd.so", "strict": "libgmd_strict.so"}
+LIB_NAMES = {"fast": "libgmd.so", "strict": "libgmd_strict.so", "trace": "libgmd_trace.so"}
 
 
 def build(force: bool = False) -> None:
@@ -149,11 +149,42 @@ def load(kind: str = "fast") -> C.CDLL:
     lib.gmd_algorithmic_bytes_per_column_step.restype = C.c_double
     lib.gmd_time_stage_kernel.argtypes = [P, C.c_int, C.POINTER(C.c_float), D]
     lib.gmd_time_stage_variant.argtypes = [P, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), D]
+    lib.gmd_trace_begin.argtypes = [P]
+    lib.gmd_trace_dump.argtypes = [P, C.c_char_p]
     _LIBS[kind] = lib
     return lib
 
 
 PEER_BLOB_BYTES = 256   # GMD_PEER_BLOB_BYTES, include/gmd.h
+
+_HOST = None
+
+
+def load_host() -> C.CDLL:
+    """libgmd_host.so: the host side of the drop-in behind a C ABI (include/gmd_host.h) -- the IC plugins."""
+    global _HOST
+    if _HOST is None:
+        path = os.path.join(_HERE, "libgmd_host.so")
+        if not os.path.exists(path):
+            raise FileNotFoundError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
+        lib = C.CDLL(path)
+        D = C.POINTER(C.c_double)
+        lib.gmd_host_initial_condition.argtypes = [C.c_char_p, C.c_int, C.c_int, D, D, D, D]
+        lib.gmd_host_last_error.restype = C.c_char_p
+        _HOST = lib
+    return _HOST
+
+
+def initial_condition(test_case: str, num_lon: int, num_lat: int):
+    """(u, v, gd, ghs) of the named test-case plugin (src/test_cases/barotropic/*_test_mod.F90 as rebuilt in
+    gamil_dycore_b200/host/test_cases.cpp), compact layout"""
+    lib = load_host()
+    u, v = np.zeros((num_lat, num_lon)), np.zeros((num_lat - 1, num_lon))
+    gd, ghs = np.zeros((num_lat, num_lon)), np.zeros((num_lat, num_lon))
+    ier = lib.gmd_host_initial_condition(test_case.encode(), num_lon, num_lat, _dp(u), _dp(v), _dp(gd), _dp(ghs))
+    if ier:
+        raise GmdError(ier, lib.gmd_host_last_error().decode())
+    return u, v, gd, ghs
 
 
 def _dp(a: Optional[np.ndarray]):
@@ -332,6 +363,18 @@ class Dycore:
         ms, nb = C.c_float(), C.c_double()
         self._chk(self.lib.gmd_time_stage_variant(self.h, PASS[pass_], mode, reps, C.byref(ms), C.byref(nb)))
         return ms.value, nb.value
+
+    def trace_begin(self):
+        """start recording the device timeline of the following steps (kind="trace" build only)"""
+        self._chk(self.lib.gmd_trace_begin(self.h))
+
+    def trace_end(self):
+        """the recorded timeline: {"steps": [{"step", "launches": [{"seq", "kernel", "start_ns", "end_ns", "wait_ns"}]}]}"""
+        import json
+        import tempfile
+        with tempfile.NamedTemporaryFile(suffix=".json") as f:
+            self._chk(self.lib.gmd_trace_dump(self.h, f.name.encode()))
+            return json.load(open(f.name))
 
     def time_stage_kernel(self, reps: int = 20):
         ms, nb = C.c_float(), C.c_double()

@@ -202,7 +202,30 @@ struct gmd_model {
   float last_ms = 0.f;
   bool span_open = false;
   int pending_steps = 0;
+
+  // device timeline (GMD_TRACE builds, gmd_trace_begin / gmd_trace_dump)
+  bool in_step = false;
+  long long step_launch0 = 0;
+  u64 *d_trace = nullptr;
+  std::vector<std::string> trace_names;
+  int trace_step0 = 0;
+  static const int TRACE_STEPS = 4, TRACE_PER_STEP = 768;
 };
+
+// timeline slot of the launch that is about to be issued: its position inside the model step (GMD_TRACE builds)
+static inline int tseq(gmd_model *m, const char *name) {
+#if GMD_TRACE
+  if (!m->in_step) return 0;
+  const long long q = m->launches - m->step_launch0;
+  if (q < 0 || q >= gmd_model::TRACE_PER_STEP) return 0;
+  if ((long long)m->trace_names.size() <= q) m->trace_names.resize((size_t)q + 1);
+  m->trace_names[(size_t)q] = name;
+  return (int)q + 1;   // 0 = no slot
+#else
+  (void)m; (void)name;
+  return 0;
+#endif
+}
 
 static int set_dev(gmd_model *m) {
   CK(cudaSetDevice(m->dev));
@@ -515,11 +538,13 @@ static int halo_sides(const gmd_model *m) {
 }
 // store halo rows of up to three fields into the neighbours' ghost rows and release halo epoch ++xk
 static int halo_push(gmd_model *m, double *const f[3], const int ns[3], const int nn[3]) {
+  const int ts = tseq(m, "k_halo_push");
   m->xk++;
   m->launches++;
   if (m->dry) return 0;
   PushArgs a;
   memset(&a, 0, sizeof a);
+  a.tseq = ts;
   a.g = m->geo;
   int rows = 0;
   for (int k = 0; k < 3; k++) {
@@ -545,15 +570,17 @@ static int halo_push(gmd_model *m, double *const f[3], const int ns[3], const in
 static int halo_wait(gmd_model *m) {
   if (!m->p2p || m->xwaited == m->xk) return 0;
   m->xwaited = m->xk;
+  const int ts = tseq(m, "k_halo_wait");
   m->launches++;
   if (m->dry) return 0;
-  k_halo_wait<<<1, 32, 0, m->stream>>>(m->page, m->xk, halo_sides(m));
+  k_halo_wait<<<1, 32, 0, m->stream>>>(m->page, m->xk, halo_sides(m), ts);
   return 0;
 }
 // close a unit of work (k_unit_end): all incoming halo rows have landed, epoch bases advance
 static int unit_end(gmd_model *m) {
   if (!m->p2p || (m->xk == 0 && m->rk == 0)) return 0;
-  if (!m->dry) k_unit_end<<<1, 32, 0, m->stream>>>(m->page, m->xk, m->rk, halo_sides(m));
+  const int ts = tseq(m, "k_unit_end");
+  if (!m->dry) k_unit_end<<<1, 32, 0, m->stream>>>(m->page, m->xk, m->rk, halo_sides(m), ts);
   m->launches++;
   m->xk = m->rk = m->xwaited = 0;
   return 0;
@@ -814,11 +841,15 @@ static int stage(gmd_model *m, int pass, int mode, const State &E, const State *
     b.rb[0] = r0; b.re[0] = r0 + m->bs; b.pofs[0] = 0;
     b.rb[1] = r1 - m->bn; b.re[1] = r1; b.pofs[1] = m->nbx * m->nchunks_b;
     dim3 gb((unsigned)m->nbx, (unsigned)m->nchunks_b, 2);
+    static const char *const bnames[4] = {"k_stage.S1.boundary", "k_stage.S2.boundary", "k_stage.S3a.boundary", "k_stage.eval.boundary"};
+    b.tseq = tseq(m, bnames[mode]);
     if (!m->dry) fnb<<<gb, BX, m->stage_smem_b, m->stream>>>(b);
     if ((r = post_launch(m))) return r;
     a.rows_per_cta = m->rows_per_cta;
     a.rb[0] = r0 + m->bs; a.re[0] = r1 - m->bn; a.pofs[0] = 2 * m->nbx * m->nchunks_b;
     dim3 gi((unsigned)m->nbx, (unsigned)m->nchunks_i, 1);
+    static const char *const inames[4] = {"k_stage.S1.interior", "k_stage.S2.interior", "k_stage.S3a.interior", "k_stage.eval.interior"};
+    a.tseq = tseq(m, inames[mode]);
     if (!m->dry) fn<<<gi, BX, m->stage_smem, m->stream2>>>(a);
     if ((r = post_launch(m))) return r;
     if ((r = split_end(m))) return r;
@@ -829,6 +860,8 @@ static int stage(gmd_model *m, int pass, int mode, const State &E, const State *
     a.rows_per_cta = m->rows_per_cta;
     a.rb[0] = r0; a.re[0] = r1; a.pofs[0] = 0;
     dim3 grid((unsigned)m->nbx, (unsigned)m->nchunks, 1);
+    static const char *const wnames[4] = {"k_stage.S1", "k_stage.S2", "k_stage.S3a", "k_stage.eval"};
+    a.tseq = tseq(m, wnames[mode]);
     if (!m->dry) fn<<<grid, BX, m->stage_smem, m->stream>>>(a);
     if ((r = post_launch(m))) return r;
     nst = m->nbx * m->nchunks;
@@ -852,13 +885,15 @@ static int stage(gmd_model *m, int pass, int mode, const State &E, const State *
     p.dlat = m->mesh.dlat;
     p.fold = a.fold;
     p.fold_partials = m->d_partials;
+    p.tseq = tseq(m, "k_polar");
     if (!m->dry) launch_polar(m, mode, m->n_items[li], p, m->stream);
     if ((r = post_launch(m))) return r;
   }
   if (mode == MODE_S3A && !fold) {
     if ((r = join(m))) return r;
     {
-      const RedArgs ra = red_args(m);
+      RedArgs ra = red_args(m);
+      ra.tseq = tseq(m, "k_reduce_pairs.ip");
       if (!m->dry) k_reduce_pairs<<<1, 256, 0, m->stream>>>(m->d_partials, nst + m->n_items[li], m->d_ip, ra);
     }
     if ((r = post_launch(m))) return r;
@@ -889,15 +924,18 @@ static int update(gmd_model *m, const State &O, const Tend &T, double dt, int be
     UpdateArgs b = a;
     b.rb[0] = r0; b.re[0] = r0 + m->bs; b.rb[1] = r1 - m->bn; b.re[1] = r1;
     const int nb = std::max(1, std::min(m->ew_blocks, (m->bs + m->bn) * m->geo.nlon / 1024 + 1));
+    b.tseq = tseq(m, "k_update.boundary");
     if (!m->dry) k_update<<<nb, 256, 0, m->stream>>>(b);
     if ((r = post_launch(m))) return r;
     a.rb[0] = r0 + m->bs; a.re[0] = r1 - m->bn; a.rb[1] = a.re[1] = 0;
+    a.tseq = tseq(m, "k_update.interior");
     if (!m->dry) k_update<<<m->ew_blocks, 256, 0, m->stream2>>>(a);
     if ((r = post_launch(m))) return r;
     return split_end(m);
   }
   if ((r = join(m))) return r;
   a.rb[0] = r0; a.re[0] = r1; a.rb[1] = a.re[1] = 0;
+  a.tseq = tseq(m, "k_update");
   if (!m->dry) k_update<<<m->ew_blocks, 256, 0, m->stream>>>(a);
   return post_launch(m);
 }
@@ -1070,7 +1108,8 @@ static int isp(gmd_model *m, const State &F, State *out) {
   if ((r = dot(m, T2.U, T2.V, T2.gd, F.U, F.V, F.gd, 0))) return r;
   if ((r = dot(m, T2.U, T2.V, T2.gd, T2.U, T2.V, T2.gd, 1))) return r;
   {
-    const RedArgs ra = red_args(m);
+    RedArgs ra = red_args(m);
+    ra.tseq = tseq(m, "k_reduce_pairs.isp");
     if (!m->dry) k_reduce_pairs<<<1, 256, 0, m->stream>>>(m->d_partials, m->ew_blocks, m->d_ip, ra);
   }
   if ((r = post_launch(m))) return r;
@@ -1145,22 +1184,37 @@ static int diffusion(gmd_model *m, double dt, const State &in, State *out) {
 static int diag(gmd_model *m, const State &s, int advance) {
   int r;
   if ((r = join(m))) return r;
-  if (!m->dry) k_diag<<<m->ew_blocks, 256, 0, m->stream>>>(m->geo, m->tab, s.U, s.V, s.gd, m->ghs, m->mesh.dlon, m->mesh.dlat,
-                                             m->d_partials);
+  {
+    const int ts = tseq(m, "k_diag");
+    if (!m->dry) k_diag<<<m->ew_blocks, 256, 0, m->stream>>>(m->geo, m->tab, s.U, s.V, s.gd, m->ghs, m->mesh.dlon, m->mesh.dlat,
+                                               m->d_partials, ts);
+  }
   if ((r = post_launch(m))) return r;
   {
-    const RedArgs ra = red_args(m);
+    RedArgs ra = red_args(m);
+    ra.tseq = tseq(m, "k_reduce_pairs.diag");
     if (!m->dry) k_reduce_pairs<<<1, 256, 0, m->stream>>>(m->d_partials, m->ew_blocks, m->d_sums, ra);
   }
   if ((r = post_launch(m))) return r;
   if ((r = allreduce2(m, m->d_sums))) return r;
-  if (!m->dry) k_diag_store<<<1, 32, 0, m->stream>>>(m->d_sums, m->d_beta, m->mesh.radius, m->d_ring, m->d_ctr, advance, gmd_model::RING);
+  {
+    const int ts = tseq(m, "k_diag_store");
+    if (!m->dry) k_diag_store<<<1, 32, 0, m->stream>>>(m->d_sums, m->d_beta, m->mesh.radius, m->d_ring, m->d_ctr, advance, gmd_model::RING, ts);
+  }
   if ((r = post_launch(m))) return r;
   return unit_end(m);
 }
 
 // time_integrate (src/dycore_mod.F90:654-669) + time_advance + diag_run for ONE step; consumes m->cur
+static int one_step_body(gmd_model *m);
 static int one_step(gmd_model *m) {
+  m->in_step = true;
+  m->step_launch0 = m->launches;
+  const int r = one_step_body(m);
+  m->in_step = false;
+  return r;
+}
+static int one_step_body(gmd_model *m) {
   int r;
   State next;
   switch (m->cfg.split_scheme) {
@@ -2107,6 +2161,69 @@ int gmd_get_table(const gmd_model *m, int which, double *out) {
   }
   for (int j = 0; j < n; j++) out[j] = (*t)[(size_t)(j + TPAD)];
   return 0;
+}
+
+}  // extern "C"
+
+extern "C" {
+
+int gmd_trace_begin(gmd_model *m) {
+  if (!m) return fail(GMD_ERR_ARG, "null model");
+#if GMD_TRACE
+  int r = set_dev(m);
+  if (r) return r;
+  if ((r = join(m))) return r;
+  CK(cudaStreamSynchronize(m->stream));
+  const size_t n = (size_t)gmd_model::TRACE_STEPS * gmd_model::TRACE_PER_STEP;
+  if (!m->d_trace) CK(cudaMalloc(&m->d_trace, n * 3 * sizeof(u64)));
+  std::vector<u64> h(n * 3, 0);
+  for (size_t k = 0; k < n; k++) h[3 * k] = ~0ull;
+  CK(cudaMemcpy(m->d_trace, h.data(), h.size() * sizeof(u64), cudaMemcpyHostToDevice));
+  TraceBuf tb = {m->d_trace, m->d_ctr, gmd_model::TRACE_STEPS, gmd_model::TRACE_PER_STEP};
+  CK(cudaMemcpyToSymbol(g_trace, &tb, sizeof tb));
+  m->trace_step0 = m->step;
+  return 0;
+#else
+  return fail(GMD_ERR_STATE, "this build has no device timeline (load libgmd_trace.so)");
+#endif
+}
+
+int gmd_trace_dump(gmd_model *m, const char *path) {
+  if (!m || !path) return fail(GMD_ERR_ARG, "null argument");
+#if GMD_TRACE
+  if (!m->d_trace) return fail(GMD_ERR_STATE, "gmd_trace_begin has not been called");
+  int r = set_dev(m);
+  if (r) return r;
+  if ((r = join(m))) return r;
+  CK(cudaStreamSynchronize(m->stream));
+  const size_t n = (size_t)gmd_model::TRACE_STEPS * gmd_model::TRACE_PER_STEP;
+  std::vector<u64> h(n * 3);
+  CK(cudaMemcpy(h.data(), m->d_trace, h.size() * sizeof(u64), cudaMemcpyDeviceToHost));
+  FILE *f = fopen(path, "w");
+  if (!f) return fail(GMD_ERR_ARG, "cannot write %s", path);
+  fprintf(f, "{\"rank\": %d, \"nranks\": %d, \"band\": [%d, %d], \"steps\": [", m->cfg.rank, m->cfg.nranks, m->geo.r0, m->geo.r1);
+  const int first = std::max(m->trace_step0, m->step - gmd_model::TRACE_STEPS);
+  for (int st = first; st < m->step; st++) {
+    fprintf(f, "%s{\"step\": %d, \"launches\": [", st == first ? "" : ", ", st);
+    const u64 *rec = h.data() + (size_t)(st % gmd_model::TRACE_STEPS) * gmd_model::TRACE_PER_STEP * 3;
+    bool any = false;
+    for (int q = 0; q < gmd_model::TRACE_PER_STEP; q++) {
+      if (rec[3 * q] == ~0ull) continue;
+      const char *nm = (size_t)q < m->trace_names.size() ? m->trace_names[(size_t)q].c_str() : "?";
+      fprintf(f, "%s{\"seq\": %d, \"kernel\": \"%s\", \"start_ns\": %llu, \"end_ns\": %llu, \"wait_ns\": %llu}", any ? ", " : "", q, nm,
+              rec[3 * q], rec[3 * q + 1], rec[3 * q + 2]);
+      any = true;
+    }
+    fprintf(f, "]}");
+  }
+  fprintf(f, "]}\n");
+  fclose(f);
+  TraceBuf tb = {nullptr, nullptr, 0, 0};
+  CK(cudaMemcpyToSymbol(g_trace, &tb, sizeof tb));
+  return 0;
+#else
+  return fail(GMD_ERR_STATE, "this build has no device timeline (load libgmd_trace.so)");
+#endif
 }
 
 }  // extern "C"

@@ -27,6 +27,59 @@ namespace gmd {
 constexpr int GHOST = 2;      // ghost rows on each side of a band
 typedef unsigned long long u64;
 
+// ---------------------------------------------------------------------------------------------------------
+// Device timeline (libgmd_trace.so only, -DGMD_TRACE=1): every launch of a model step records
+// {first CTA start, last CTA end, longest in-kernel wait for a neighbour} from %globaltimer into
+// rec[((step % steps) * per_step + seq) * 3 ..]; `seq` is the launch's position inside the step, baked into its
+// arguments (so a captured graph replays into the slots of the current step), the step number is the device step
+// counter.  The product build compiles all of this away.
+// ---------------------------------------------------------------------------------------------------------
+#ifndef GMD_TRACE
+#define GMD_TRACE 0
+#endif
+#if GMD_TRACE
+struct TraceBuf {
+  u64 *rec;
+  const int *ctr;
+  int steps, per_step;
+};
+__device__ TraceBuf g_trace;
+__device__ __forceinline__ u64 gtimer() {
+  u64 t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ u64 *trace_slot(int seq, int back) {
+  seq -= 1;   // 0 = no slot (zero-initialised argument structs)
+  if (seq < 0 || g_trace.rec == nullptr || seq >= g_trace.per_step) return nullptr;
+  const int st = (*g_trace.ctr - back) % g_trace.steps;
+  return g_trace.rec + ((size_t)(st < 0 ? st + g_trace.steps : st) * g_trace.per_step + seq) * 3;
+}
+__device__ __forceinline__ void trace_in(int seq, int back = 0) {
+  if (threadIdx.x == 0) {
+    u64 *r = trace_slot(seq, back);
+    if (r) atomicMin(r, gtimer());
+  }
+}
+__device__ __forceinline__ void trace_out(int seq, int back = 0) {
+  if (threadIdx.x == 0) {
+    u64 *r = trace_slot(seq, back);
+    if (r) atomicMax(r + 1, gtimer());
+  }
+}
+__device__ __forceinline__ void trace_wait(int seq, u64 t0) {
+  u64 *r = trace_slot(seq, 0);
+  if (r) atomicMax(r + 2, gtimer() - t0);
+}
+#define GMD_TRACE_T0() const u64 trace_t0_ = gtimer()
+#define GMD_TRACE_WAIT(seq) trace_wait(seq, trace_t0_)
+#else
+__device__ __forceinline__ void trace_in(int, int = 0) {}
+__device__ __forceinline__ void trace_out(int, int = 0) {}
+#define GMD_TRACE_T0() do { } while (0)
+#define GMD_TRACE_WAIT(seq) do { } while (0)
+#endif
+
 enum { PASS_ALL = 0, PASS_FAST = 1, PASS_SLOW = 2 };
 enum { ADV_CENTER = 0, ADV_UPWIND = 1, ADV_WENO = 2 };
 // what the stage kernel does with the tendency it has just computed
@@ -67,6 +120,7 @@ struct RedArgs {
   u64 *page;          // my signal page (page[SP_PEERTAB + p] = rank p's page as mapped here)
   int rank, nranks;
   unsigned k;         // reduction epoch = page[SP_RBASE] + k
+  int tseq;           // timeline slot + 1 of the launch (GMD_TRACE builds), 0 = none
 };
 // the inner-product finalisation folded into the launches that produce the partials (fold_tail below)
 struct Fold {
@@ -113,6 +167,7 @@ struct StageArgs {
   double ldt;
   int lqcon;
   Fold fold;   // MODE_S3A
+  int tseq;    // timeline slot + 1 of the launch (GMD_TRACE builds), 0 = none
 };
 
 // beta of predict_correct (src/dycore_mod.F90:784-785) from the device-resident inner products
@@ -186,7 +241,7 @@ __device__ __forceinline__ double block_sum(double v, double *red) {
 // releases a flag, acquires the flags of all ranks and sums the pairs in rank order (same bits on every rank).
 template <int NT>
 __device__ __forceinline__ void reduce_pairs_body(const double *partials, int n, double *out, u64 *page, int rank,
-                                                  int nranks, unsigned k, double *red, double *gath) {
+                                                  int nranks, unsigned k, double *red, double *gath, int tseq = 0) {
   double a0 = 0.0, a1 = 0.0;
   for (int q = threadIdx.x; q < n; q += NT) {
     a0 += __ldcg(partials + 2 * q);
@@ -216,7 +271,9 @@ __device__ __forceinline__ void reduce_pairs_body(const double *partials, int n,
     slot[1] = gath[2 * MAXR + 1];
     __threadfence_system();
     st_release_sys(pp + SP_RFLAG + par * MAXR + rank, ep);
+    GMD_TRACE_T0();
     spin_until(page + SP_RFLAG + par * MAXR + p, ep, page);
+    GMD_TRACE_WAIT(tseq);
     const volatile double *mine = reinterpret_cast<const volatile double *>(page + SP_RSLOT) + (par * MAXR + p) * 2;
     gath[2 * p] = mine[0];
     gath[2 * p + 1] = mine[1];
@@ -238,7 +295,7 @@ __device__ __forceinline__ void reduce_pairs_body(const double *partials, int n,
 // inlined and fed by scalars only: the row loop of k_stage keeps its registers.
 template <int NT>
 __device__ __noinline__ void fold_tail(unsigned *ticket, unsigned total, const double *partials, int n, double *out,
-                                       u64 *page, int rank, int nranks, unsigned k) {
+                                       u64 *page, int rank, int nranks, unsigned k, int tseq = 0) {
   __shared__ double red[32];
   __shared__ double gath[2 * MAXR + 2];
   __shared__ int last;
@@ -249,7 +306,7 @@ __device__ __noinline__ void fold_tail(unsigned *ticket, unsigned total, const d
   __syncthreads();
   if (!last) return;
   __threadfence();
-  reduce_pairs_body<NT>(partials, n, out, page, rank, nranks, k, red, gath);
+  reduce_pairs_body<NT>(partials, n, out, page, rank, nranks, k, red, gath, tseq);
   if (threadIdx.x == 0) *ticket = 0;
 }
 
@@ -476,6 +533,7 @@ __global__ void __launch_bounds__(BX, (LAZY ? GMD_LAZY_MINB : GMD_MINB)) k_stage
   const int nstrips = (nlon + WOUT - 1) / WOUT;
   const int ja = a.rb[blockIdx.z] + blockIdx.y * a.rows_per_cta;
   const int jb = min(ja + a.rows_per_cta, a.re[blockIdx.z]);
+  trace_in(a.tseq);
   if (ja >= jb) {  // whole CTA: this range has fewer chunks than gridDim.y
     if (MODE == MODE_S3A && threadIdx.x == 0) {
       const size_t b = (size_t)a.pofs[blockIdx.z] + (size_t)blockIdx.y * gridDim.x + blockIdx.x;
@@ -484,8 +542,9 @@ __global__ void __launch_bounds__(BX, (LAZY ? GMD_LAZY_MINB : GMD_MINB)) k_stage
     }
     if (MODE == MODE_S3A && a.fold.ticket)
       fold_tail<BX>(a.fold.ticket, a.fold.total, a.partials, a.fold.n, a.fold.out, a.fold.r.page, a.fold.r.rank, a.fold.r.nranks,
-                    a.fold.r.k);
+                    a.fold.r.k, a.tseq);
     if (PUSH) stage_signal(a);
+    trace_out(a.tseq);
     return;
   }
   const bool need_gh = (PASS != PASS_SLOW);
@@ -500,8 +559,10 @@ __global__ void __launch_bounds__(BX, (LAZY ? GMD_LAZY_MINB : GMD_MINB)) k_stage
     const int hs = a.hside[blockIdx.z];
     if (hs) {
       const u64 want = a.hpage[SP_XBASE] + a.hwait_k;
+      GMD_TRACE_T0();
       if (hs & 1) spin_until(a.hpage + SP_SIG, want, a.hpage);
       if (hs & 2) spin_until(a.hpage + SP_SIG + 1, want, a.hpage);
+      GMD_TRACE_WAIT(a.tseq);
     }
   }
   __syncthreads();
@@ -866,9 +927,10 @@ __global__ void __launch_bounds__(BX, (LAZY ? GMD_LAZY_MINB : GMD_MINB)) k_stage
     }
     if (a.fold.ticket)
       fold_tail<BX>(a.fold.ticket, a.fold.total, a.partials, a.fold.n, a.fold.out, a.fold.r.page, a.fold.r.rank, a.fold.r.nranks,
-                    a.fold.r.k);
+                    a.fold.r.k, a.tseq);
   }
   if (PUSH) stage_signal(a);
+  trace_out(a.tseq);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -912,6 +974,7 @@ struct PolarArgs {
   double radius, dlat;
   Fold fold;              // MODE_S3A: see k_stage
   const double *fold_partials;   // start of the whole partials array (this kernel's own pairs start at `partials`)
+  int tseq;               // timeline slot + 1 (GMD_TRACE builds), 0 = none
   unsigned items[MAX_ITEMS];
 };
 
@@ -1031,6 +1094,7 @@ __global__ void __launch_bounds__(PT) k_polar(const __grid_constant__ PolarArgs 
   const int j = (int)(pk & 0xffffu), cutoff = (int)((pk >> 16) & 0x1ffu) - 1, kind = (int)(pk >> 28);
   const int n = a.g.nlon, r0 = a.g.r0;
   const int tid = threadIdx.x;
+  trace_in(a.tseq);
   double *x = psm, *w = psm + n, *qs = psm + 2 * (size_t)n;
   const ptrdiff_t off = (ptrdiff_t)(j - r0) * (ptrdiff_t)n;
   const bool useq = (MODE != MODE_EVAL) && a.use_q;
@@ -1294,15 +1358,18 @@ __global__ void __launch_bounds__(PT) k_polar(const __grid_constant__ PolarArgs 
     }
     if (a.fold.ticket)
       fold_tail<PT>(a.fold.ticket, a.fold.total, a.fold_partials, a.fold.n, a.fold.out, a.fold.r.page, a.fold.r.rank,
-                    a.fold.r.nranks, a.fold.r.k);
+                    a.fold.r.nranks, a.fold.r.k, a.tseq);
   }
+  trace_out(a.tseq);
 }
 
 __global__ void __launch_bounds__(256) k_reduce_pairs(const double *__restrict__ partials, int n, double *out,
                                                       const RedArgs r) {
   __shared__ double red[32];
   __shared__ double gath[2 * MAXR + 2];
-  reduce_pairs_body<256>(partials, n, out, r.page, r.rank, r.nranks, r.k, red, gath);
+  trace_in(r.tseq);
+  reduce_pairs_body<256>(partials, n, out, r.page, r.rank, r.nranks, r.k, red, gath, r.tseq);
+  trace_out(r.tseq);
 }
 
 // Halo rows of up to three fields stored straight into the neighbours' ghost rows, then one release per
@@ -1316,8 +1383,10 @@ struct PushArgs {
   u64 *page;          // my signal page
   u64 *sigS, *sigN;   // the word each neighbour waits on (its SP_SIG+1 / SP_SIG+0), or null
   unsigned k;         // halo epoch = page[SP_XBASE] + k
+  int tseq;
 };
 __global__ void __launch_bounds__(256) k_halo_push(const PushArgs a) {
+  trace_in(a.tseq);
   const int nlon = a.g.nlon, nr = a.g.r1 - a.g.r0;
   const int n2 = nlon >> 1;  // 16-byte units per row
   int first[7];              // prefix of rows: (f0 S, f0 N, f1 S, f1 N, f2 S, f2 N)
@@ -1353,19 +1422,25 @@ __global__ void __launch_bounds__(256) k_halo_push(const PushArgs a) {
       if (a.sigN) st_release_sys(a.sigN, ep);
     }
   }
+  trace_out(a.tseq);
 }
 // consumers that are not the stage kernel: block the stream until halo epoch page[SP_XBASE] + k has arrived
-__global__ void k_halo_wait(u64 *page, unsigned k, int sides) {
+__global__ void k_halo_wait(u64 *page, unsigned k, int sides, int tseq) {
+  trace_in(tseq);
   if (threadIdx.x == 0) {
     const u64 want = page[SP_XBASE] + k;
+    GMD_TRACE_T0();
     if (sides & 1) spin_until(page + SP_SIG, want, page);
     if (sides & 2) spin_until(page + SP_SIG + 1, want, page);
+    GMD_TRACE_WAIT(tseq);
   }
+  trace_out(tseq);
 }
 // end of a unit of work (one model step, one direct API call): all incoming halos of the unit have landed (so the
 // host may touch the ghost rows, and a neighbour may free its slab), then the epoch bases advance.  The epochs
 // inside a unit are base + k with k baked into the launches, which is what makes a captured step replayable.
-__global__ void k_unit_end(u64 *page, unsigned nx, unsigned nred, int sides) {
+__global__ void k_unit_end(u64 *page, unsigned nx, unsigned nred, int sides, int tseq) {
+  trace_in(tseq, 1);   // runs after k_diag_store has advanced the step counter
   if (threadIdx.x == 0) {
     const u64 want = page[SP_XBASE] + nx;
     if (sides & 1) spin_until(page + SP_SIG, want, page);
@@ -1373,6 +1448,7 @@ __global__ void k_unit_end(u64 *page, unsigned nx, unsigned nred, int sides) {
     page[SP_XBASE] = want;
     page[SP_RBASE] = page[SP_RBASE] + nred;
   }
+  trace_out(tseq, 1);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -1390,11 +1466,13 @@ struct UpdateArgs {
   double *beta_out;   // device scalar, written by one thread
   int with_gd;        // 0: slow pass, gd is shared
   int rb[2], re[2];   // up to two row ranges handled by this launch (empty when rb >= re)
+  int tseq;
 };
 
 
 // update_state on stored tendencies (src/dycore_mod.F90:600-652), U/V/gd only: new = old + dt' * tend
 __global__ void __launch_bounds__(256) k_update(const UpdateArgs a) {
+  trace_in(a.tseq);
   double dt = a.dt;
   if (a.beta_mode) {
     double beta = beta_from_ip(a.ip, a.qcon);
@@ -1415,6 +1493,7 @@ __global__ void __launch_bounds__(256) k_update(const UpdateArgs a) {
       if (a.with_gd) a.Ngd[k] = a.Ogd[k] + dt * a.Tgd[k];
     }
   }
+  trace_out(a.tseq);
 }
 
 // iap_transform (src/types_mod.F90:399-426): U = 0.5 (s_i + s_i+1) u ; V = 0.5 (s_j + s_j+1) v
@@ -1454,8 +1533,9 @@ __global__ void __launch_bounds__(256) k_derive(Geo g, int ja, int jb, const dou
 
 // diag_run totals (src/diag_mod.F90:71-77,98-121): per-CTA partials {sum cos dlon dlat gd, energy}
 __global__ void __launch_bounds__(256) k_diag(Geo g, Tab t, const double *U, const double *V, const double *gd,
-                                              const double *ghs, double dlon, double dlat, double *partials) {
+                                              const double *ghs, double dlon, double dlat, double *partials, int tseq) {
   __shared__ double red[32];
+  trace_in(tseq);
   const int nlon = g.nlon;
   const size_t total = (size_t)(g.r1 - g.r0) * (size_t)nlon;
   double m = 0.0, e = 0.0;
@@ -1480,12 +1560,15 @@ __global__ void __launch_bounds__(256) k_diag(Geo g, Tab t, const double *U, con
     partials[2 * blockIdx.x] = rm;
     partials[2 * blockIdx.x + 1] = re;
   }
+  trace_out(tseq);
 }
 
 // ring[ctr % nring] = {mass * radius^2, energy, beta}; the step counter lives on the device so that a
 // captured graph of one model step is replayable for any step number
 __global__ void k_diag_store(const double *sums, const double *beta, double radius, double *ring, int *ctr,
-                             int advance, int nring) {
+                             int advance, int nring, int tseq) {
+  trace_in(tseq);
+  trace_out(tseq);   // (a few hundred ns; stamped before the counter advances)
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     int c = *ctr;
     if (advance) {

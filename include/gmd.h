@@ -173,6 +173,12 @@ int gmd_time_stage_kernel(gmd_model *m, int reps, float *ms_per_launch, double *
    2 = S3a (tendency + inner products), 3 = evaluation only */
 int gmd_time_stage_variant(gmd_model *m, int pass, int mode, int reps, float *ms_per_launch,
                            double *alg_bytes_per_launch);
+/* Device timeline of the following model steps (libgmd_trace.so, the -DGMD_TRACE=1 build of the same sources; the
+   product build returns GMD_ERR_STATE): every kernel launch of a step records the %globaltimer of its first CTA's
+   start, its last CTA's end and the longest in-kernel wait for a neighbour rank.  gmd_trace_dump writes the last
+   (up to 4) steps as JSON: {"steps": [{"step": n, "launches": [{"seq", "kernel", "start_ns", "end_ns", "wait_ns"}]}]} */
+int gmd_trace_begin(gmd_model *m);
+int gmd_trace_dump(gmd_model *m, const char *path);
 
 #ifdef __cplusplus
 }

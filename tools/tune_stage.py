@@ -9,10 +9,10 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import gamil_dycore_b200 as gmd  # noqa: E402
-from gamil_dycore_b200 import ics  # noqa: E402
+import gamil_dycore_b200 as gmd_pkg  # noqa: E402
 
 nlon, nlat = int(os.environ.get("NLON", 3600)), int(os.environ.get("NLAT", 1801))
-u, v, gd, ghs = ics.steady_geostrophic_flow(nlon, nlat)
+u, v, gd, ghs = gmd_pkg.initial_condition("steady_geostrophic_flow", nlon, nlat)
 libs = sys.argv[1:] or ["fast"]
 for lib in libs:
     kind = lib if lib in ("fast", "strict") else os.path.abspath(lib)
