@@ -206,6 +206,7 @@ def main():
                          "against the polar-row work, gamil_dycore_b200.parallel.polar_band_rows_for)")
     ap.add_argument("--comm", default="peer", choices=["peer", "nccl"],
                     help="multi-GPU data path: NVLink peer memory (default) or NCCL send/recv + all-reduce")
+    ap.add_argument("--lib", default=None, help="path of an alternative build of libgmd (experiments; default: the product)")
     ap.add_argument("--trace", default=None,
                     help="write a per-launch device timeline of one model step (libgmd_trace.so build) to this file "
                          "prefix (one JSON per rank) instead of benchmarking")
@@ -236,7 +237,7 @@ def main():
     from gamil_dycore_b200 import parallel
     pbr = args.polar_band_rows if args.polar_band_rows >= 0 else parallel.polar_band_rows_for(
         world, kw["num_lon"], kw["num_lat"], any(kw["zonal_tend_filter_cutoff_wavenumber"]))
-    kind = "trace" if args.trace else "fast"
+    kind = os.path.abspath(args.lib) if args.lib else ("trace" if args.trace else "fast")
     d = gmd.Dycore(gmd.Config(rank=rank, nranks=world, device=local, polar_band_rows=pbr, **kw), kind=kind)
     if world > 1:
         args.comm = parallel.connect(d, mode=args.comm)   # "peer" falls back to "nccl" if CUDA IPC is not available

@@ -135,7 +135,10 @@ struct gmd_model {
 
   State cur;
   double *ghs = nullptr;
-  Tend tendOld, tendNew, tendA, tendB;  // tendA/B: isp only
+  Tend tendOld, tendNew, tendNew2, tendA, tendB;  // tendA/B: isp only
+  // the new tendency of predict_correct alternates between tendNew and tendNew2: a neighbour band stores the ghost
+  // rows of predict_correct k+1 while this band may still be reading those of k (deferred update)
+  int tn_idx = 0;
   double *d_partials = nullptr;
   int n_partials = 0;
   double *d_ip = nullptr;    // {ip1, ip2}
@@ -161,6 +164,7 @@ struct gmd_model {
   std::vector<cudaEvent_t> evpool;
   size_t evnext = 0;
   cudaEvent_t last_eI = nullptr;  // completion of the last interior launch on stream2
+  cudaEvent_t ev_polar_side = nullptr;  // completion of the last polar-side stage launch on the main stream
   bool split = true;
   int ew_blocks = 0;  // grid of element-wise kernels
 
@@ -174,8 +178,15 @@ struct gmd_model {
   size_t peer_fld[2] = {0, 0};
   std::vector<void *> ipc_opened;
   unsigned xk = 0, rk = 0, xwaited = 0;  // halo epochs released / reductions done / halo epoch waited for, this unit
-  bool fuse_push = false;     // band-edge rows are stored to the neighbours by the boundary stage launch itself
-  bool stage_pushed = false;  // the last stage() call did so: the exchange that follows is already done
+  bool fuse_push = false;     // band-edge rows of the new tendency are stored to the neighbours by the S3a launches
+  // wide-halo predict_correct: the three sweeps run on rows shrinking by (1 south, 2 north) per
+  // sweep, the bands exchange only the new tendency, once per predict_correct
+  bool wide = false;
+  // A wide-halo predict_correct synchronises the bands only through its all-reduce, so after it a band may still be
+  // reading buffers (its k_update) that a faster neighbour has already released, re-acquired and would now store
+  // ghost rows into.  The first generic halo push after such a predict_correct is therefore preceded by a
+  // signal-only exchange: it completes once BOTH neighbours have reached the same point of their streams.
+  bool need_fence = false;
 
   // graphs
   bool graph_mode = true;
@@ -455,7 +466,7 @@ static int build_tables(gmd_model *m) {
 // launchers
 // ---------------------------------------------------------------------------------------------------------
 typedef void (*stage_fn)(const StageArgs);
-// PUSH instantiations exist for the schemes a multi-rank run supports (not WENO) and the modes that produce rows
+// PUSH instantiations exist for MODE_S3A of the schemes a wide-halo predict_correct supports (not WENO)
 template <int MODE, bool PUSH>
 static stage_fn pick_stage_mode(int pass, int adv) {
   if (pass == PASS_FAST) return k_stage<PASS_FAST, ADV_CENTER, MODE, 0, PUSH>;
@@ -471,14 +482,7 @@ static stage_fn pick_stage_mode(int pass, int adv) {
   else return k_stage<PASS_SLOW, ADV_WENO, MODE, 0, false>;
 }
 static stage_fn pick_stage(int pass, int adv, int mode, bool push = false) {
-  if (push) {
-    switch (mode) {
-      case MODE_S1: return pick_stage_mode<MODE_S1, true>(pass, adv);
-      case MODE_S2: return pick_stage_mode<MODE_S2, true>(pass, adv);
-      case MODE_S3A: return pick_stage_mode<MODE_S3A, true>(pass, adv);
-      default: return nullptr;
-    }
-  }
+  if (push) return mode == MODE_S3A ? pick_stage_mode<MODE_S3A, true>(pass, adv) : nullptr;
   switch (mode) {
     case MODE_S1: return pick_stage_mode<MODE_S1, false>(pass, adv);
     case MODE_S2: return pick_stage_mode<MODE_S2, false>(pass, adv);
@@ -489,16 +493,15 @@ static stage_fn pick_stage(int pass, int adv, int mode, bool push = false) {
 
 // MODE_S1 with the previous predict_correct's update folded in (k_stage LAZY = 1 / 2); never with WENO (its
 // advection terms come from separate sweeps over a stored state)
-template <int LZ, bool PUSH>
+template <int LZ>
 static stage_fn pick_stage_lazy_t(int pass, int adv) {
-  if (pass == PASS_FAST) return k_stage<PASS_FAST, ADV_CENTER, MODE_S1, LZ, PUSH>;
+  if (pass == PASS_FAST) return k_stage<PASS_FAST, ADV_CENTER, MODE_S1, LZ, false>;
   if (pass == PASS_ALL)
-    return adv == ADV_UPWIND ? k_stage<PASS_ALL, ADV_UPWIND, MODE_S1, LZ, PUSH> : k_stage<PASS_ALL, ADV_CENTER, MODE_S1, LZ, PUSH>;
-  return adv == ADV_UPWIND ? k_stage<PASS_SLOW, ADV_UPWIND, MODE_S1, LZ, PUSH> : k_stage<PASS_SLOW, ADV_CENTER, MODE_S1, LZ, PUSH>;
+    return adv == ADV_UPWIND ? k_stage<PASS_ALL, ADV_UPWIND, MODE_S1, LZ, false> : k_stage<PASS_ALL, ADV_CENTER, MODE_S1, LZ, false>;
+  return adv == ADV_UPWIND ? k_stage<PASS_SLOW, ADV_UPWIND, MODE_S1, LZ, false> : k_stage<PASS_SLOW, ADV_CENTER, MODE_S1, LZ, false>;
 }
-static stage_fn pick_stage_lazy(int pass, int adv, int lazy, bool push = false) {
-  if (lazy == 1) return push ? pick_stage_lazy_t<1, true>(pass, adv) : pick_stage_lazy_t<1, false>(pass, adv);
-  return push ? pick_stage_lazy_t<2, true>(pass, adv) : pick_stage_lazy_t<2, false>(pass, adv);
+static stage_fn pick_stage_lazy(int pass, int adv, int lazy) {
+  return lazy == 1 ? pick_stage_lazy_t<1>(pass, adv) : pick_stage_lazy_t<2>(pass, adv);
 }
 
 static int post_launch(gmd_model *m) {
@@ -537,7 +540,16 @@ static int halo_sides(const gmd_model *m) {
   return (m->cfg.rank > 0 ? 1 : 0) | (m->cfg.rank + 1 < m->cfg.nranks ? 2 : 0);
 }
 // store halo rows of up to three fields into the neighbours' ghost rows and release halo epoch ++xk
+static int halo_wait(gmd_model *m);
 static int halo_push(gmd_model *m, double *const f[3], const int ns[3], const int nn[3]) {
+  if (m->need_fence) {
+    m->need_fence = false;
+    double *const none[3] = {nullptr, nullptr, nullptr};
+    const int z[3] = {0, 0, 0};
+    int r;
+    if ((r = halo_push(m, none, z, z))) return r;   // signal only
+    if ((r = halo_wait(m))) return r;
+  }
   const int ts = tseq(m, "k_halo_push");
   m->xk++;
   m->launches++;
@@ -598,21 +610,23 @@ static RedArgs red_args(gmd_model *m) {
   return r;
 }
 
-// ghosts the stage kernel needs: south U,V,gd row r0-1; north U,V row r1, gd rows r1, r1+1
+// ghost rows of a state: a sweep needs U, V, gd row r0-1 from the south and U, V row r1, gd rows r1, r1+1 from the
+// north; a wide-halo predict_correct starts from HALO_S / HALO_N rows.  Every state exchange moves the
+// wide set (my top HALO_S rows go north, my bottom HALO_N rows go south).
 static int exchange_state(gmd_model *m, const State &s, bool with_gd) {
   if (m->cfg.nranks == 1) return 0;
   if (m->p2p) {
     double *const f[3] = {s.U, s.V, with_gd ? s.gd : nullptr};
-    const int ns[3] = {1, 1, 1}, nn[3] = {1, 1, 2};
+    const int ns[3] = {HALO_S, HALO_S, HALO_S}, nn[3] = {HALO_N, HALO_N, HALO_N};
     return halo_push(m, f, ns, nn);
   }
   if (m->dry) return 0;
   if (!m->comm) return fail(GMD_ERR_COMM, "neither gmd_peer_connect nor gmd_comm_init has been called on this rank");
   NK(g_nccl.GroupStart());
   int r;
-  if ((r = exchange_field(m, s.U, 1, 1))) return r;
-  if ((r = exchange_field(m, s.V, 1, 1))) return r;
-  if (with_gd && (r = exchange_field(m, s.gd, 1, 2))) return r;
+  if ((r = exchange_field(m, s.U, HALO_S, HALO_N))) return r;
+  if ((r = exchange_field(m, s.V, HALO_S, HALO_N))) return r;
+  if (with_gd && (r = exchange_field(m, s.gd, HALO_S, HALO_N))) return r;
   NK(g_nccl.GroupEnd());
   return 0;
 }
@@ -651,11 +665,18 @@ static int join(gmd_model *m) {
 }
 // stream2 sees everything queued on the main stream so far (previous boundary launch, polar rows, halo exchange,
 // reductions); the main stream sees the previous interior launch
-static int split_begin(gmd_model *m) {
+// `light`: stream2 only needs the polar-side launch of the previous sweep (recorded in ev_polar_side), valid when
+// nothing but that launch and its polar rows has been queued on the main stream since
+static int split_begin(gmd_model *m, bool light = false) {
   if (m->dry) return 0;
-  cudaEvent_t e = next_event(m);
-  CK(cudaEventRecord(e, m->stream));
-  CK(cudaStreamWaitEvent(m->stream2, e, 0));
+  if (light && m->ev_polar_side) {
+    CK(cudaStreamWaitEvent(m->stream2, m->ev_polar_side, 0));
+  } else {
+    cudaEvent_t e = next_event(m);
+    CK(cudaEventRecord(e, m->stream));
+    CK(cudaStreamWaitEvent(m->stream2, e, 0));
+  }
+  m->ev_polar_side = nullptr;
   return join(m);
 }
 static int split_end(gmd_model *m) {
@@ -665,7 +686,7 @@ static int split_end(gmd_model *m) {
   m->last_eI = e;
   return 0;
 }
-static bool use_split(const gmd_model *m) { return m->split && (m->geo.r0 + m->bs < m->geo.r1 - m->bn); }
+static bool use_split(const gmd_model *m) { return m->split && (m->bs + m->bn > 0) && (m->geo.r0 + m->bs < m->geo.r1 - m->bn); }
 
 static int ensure_weno(gmd_model *m) {
   if (m->w_fpu) return 0;
@@ -763,12 +784,15 @@ struct LazyIn {
   int kind;   // 1: U, V and gd carry a tendency; 2: U, V only (previous pass was slow)
 };
 
+// es / en: the sweep also covers `es` rows south and `en` rows north of the band (wide-halo predict_correct; 0 on a
+// side without a neighbour).  push: MODE_S3A of a wide-halo predict_correct on the peer path -- the band-edge rows
+// of the tendency T are stored into the neighbours' ghost rows by the launch itself.
 static int stage(gmd_model *m, int pass, int mode, const State &E, const State *O, double dt, State *N, Tend *T,
-                 const Tend *P, const LazyIn *lz = nullptr, bool want_push = false) {
+                 const Tend *P, const LazyIn *lz = nullptr, int es = 0, int en = 0, bool push = false) {
   int r;
   const int adv = m->cfg.uv_adv_scheme;
-  m->stage_pushed = false;
   if (pass != PASS_FAST && adv == ADV_WENO && (r = weno_terms(m, E))) return r;
+  if ((r = halo_wait(m))) return r;   // rows pushed by a generic exchange (isp, diffusion, WENO, direct API calls)
   StageArgs a;
   memset(&a, 0, sizeof a);
   a.g = m->geo;
@@ -800,71 +824,73 @@ static int stage(gmd_model *m, int pass, int mode, const State &E, const State *
     fn = pick_stage_lazy(pass, adv, lz->kind);
   }
   const int r0 = m->geo.r0, r1 = m->geo.r1;
-  int nst;
+  if (push && mode == MODE_S3A && m->p2p) {
+    stage_fn pf = pick_stage(pass, adv, mode, true);
+    if (pf) {
+      double *fg = (pass == PASS_SLOW) ? nullptr : T->gd;
+      fn = pf;
+      a.hpS_U = peer_ptr(m, 0, T->U); a.hpS_V = peer_ptr(m, 0, T->V); a.hpS_G = peer_ptr(m, 0, fg);
+      a.hpN_U = peer_ptr(m, 1, T->U); a.hpN_V = peer_ptr(m, 1, T->V); a.hpN_G = peer_ptr(m, 1, fg);
+      a.push_s_end = r0 + HALO_N;
+      a.push_n_begin = r1 - HALO_S;
+    }
+  }
+  const bool poleS = (r0 == 0), poleN = (r1 == m->geo.nlat);
+  const int R0 = r0 - es, R1 = r1 + en;   // rows of this sweep
   const int li = (pass == PASS_SLOW) ? 1 : 0;
+  const bool split = use_split(m);
+  // launch geometry
+  const int I0 = split ? (poleS ? r0 + m->bs : R0) : R0, I1 = split ? (poleN ? r1 - m->bn : R1) : R1;
+  const int nci = (I1 - I0 + m->rows_per_cta - 1) / m->rows_per_cta;
+  const int ncb = split ? m->nchunks_b : 0;
+  const int nst = 2 * m->nbx * ncb + m->nbx * nci;
   if (fold) {  // one partial pair and one ticket per CTA of the stage launch(es) and of the polar-row launch
-    const int ncta = use_split(m) ? 2 * m->nbx * m->nchunks_b + m->nbx * m->nchunks_i : m->nbx * m->nchunks;
     a.fold.ticket = reinterpret_cast<unsigned *>(m->d_ip + 7);
-    a.fold.total = (unsigned)(ncta + m->n_items[li]);
-    a.fold.n = ncta + m->n_items[li];
+    a.fold.total = (unsigned)(nst + m->n_items[li]);
+    a.fold.n = nst + m->n_items[li];
     a.fold.out = m->d_ip;
     a.fold.r = red_args(m);
   }
-  if (use_split(m)) {
-    // boundary rows first on the main stream (then polar rows / halo exchange), interior rows on stream2
-    if ((r = split_begin(m))) return r;
+  const int edges = (es ? 1 : 0) | (en ? 2 : 0);   // sides on which the deferred update also writes the rows beyond the sweep
+  if (split) {
+    // rows next to a pole first on the main stream (then the polar rows), the other rows on stream2
+    // S2 / S3a follow S1 / S2 of the same predict_correct directly: their interior launch reads nothing the polar rows
+    // of the previous sweep produce (S1 of a deferred update reads the inner products: full dependency)
+    if ((r = split_begin(m, mode == MODE_S2 || mode == MODE_S3A))) return r;
     StageArgs b = a;
-    stage_fn fnb = fn;
-    if (m->p2p) {  // the boundary CTAs wait for the neighbours' halo rows themselves
-      b.hpage = m->page;
-      b.hwait_k = m->xk;
-      b.hside[0] = halo_sides(m) & 1;
-      b.hside[1] = halo_sides(m) & 2;
-      m->xwaited = m->xk;
-      stage_fn pf = nullptr;
-      if (want_push && m->fuse_push && mode != MODE_EVAL)
-        pf = lz ? pick_stage_lazy(pass, adv, lz->kind, true) : pick_stage(pass, adv, mode, true);
-      if (pf) {
-        // the rows the neighbours need: new state (S1, S2) or tendency (S3A)
-        double *fu = (mode == MODE_S3A) ? T->U : N->U, *fv = (mode == MODE_S3A) ? T->V : N->V;
-        double *fg = (pass == PASS_SLOW) ? nullptr : ((mode == MODE_S3A) ? T->gd : N->gd);
-        fnb = pf;
-        b.hsig_k = ++m->xk;
-        b.hpS_U = peer_ptr(m, 0, fu); b.hpS_V = peer_ptr(m, 0, fv); b.hpS_G = peer_ptr(m, 0, fg);
-        b.hpN_U = peer_ptr(m, 1, fu); b.hpN_V = peer_ptr(m, 1, fv); b.hpN_G = peer_ptr(m, 1, fg);
-        b.hsigS = (m->cfg.rank > 0) ? m->peer_page[m->cfg.rank - 1] + SP_SIG + 1 : nullptr;
-        b.hsigN = (m->cfg.rank + 1 < m->cfg.nranks) ? m->peer_page[m->cfg.rank + 1] + SP_SIG : nullptr;
-        m->stage_pushed = true;
-      }
-    }
+    b.hpS_U = b.hpS_V = b.hpS_G = b.hpN_U = b.hpN_V = b.hpN_G = nullptr;   // band-edge rows are interior rows
     b.rows_per_cta = m->rows_per_cta_b;
-    b.rb[0] = r0; b.re[0] = r0 + m->bs; b.pofs[0] = 0;
-    b.rb[1] = r1 - m->bn; b.re[1] = r1; b.pofs[1] = m->nbx * m->nchunks_b;
-    dim3 gb((unsigned)m->nbx, (unsigned)m->nchunks_b, 2);
-    static const char *const bnames[4] = {"k_stage.S1.boundary", "k_stage.S2.boundary", "k_stage.S3a.boundary", "k_stage.eval.boundary"};
+    b.rb[0] = r0; b.re[0] = poleS ? r0 + m->bs : r0; b.pofs[0] = 0;
+    b.rb[1] = poleN ? r1 - m->bn : r1; b.re[1] = r1; b.pofs[1] = m->nbx * ncb;
+    dim3 gb((unsigned)m->nbx, (unsigned)ncb, 2);
+    static const char *const bnames[4] = {"k_stage.S1.polar_side", "k_stage.S2.polar_side", "k_stage.S3a.polar_side", "k_stage.eval.polar_side"};
     b.tseq = tseq(m, bnames[mode]);
-    if (!m->dry) fnb<<<gb, BX, m->stage_smem_b, m->stream>>>(b);
+    if (!m->dry) fn<<<gb, BX, m->stage_smem_b, m->stream>>>(b);
     if ((r = post_launch(m))) return r;
+    if (!m->dry) {   // what the NEXT sweep's interior launch has to wait for on the main stream: this launch, not the
+      cudaEvent_t e = next_event(m);   // polar rows that follow it (its rows are at least two rows away from them)
+      CK(cudaEventRecord(e, m->stream));
+      m->ev_polar_side = e;
+    }
     a.rows_per_cta = m->rows_per_cta;
-    a.rb[0] = r0 + m->bs; a.re[0] = r1 - m->bn; a.pofs[0] = 2 * m->nbx * m->nchunks_b;
-    dim3 gi((unsigned)m->nbx, (unsigned)m->nchunks_i, 1);
+    a.rb[0] = I0; a.re[0] = I1; a.pofs[0] = 2 * m->nbx * ncb;
+    a.medge[0] = edges & ((poleS ? 0 : 1) | (poleN ? 0 : 2));
+    dim3 gi((unsigned)m->nbx, (unsigned)nci, 1);
     static const char *const inames[4] = {"k_stage.S1.interior", "k_stage.S2.interior", "k_stage.S3a.interior", "k_stage.eval.interior"};
     a.tseq = tseq(m, inames[mode]);
     if (!m->dry) fn<<<gi, BX, m->stage_smem, m->stream2>>>(a);
     if ((r = post_launch(m))) return r;
     if ((r = split_end(m))) return r;
-    nst = 2 * m->nbx * m->nchunks_b + m->nbx * m->nchunks_i;
   } else {
     if ((r = join(m))) return r;
-    if ((r = halo_wait(m))) return r;
     a.rows_per_cta = m->rows_per_cta;
-    a.rb[0] = r0; a.re[0] = r1; a.pofs[0] = 0;
-    dim3 grid((unsigned)m->nbx, (unsigned)m->nchunks, 1);
+    a.rb[0] = R0; a.re[0] = R1; a.pofs[0] = 0;
+    a.medge[0] = edges;
+    dim3 grid((unsigned)m->nbx, (unsigned)nci, 1);
     static const char *const wnames[4] = {"k_stage.S1", "k_stage.S2", "k_stage.S3a", "k_stage.eval"};
     a.tseq = tseq(m, wnames[mode]);
     if (!m->dry) fn<<<grid, BX, m->stage_smem, m->stream>>>(a);
     if ((r = post_launch(m))) return r;
-    nst = m->nbx * m->nchunks;
   }
 
   if (m->n_items[li]) {
@@ -902,8 +928,10 @@ static int stage(gmd_model *m, int pass, int mode, const State &E, const State *
   return 0;
 }
 
+// es / en: also on `es` ghost rows south and `en` ghost rows north of the band (wide-halo predict_correct: the
+// tendency's ghost rows have arrived with the inner-product all-reduce)
 static int update(gmd_model *m, const State &O, const Tend &T, double dt, int beta_mode, double dt0, bool with_gd,
-                  State *N) {
+                  State *N, int es = 0, int en = 0) {
   UpdateArgs a;
   memset(&a, 0, sizeof a);
   a.g = m->geo;
@@ -918,21 +946,8 @@ static int update(gmd_model *m, const State &O, const Tend &T, double dt, int be
   a.beta_out = m->d_beta;
   a.with_gd = with_gd ? 1 : 0;
   int r;
-  const int r0 = m->geo.r0, r1 = m->geo.r1;
-  if (use_split(m)) {
-    if ((r = split_begin(m))) return r;
-    UpdateArgs b = a;
-    b.rb[0] = r0; b.re[0] = r0 + m->bs; b.rb[1] = r1 - m->bn; b.re[1] = r1;
-    const int nb = std::max(1, std::min(m->ew_blocks, (m->bs + m->bn) * m->geo.nlon / 1024 + 1));
-    b.tseq = tseq(m, "k_update.boundary");
-    if (!m->dry) k_update<<<nb, 256, 0, m->stream>>>(b);
-    if ((r = post_launch(m))) return r;
-    a.rb[0] = r0 + m->bs; a.re[0] = r1 - m->bn; a.rb[1] = a.re[1] = 0;
-    a.tseq = tseq(m, "k_update.interior");
-    if (!m->dry) k_update<<<m->ew_blocks, 256, 0, m->stream2>>>(a);
-    if ((r = post_launch(m))) return r;
-    return split_end(m);
-  }
+  const int r0 = m->geo.r0 - es, r1 = m->geo.r1 + en;
+  if ((r = halo_wait(m))) return r;
   if ((r = join(m))) return r;
   a.rb[0] = r0; a.re[0] = r1; a.rb[1] = a.re[1] = 0;
   a.tseq = tseq(m, "k_update");
@@ -948,19 +963,33 @@ struct Carry {
   State base;
   bool deferred = false;
   double dts = 0.0;
-  bool with_gd = false;   // tendNew.gd takes part (the pass that produced it was not slow)
+  bool with_gd = false;   // the tendency's gd takes part (the pass that produced it was not slow)
+  const Tend *L = nullptr;  // deferred: the new tendency of the predict_correct that produced this carry
 };
 
 // predict_correct(dt, in -> *out, pass), src/dycore_mod.F90:754-792.  `in.base` is kept (the caller releases it);
 // with `defer_out` the result is returned deferred (out->base = the old state of THIS call, retained once more).
+//
+// Latitude bands (m->wide): the call starts from a state that is valid on HALO_S ghost rows south and HALO_N north of
+// the band; sweep 1 covers (2, 4) rows beyond the band, sweep 2 (1, 2), sweep 3 the band itself -- each sweep's
+// stencil reaches 1 row south and 2 rows north -- and the only rows exchanged are those of the new tendency, whose
+// arrival is signalled by the inner-product all-reduce every rank waits for anyway.  The last update_state (or the
+// next call's deferred one) then runs on the ghost rows as well, which restores the invariant.
 static int predict_correct(gmd_model *m, double dts, const Carry &in, int pass, bool defer_out, Carry *out) {
   int r;
   const bool slow = (pass == PASS_SLOW);
   const double dt = dts * 0.5;
+  const bool wide = m->wide;
+  const int hs = (wide && m->cfg.rank > 0) ? 1 : 0, hn = (wide && m->cfg.rank + 1 < m->cfg.nranks) ? 1 : 0;
+  Tend *Tn = &m->tendNew;
+  if (m->cfg.nranks > 1) {   // see gmd_model::tn_idx
+    if (m->tn_idx) Tn = &m->tendNew2;
+    m->tn_idx ^= 1;
+  }
   State O = in.base, M, A, B;
   bool ownO = false;
   if (in.deferred) {
-    // old state of this call = in.base + beta in.dts tendNew, materialised by the first sweep
+    // old state of this call = in.base + beta in.dts tend(new) of the previous call, materialised by the first sweep
     if ((r = new_state(m, &M, in.with_gd ? nullptr : in.base.gd))) return r;
     O = M;
     ownO = true;
@@ -969,22 +998,27 @@ static int predict_correct(gmd_model *m, double dts, const Carry &in, int pass, 
   if ((r = new_state(m, &B, slow ? O.gd : nullptr))) return r;
   // tend(old) = L(old); new = old + dt/2 tend(old)
   if (in.deferred) {
-    LazyIn lz = {&m->tendNew, in.dts, &M, in.with_gd ? 1 : 2};
-    if ((r = stage(m, pass, MODE_S1, in.base, nullptr, dt, &A, &m->tendOld, nullptr, &lz, true))) return r;
+    LazyIn lz = {in.L, in.dts, &M, in.with_gd ? 1 : 2};
+    if ((r = stage(m, pass, MODE_S1, in.base, nullptr, dt, &A, &m->tendOld, nullptr, &lz, 2 * hs, 4 * hn))) return r;
   } else {
-    if ((r = stage(m, pass, MODE_S1, O, &O, dt, &A, &m->tendOld, nullptr, nullptr, true))) return r;
+    if ((r = stage(m, pass, MODE_S1, O, &O, dt, &A, &m->tendOld, nullptr, nullptr, 2 * hs, 4 * hn))) return r;
   }
-  if (!m->stage_pushed && (r = exchange_state(m, A, !slow))) return r;
+  if (!wide && (r = exchange_state(m, A, !slow))) return r;
   // tend(old) = L(new); new = old + dt/2 tend(old)
-  if ((r = stage(m, pass, MODE_S2, A, &O, dt, &B, &m->tendOld, nullptr, nullptr, true))) return r;
-  if (!m->stage_pushed && (r = exchange_state(m, B, !slow))) return r;
+  if ((r = stage(m, pass, MODE_S2, A, &O, dt, &B, &m->tendOld, nullptr, nullptr, hs, 2 * hn))) return r;
+  if (!wide && (r = exchange_state(m, B, !slow))) return r;
   // tend(new) = L(new); ip1 = <tend(old), tend(new)>, ip2 = <tend(new), tend(new)>
-  if ((r = stage(m, pass, MODE_S3A, B, nullptr, 0.0, nullptr, &m->tendNew, &m->tendOld, nullptr, defer_out))) return r;
+  if ((r = stage(m, pass, MODE_S3A, B, nullptr, 0.0, nullptr, Tn, &m->tendOld, nullptr, 0, 0, wide && m->fuse_push))) return r;
+  if (wide && m->p2p) m->need_fence = true;
   release_state(m, &B);
+  if (wide && !m->fuse_push) {   // NCCL, or a peer run whose band-edge rows are filtered rows
+    if ((r = join(m))) return r;
+    if ((r = exchange_tend3(m, Tn->U, Tn->V, slow ? nullptr : Tn->gd, HALO_S, HALO_N))) return r;
+  }
   if (defer_out) {
     // new = old + dt beta tend(new) is left to the next call: it needs the ghost rows of tend(new)
-    const State tv = {m->tendNew.U, m->tendNew.V, m->tendNew.gd};
-    if (!m->stage_pushed && (r = exchange_state(m, tv, !slow))) return r;
+    const State tv = {Tn->U, Tn->V, Tn->gd};
+    if (!wide && (r = exchange_state(m, tv, !slow))) return r;
     release_state(m, &A);
     out->base = O;
     if (!ownO) {  // the caller still owns in.base: take our own references
@@ -995,11 +1029,12 @@ static int predict_correct(gmd_model *m, double dts, const Carry &in, int pass, 
     out->deferred = true;
     out->dts = dts;
     out->with_gd = !slow;
+    out->L = Tn;
     return 0;
   }
   // new = old + dt beta tend(new)
-  if ((r = update(m, O, m->tendNew, dts, 1, 0.0, !slow, &A))) return r;
-  if ((r = exchange_state(m, A, !slow))) return r;
+  if ((r = update(m, O, *Tn, dts, 1, 0.0, !slow, &A, HALO_S * hs, HALO_N * hn))) return r;
+  if (!wide && (r = exchange_state(m, A, !slow))) return r;
   if (ownO) release_state(m, &M);
   out->base = A;
   out->deferred = false;
@@ -1208,6 +1243,7 @@ static int diag(gmd_model *m, const State &s, int advance) {
 // time_integrate (src/dycore_mod.F90:654-669) + time_advance + diag_run for ONE step; consumes m->cur
 static int one_step_body(gmd_model *m);
 static int one_step(gmd_model *m) {
+  for (int q = 0; q < 3; q++) std::sort(m->free_[q].begin(), m->free_[q].end());   // canonical pool order
   m->in_step = true;
   m->step_launch0 = m->launches;
   const int r = one_step_body(m);
@@ -1514,12 +1550,24 @@ int gmd_create(const gmd_config *cfg, gmd_model **out) {
     if (cfg->use_zonal_tend_filter)
       for (int k = 0; k < 20; k++)
         if (cfg->zonal_tend_filter_cutoff_wavenumber[k]) K = k + 1;
-    m->bs = (m->geo.r0 == 0) ? K + 2 : 2;
-    m->bn = (m->geo.r1 == nlat) ? K + 3 : 2;
+    m->bs = (m->geo.r0 == 0) ? K + 2 : 0;
+    m->bn = (m->geo.r1 == nlat) ? K + 3 : 0;
+    // wide-halo predict_correct: every band edge needs HALO_N plain rows (no filtered row, no pole row) on both sides
+    // -- the rows a neighbour recomputes / receives.  Decided from the configuration alone, so every rank agrees.
+    m->wide = cfg->nranks > 1 && cfg->uv_adv_scheme != GMD_ADV_WENO;
+    for (int q = 1; q < cfg->nranks && m->wide; q++) {
+      int e0, e1;
+      band_rows(nlat, cfg->nranks, cfg->polar_band_rows, q, &e0, &e1);   // edge between band q-1 and band q: row e0
+      for (int j = e0 - HALO_N; j < e0 + HALO_N; j++)
+        if (j < 1 || j > nlat - 2 || m->mesh.flag_full[(size_t)j] || m->mesh.flag_half[(size_t)j]) m->wide = false;
+      if (e1 - e0 < HALO_N) m->wide = false;
+    }
+    if (getenv("GMD_NO_WIDE")) m->wide = false;
     // single band: the split buys nothing (the one-wave interior launch owns every register file, so the polar-row
-    // CTAs cannot co-run; measured 4.80 vs 4.75 ms per step) -- it exists for the halo exchange of multi-band runs
-    m->split = cfg->nranks > 1;
-    if (const char *ev = getenv("GMD_NO_SPLIT")) m->split = atoi(ev) == 0;
+    // CTAs cannot co-run; measured 4.80 vs 4.75 ms per step); with several bands the two polar ranks split off the
+    // rows next to their pole, so that the polar-row kernel that follows them overlaps the rest of the sweep
+    m->split = m->wide && (m->bs + m->bn > 0);
+    if (const char *ev = getenv("GMD_NO_SPLIT")) m->split = (atoi(ev) == 0) && (cfg->nranks == 1 || m->wide);
     if (m->bs + m->bn >= m->nr) m->split = false;
     const int nstrips = (nlon + WOUT - 1) / WOUT;
     m->nbx = (nstrips + SW - 1) / SW;
@@ -1571,7 +1619,7 @@ int gmd_create(const gmd_config *cfg, gmd_model **out) {
   if (2 * (size_t)nlon * sizeof(double) > 200 * 1024) { fail(GMD_ERR_ARG, "num_lon too large for the polar-row kernel"); gmd_destroy(m); return GMD_ERR_ARG; }
   // persistent buffers
   if ((r = new_state(m, &m->cur, nullptr)) || (r = acquire(m, KIND_G, &m->ghs)) || (r = new_tend(m, &m->tendOld)) ||
-      (r = new_tend(m, &m->tendNew))) {
+      (r = new_tend(m, &m->tendNew)) || (cfg->nranks > 1 && (r = new_tend(m, &m->tendNew2)))) {
     gmd_destroy(m);
     return r;
   }
@@ -1661,11 +1709,10 @@ int gmd_peer_connect(gmd_model *m, const void *blobs, int nblobs) {
   if (nblobs != np) return fail(GMD_ERR_ARG, "%d blobs for %d ranks", nblobs, np);
   if (np > MAXR) return fail(GMD_ERR_ARG, "the peer-memory path serves up to %d ranks (one node); use gmd_comm_init", MAXR);
   if (m->p2p) return fail(GMD_ERR_STATE, "gmd_peer_connect called twice");
-  // A boundary CTA reads the neighbour-written ghost rows through the read-only path after acquiring the epoch, while
-  // interior CTAs of the same phase may already have read the last owned row: the two must never share a 32-byte L1
-  // sector, i.e. a row must be a whole number of sectors.
-  if (m->geo.nlon % 4)
-    return fail(GMD_ERR_ARG, "the peer-memory path needs num_lon to be a multiple of 4 (got %d); use gmd_comm_init", m->geo.nlon);
+  // No kernel reads a ghost row while a neighbour may be writing it: every wait for a neighbour (the inner-product
+  // all-reduce of predict_correct, k_halo_wait for the generic exchanges) completes in a launch BEFORE the one that
+  // reads the rows, so the read-only (ld.global.nc) path of the stage kernel only ever sees rows that are immutable
+  // for its lifetime.
   int r = set_dev(m);
   if (r) return r;
   if ((r = join(m))) return r;
@@ -1702,18 +1749,8 @@ int gmd_peer_connect(gmd_model *m, const void *blobs, int nblobs) {
   }
   m->p2p = true;
   m->xk = m->rk = m->xwaited = 0;
-  {
-    // the boundary stage launch may push the band-edge rows itself if none of them is a filtered row (those get
-    // their final values from the polar-row kernel, which runs after it)
-    auto plain = [&](int j) {
-      return j >= 1 && j <= m->geo.nlat - 2 && !m->mesh.flag_full[(size_t)j] && !m->mesh.flag_half[(size_t)j];
-    };
-    bool ok = m->split;
-    if (rank > 0) ok = ok && plain(m->geo.r0) && plain(m->geo.r0 + 1);
-    if (rank + 1 < np) ok = ok && plain(m->geo.r1 - 1);
-    if (getenv("GMD_NO_FUSED_PUSH")) ok = false;
-    m->fuse_push = ok;
-  }
+  // wide-halo predict_correct: the S3a launches store the band-edge rows of the new tendency themselves
+  m->fuse_push = m->wide && !getenv("GMD_NO_FUSED_PUSH");
   for (auto &g : m->graphs) cudaGraphExecDestroy(g.exec);
   m->graphs.clear();
   return 0;
@@ -1814,8 +1851,8 @@ int gmd_set_state(gmd_model *m, const double *u, const double *v, const double *
   }
   // iap_transform on owned + ghost rows inside the globe (src/types_mod.F90:399-426)
   Geo g = m->geo;
-  g.r0 = std::max(m->geo.r0 - 1, 0);
-  g.r1 = std::min(m->geo.r1 + 1, nlat);
+  g.r0 = std::max(m->geo.r0 - GHOST, 0);
+  g.r1 = std::min(m->geo.r1 + GHOST - 1, nlat);   // V of a row needs gd of the next one
   const ptrdiff_t sh = (ptrdiff_t)(g.r0 - m->geo.r0) * nlon;
   if (!m->dry) k_iap<<<m->ew_blocks, 256, 0, m->stream>>>(g, m->w_u + sh, m->w_v + sh, m->cur.gd + sh, m->cur.U + sh, m->cur.V + sh);
   if ((r = post_launch(m))) return r;
@@ -1855,7 +1892,14 @@ static int enqueue_steps(gmd_model *m, int nsteps) {
       if ((r = one_step(m))) return r;
       continue;
     }
-    const std::vector<double *> key = {m->cur.U, m->cur.V, m->cur.gd};
+    // the buffers a step uses follow from `cur`, the tendency parity and the free lists (public entry points other than
+    // gmd_step may have acquired / released buffers since the graph was captured): all of it is the key
+    for (int q = 0; q < 3; q++) std::sort(m->free_[q].begin(), m->free_[q].end());
+    std::vector<double *> key = {m->cur.U, m->cur.V, m->cur.gd, (double *)(uintptr_t)m->tn_idx, (double *)(uintptr_t)m->slab_next};
+    for (int q = 0; q < 3; q++) {
+      key.push_back(nullptr);
+      key.insert(key.end(), m->free_[q].begin(), m->free_[q].end());
+    }
     gmd_model::GraphEntry *hit = nullptr;
     for (auto &g : m->graphs)
       if (g.key == key) { hit = &g; break; }

@@ -24,7 +24,13 @@
 
 namespace gmd {
 
-constexpr int GHOST = 2;      // ghost rows on each side of a band
+constexpr int GHOST = 6;      // ghost rows on each side of a band
+// Wide halos (latitude bands): at the start of a predict_correct a band holds its state on
+// HALO_S rows beyond its southern and HALO_N rows beyond its northern edge; the three operator sweeps of the
+// predict_correct then run on rows that shrink by (1 south, 2 north) per sweep -- the stencil's reach -- so that the
+// bands exchange rows ONCE per predict_correct (the new tendency) instead of once per sweep.
+constexpr int HALO_S = 3, HALO_N = 6;
+static_assert(HALO_N <= GHOST && HALO_S <= GHOST, "ghost rows");
 typedef unsigned long long u64;
 
 // ---------------------------------------------------------------------------------------------------------
@@ -146,26 +152,24 @@ struct StageArgs {
   // row ranges of this launch, selected by blockIdx.z (boundary launches cover two disjoint ranges)
   int rb[2], re[2];
   int pofs[2];       // first partial slot of each range
-  // peer halo: the CTAs of range z wait for halo epoch page[SP_XBASE] + hwait_k from the south (hside[z] & 1) /
-  // north (hside[z] & 2) neighbour before their first load (their rows read ghost rows)
-  u64 *hpage;
-  unsigned hwait_k;
-  int hside[2];
-  // ... and, in the PUSH instantiations (boundary launches that produce the rows a neighbour needs), store the band-edge rows
-  // of the new state (S1, S2) or of the tendency (S3A) straight into the neighbours' ghost rows (pointers already
-  // shifted to this rank's row coordinates) and release halo epoch page[SP_XBASE] + hsig_k when the last CTA is done
-  // (PUSH instantiations only)
-  unsigned hsig_k;
+  // peer halo (the PUSH instantiations of MODE_S3A): rows j < push_s_end of the new tendency are also stored
+  // into the south neighbour's ghost rows, rows j >= push_n_begin into the north neighbour's (pointers already shifted
+  // to this rank's row coordinates, null = no neighbour).  The epoch that tells the neighbours the rows have landed
+  // is the one the inner-product all-reduce of the same predict_correct releases (reduce_pairs_body): every CTA
+  // fences its peer stores at system scope before it takes its ticket / before the kernel ends.
   double *hpS_U, *hpS_V, *hpS_G, *hpN_U, *hpN_V, *hpN_G;
-  u64 *hsigS, *hsigN;
+  int push_s_end, push_n_begin;
   // deferred update (LAZY variants of MODE_S1): the evaluated state is E = (EU,EV,Egd) + beta ldt (LU,LV,Lgd), the
   // last update_state of the previous predict_correct (src/dycore_mod.F90:786-790) folded into this sweep; E is
-  // also written out to (MU,MV,Mgd) on the rows of this CTA (and on the band's ghost rows by the edge CTAs)
+  // also written out to (MU,MV,Mgd) on the rows of this CTA; the first CTA of a range with medge[z] & 1 also writes
+  // the row below the range, the last CTA of a range with medge[z] & 2 the row above it (and gd of the next one):
+  // the rows of E the later sweeps of this predict_correct read beyond the rows evaluated here
   const double *LU, *LV, *Lgd;
   double *MU, *MV, *Mgd;
   const double *lip;
   double ldt;
   int lqcon;
+  int medge[2];
   Fold fold;   // MODE_S3A
   int tseq;    // timeline slot + 1 of the launch (GMD_TRACE builds), 0 = none
 };
@@ -350,6 +354,15 @@ __device__ __forceinline__ void st2(double *p, double x, double y) {
 #ifndef GMD_LAZY_MINB
 #define GMD_LAZY_MINB GMD_MINB
 #endif
+#ifndef GMD_S3A_MINB
+#define GMD_S3A_MINB GMD_MINB
+#endif
+#ifndef GMD_S3A_UNROLL
+#define GMD_S3A_UNROLL GMD_UNROLL
+#endif
+#ifndef GMD_ALL_MINB
+#define GMD_ALL_MINB GMD_MINB   // unsplit pass (advection + fast terms in one sweep): the widest register window
+#endif
 #define GMD_PRAGMA_(x) _Pragma(#x)
 #define GMD_UNROLL_PRAGMA(n) GMD_PRAGMA_(unroll n)
 // 2 a / b and sqrt(x) for the on-chip recomputation of u, v, sqrt(gd).  Strict build: IEEE division / sqrt.
@@ -502,29 +515,17 @@ constexpr int WOUT = 60;  // output columns per warp strip (64 held)
 constexpr int SW = 4;     // warps per CTA
 constexpr int BX = SW * 32;
 
-// end of a boundary launch that pushed halo rows: the last CTA to get here releases both neighbours
-__device__ __forceinline__ void stage_signal(const StageArgs &a) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence_system();
-    unsigned *ticket = reinterpret_cast<unsigned *>(a.hpage + SP_TICKET) + 1;  // slot 0 belongs to k_halo_push
-    const unsigned total = gridDim.x * gridDim.y * gridDim.z;
-    if (atomicAdd(ticket, 1u) == total - 1) {
-      *ticket = 0;
-      __threadfence_system();
-      const u64 ep = a.hpage[SP_XBASE] + a.hsig_k;
-      if (a.hsigS) st_release_sys(a.hsigS, ep);
-      if (a.hsigN) st_release_sys(a.hsigN, ep);
-    }
-  }
-}
-
 // LAZY: 0 = E is read as stored; 1 = E = base + beta ldt L (U, V and gd); 2 = the same for U, V only (the previous
 // predict_correct was a slow pass: gd unchanged)
-// PUSH: the boundary launches of a multi-rank run that produce rows a neighbour needs (a separate instantiation, so
-// that the row loop of the interior / single-GPU kernels keeps all of its registers)
+// PUSH (MODE_S3A of a multi-rank run): the band-edge rows of the tendency also go to the neighbours (a separate
+// instantiation, so that the row loop of the single-GPU kernels keeps all of its registers)
+// resident CTAs per SM the register allocation is capped for
+template <int PASS, int MODE, int LAZY>
+constexpr int stage_minb() {
+  return PASS == 0 /* PASS_ALL */ ? GMD_ALL_MINB : (LAZY ? GMD_LAZY_MINB : (MODE == 2 /* MODE_S3A */ ? GMD_S3A_MINB : GMD_MINB));
+}
 template <int PASS, int ADV, int MODE, int LAZY = 0, bool PUSH = false>
-__global__ void __launch_bounds__(BX, (LAZY ? GMD_LAZY_MINB : GMD_MINB)) k_stage(const StageArgs a) {
+__global__ void __launch_bounds__(BX, (stage_minb<PASS, MODE, LAZY>())) k_stage(const StageArgs a) {
   __shared__ double red[2 * SW];
   extern __shared__ double srow[];  // row records of rows ja-1 .. jb: [(jb - ja + 2)][RC_N]
   const int nlon = a.g.nlon, nlat = a.g.nlat, r0 = a.g.r0;
@@ -543,7 +544,6 @@ __global__ void __launch_bounds__(BX, (LAZY ? GMD_LAZY_MINB : GMD_MINB)) k_stage
     if (MODE == MODE_S3A && a.fold.ticket)
       fold_tail<BX>(a.fold.ticket, a.fold.total, a.partials, a.fold.n, a.fold.out, a.fold.r.page, a.fold.r.rank, a.fold.r.nranks,
                     a.fold.r.k, a.tseq);
-    if (PUSH) stage_signal(a);
     trace_out(a.tseq);
     return;
   }
@@ -554,16 +554,6 @@ __global__ void __launch_bounds__(BX, (LAZY ? GMD_LAZY_MINB : GMD_MINB)) k_stage
     const int nrec = (jb - ja + 2) * RC_N;
     const double *__restrict__ src = a.t.rowrec + (ptrdiff_t)(ja - 1) * RC_N;
     for (int k = threadIdx.x; k < nrec; k += BX) srow[k] = __ldg(src + k);
-  }
-  if (a.hpage != nullptr && threadIdx.x == 0) {
-    const int hs = a.hside[blockIdx.z];
-    if (hs) {
-      const u64 want = a.hpage[SP_XBASE] + a.hwait_k;
-      GMD_TRACE_T0();
-      if (hs & 1) spin_until(a.hpage + SP_SIG, want, a.hpage);
-      if (hs & 2) spin_until(a.hpage + SP_SIG + 1, want, a.hpage);
-      GMD_TRACE_WAIT(a.tseq);
-    }
   }
   __syncthreads();
 
@@ -582,7 +572,8 @@ __global__ void __launch_bounds__(BX, (LAZY ? GMD_LAZY_MINB : GMD_MINB)) k_stage
     //      this CTA is responsible for (its own rows; the band's ghost rows for the CTAs at the band edges)
     double bdt = 0.0;
     if (LAZY) bdt = a.ldt * beta_from_ip(a.lip, a.lqcon);
-    const bool edgeS = LAZY && (ja == r0) && (r0 > 0), edgeN = LAZY && (jb == a.g.r1) && (a.g.r1 < nlat);
+    const bool edgeS = LAZY && (ja == a.rb[blockIdx.z]) && (a.medge[blockIdx.z] & 1);
+    const bool edgeN = LAZY && (jb == a.re[blockIdx.z]) && (a.medge[blockIdx.z] & 2);
     auto mineUV = [&](int r) { return (r >= ja && r < jb) || (edgeS && r == ja - 1) || (edgeN && r == jb); };
     auto mineG = [&](int r) { return (r >= ja && r < jb) || (edgeS && r == ja - 1) || (edgeN && (r == jb || r == jb + 1)); };
     auto combU = [&](D2 b, D2 t, int r) -> D2 {
@@ -687,7 +678,7 @@ __global__ void __launch_bounds__(BX, (LAZY ? GMD_LAZY_MINB : GMD_MINB)) k_stage
 
     // measured on B200 (tools/tune_stage.py): the deferred-update variants and S2 are fastest without unrolling (no
     // spills at the 128-register cap), S1 / S3a with two rows per trip
-    constexpr int kUnroll = LAZY ? GMD_LAZY_UNROLL : (MODE == MODE_S2 ? 1 : GMD_UNROLL);
+    constexpr int kUnroll = LAZY ? GMD_LAZY_UNROLL : (MODE == MODE_S2 ? 1 : (MODE == MODE_S3A ? GMD_S3A_UNROLL : GMD_UNROLL));
 #pragma unroll kUnroll
     for (int j = ja; j < jb; j++) {
       // ---- issue every load of this iteration first: the next row of the evaluated state (consumed one
@@ -863,28 +854,18 @@ __global__ void __launch_bounds__(BX, (LAZY ? GMD_LAZY_MINB : GMD_MINB)) k_stage
           }
         }
       }
-      // ---- band-edge rows straight into the neighbours' ghost rows (south: U, V, gd of row r0 and gd of row r0+1;
-      //      north: U, V, gd of row r1-1); these rows are never filtered rows (checked by gmd_peer_connect)
-      if (PUSH && MODE != MODE_EVAL && out) {
-        const bool ps0 = (j == r0) && (a.hpS_U != nullptr), ps1 = (j == r0 + 1) && (a.hpS_U != nullptr);
-        const bool pn0 = (j == a.g.r1 - 1) && (a.hpN_U != nullptr);
-        if (ps0 || ps1 || pn0) {
-          const bool tend = (MODE == MODE_S3A);
-          const double xu0 = tend ? dUa : oU.x + a.dt * dUa, xu1 = tend ? dUb : oU.y + a.dt * dUb;
-          const double xv0 = tend ? dVa : oV.x + a.dt * dVa, xv1 = tend ? dVb : oV.y + a.dt * dVb;
-          const double xg0 = tend ? dGa : oG.x + a.dt * dGa, xg1 = tend ? dGb : oG.y + a.dt * dGb;
-          if (ps0) {
-            st2(AT(a.hpS_U, j), xu0, xu1);
-            st2(AT(a.hpS_V, j), xv0, xv1);
-          }
-          if (pn0) {
-            st2(AT(a.hpN_U, j), xu0, xu1);
-            st2(AT(a.hpN_V, j), xv0, xv1);
-          }
-          if (rowG) {
-            if (ps0 || ps1) st2(AT(a.hpS_G, j), xg0, xg1);
-            if (pn0) st2(AT(a.hpN_G, j), xg0, xg1);
-          }
+      // ---- band-edge rows of the tendency straight into the neighbours' ghost rows (the lowest HALO_N rows go south,
+      //      the highest HALO_S rows north); these rows are never filtered rows (checked by gmd_peer_connect)
+      if (PUSH && MODE == MODE_S3A && out) {
+        if (j < a.push_s_end && a.hpS_U != nullptr) {
+          st2(AT(a.hpS_U, j), dUa, dUb);
+          st2(AT(a.hpS_V, j), dVa, dVb);
+          if (rowG) st2(AT(a.hpS_G, j), dGa, dGb);
+        }
+        if (j >= a.push_n_begin && a.hpN_U != nullptr) {
+          st2(AT(a.hpN_U, j), dUa, dUb);
+          st2(AT(a.hpN_V, j), dVa, dVb);
+          if (rowG) st2(AT(a.hpN_G, j), dGa, dGb);
         }
       }
       // ---- rotate the window ------------------------------------------------------------------------------
@@ -924,12 +905,14 @@ __global__ void __launch_bounds__(BX, (LAZY ? GMD_LAZY_MINB : GMD_MINB)) k_stage
       const size_t b = (size_t)a.pofs[blockIdx.z] + (size_t)blockIdx.y * gridDim.x + blockIdx.x;
       a.partials[2 * b] = q1;
       a.partials[2 * b + 1] = q2;
+      // this CTA's peer stores (all issued before the barrier above) must be visible to the neighbours before the ticket
+      // below / the end of the kernel lets the reduction release them; CTAs that pushed nothing skip the (slow) fence
+      if (PUSH && ((a.hpS_U != nullptr && ja < a.push_s_end) || (a.hpN_U != nullptr && jb > a.push_n_begin))) __threadfence_system();
     }
     if (a.fold.ticket)
       fold_tail<BX>(a.fold.ticket, a.fold.total, a.partials, a.fold.n, a.fold.out, a.fold.r.page, a.fold.r.rank, a.fold.r.nranks,
                     a.fold.r.k, a.tseq);
   }
-  if (PUSH) stage_signal(a);
   trace_out(a.tseq);
 }
 
@@ -1484,9 +1467,11 @@ __global__ void __launch_bounds__(256) k_update(const UpdateArgs a) {
 #pragma unroll
   for (int z = 0; z < 2; z++) {
     if (a.rb[z] >= a.re[z]) continue;
-    const ptrdiff_t k0 = (ptrdiff_t)(a.rb[z] - a.g.r0) * nlon, k1 = (ptrdiff_t)(a.re[z] - a.g.r0) * nlon;
-    for (ptrdiff_t k = k0 + (ptrdiff_t)blockIdx.x * 256 + threadIdx.x; k < k1; k += (ptrdiff_t)gridDim.x * 256) {
-      const int j = a.g.r0 + (int)(k / (ptrdiff_t)nlon);
+    // rows may lie south of the band (ghost rows): count from the first row of the range, not from r0
+    const ptrdiff_t k0 = (ptrdiff_t)(a.rb[z] - a.g.r0) * nlon, kn = (ptrdiff_t)(a.re[z] - a.rb[z]) * nlon;
+    for (ptrdiff_t q = (ptrdiff_t)blockIdx.x * 256 + threadIdx.x; q < kn; q += (ptrdiff_t)gridDim.x * 256) {
+      const ptrdiff_t k = k0 + q;
+      const int j = a.rb[z] + (int)(q / (ptrdiff_t)nlon);
       if (j >= 1 && j <= nlat - 2) a.NU[k] = a.OU[k] + dt * a.TU[k];
       else a.NU[k] = a.OU[k];
       if (j <= nlat - 2) a.NV[k] = a.OV[k] + dt * a.TV[k];

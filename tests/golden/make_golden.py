@@ -43,6 +43,10 @@ CASES = {
     "mz_48x25_weno": (dict(num_lon=48, num_lat=25, time_step_size=600.0, subcycles=4, split_scheme="csp2",
                            uv_adv_scheme="weno", zonal_tend_filter_cutoff_wavenumber=[4, 4]),
                       "mountain_zonal_flow", 3),
+    # order-4 diffusion (two Laplacian passes, src/diffusion_mod.F90:107,172-179), unsplit
+    "mz_60x32_diff4": (dict(num_lon=60, num_lat=32, time_step_size=600.0, split_scheme="none", use_diffusion=True,
+                            diffusion_order=4, diffusion_coef=1.0e15, zonal_tend_filter_cutoff_wavenumber=[4, 4]),
+                       "mountain_zonal_flow", 4),
 }
 
 
@@ -90,10 +94,14 @@ def make_case(name, kw, test_case, nsteps):
 
 
 if __name__ == "__main__":
-    make_jet_profile()
+    only = sys.argv[1:]
+    if not only:
+        make_jet_profile()
     # NB: a Rossby-Haurwitz wave (R=4) must not be combined with a cutoff < 4: the filtered dv row is
     # then orthogonal to V (pure sin 4 lambda), s2 is rounding noise and s1/s2 blows up -- that is the
     # reference's own behaviour (dycore_mod.F90:229-234), not something a fixture should pin.
     for name, (kw, tc, n) in CASES.items():
+        if only and name not in only:
+            continue
         make_case(name, kw, tc, n)
         print("wrote", name)

@@ -70,7 +70,13 @@ def main():
     if shared and mode == "nccl":
         raise SystemExit("the NCCL path needs one GPU per rank")
     ok, report = True, []
-    for tc, kw, nsteps in CASES:
+    only = os.environ.get("GMD_CASES")   # e.g. "3,5": run only these cases (debugging aid)
+    cases = [c for k, c in enumerate(CASES) if only is None or str(k) in only.split(",")]
+    override = json.loads(os.environ.get("GMD_KW", "{}"))   # debugging aid: config keys to override, "nsteps" too
+    for tc, kw, nsteps in cases:
+        kw = dict(kw)
+        kw.update({k: v for k, v in override.items() if k != "nsteps"})
+        nsteps = override.get("nsteps", nsteps)
         o = Oracle(OracleConfig(**kw))
         o.set_initial_condition(tc)
         u, v, gd = o.state()

@@ -6,7 +6,8 @@ oracle/gmd_oracle.c (1-based loops over halo-padded arrays) so that a transcript
 shows up as a disagreement.  The zonal filter uses ``numpy.fft`` instead of the FFTPACK restatement.
 
 Reference anchors: src/dycore_mod.F90:184-792, src/types_mod.F90:347-426, src/filter_mod.F90:35-167,
-src/diffusion_mod.F90:74-217, src/diag_mod.F90:42-121, src/mesh_mod.F90:44-114, src/data_mod.F90:26-47.
+src/diffusion_mod.F90:74-217, src/diag_mod.F90:42-121, src/mesh_mod.F90:44-114, src/data_mod.F90:26-47,
+src/weno_mod.F90:69-300 (WENO advection), src/dycore_mod.F90:689-752 (isp splitting).
 """
 from __future__ import annotations
 
@@ -160,6 +161,8 @@ class NpModel:
                 Vn, Vs = Vp[2:], Vp[:-2]
                 vat = 0.25 / self.dlat_h[:, None] * (v2 * (V + Vn) - bt * np.abs(v2) * (Vn - V) - v1 * (V + Vs)
                                                      + bt * np.abs(v1) * (V - Vs) - (v2 - v1) * V)
+            elif self.adv == "weno":
+                ual, val, uat, vat = self.weno_advection(u, v, U, V)
             else:
                 raise NotImplementedError(self.adv)
             du[J] += -ual - uat
@@ -191,6 +194,63 @@ class NpModel:
             self.smooth(dgd, gd + self.ghs, self.full_cut)
         return du, dv, dgd
 
+    # ------------------------------------------------------------------ WENO advection (src/weno_mod.F90:69-300)
+    @staticmethod
+    def _weno2(fp1, fp2, fp3, fn2, fn3, fn4):
+        """weno_2nd_order_pass (:235-298): two 2-point stencils per side, optimal weights 1/3, 2/3, eps 1e-6"""
+        eps = 1.0e-6
+        a1, a2 = (1.0 / 3.0) / (eps + (fp2 - fp1) ** 2) ** 2, (2.0 / 3.0) / (eps + (fp3 - fp2) ** 2) ** 2
+        f = (a1 * (-0.5 * fp1 + 1.5 * fp2) + a2 * (0.5 * fp2 + 0.5 * fp3)) / (a1 + a2)
+        b1, b2 = (1.0 / 3.0) / (eps + (fn3 - fn4) ** 2) ** 2, (2.0 / 3.0) / (eps + (fn2 - fn3) ** 2) ** 2
+        return f + (b1 * (-0.5 * fn4 + 1.5 * fn3) + b2 * (0.5 * fn3 + 0.5 * fn2)) / (b1 + b2)
+
+    def weno_advection(self, u, v, U, V):
+        """returns (u_adv_lon[J], v_adv_lon, u_adv_lat[J], v_adv_lat); Lax-Friedrichs split with a fixed 20 m/s.
+        Work-array rows the reference never writes (pole rows of the u-point arrays, latitude halos) read as 0."""
+        nlat = self.nlat
+        J = slice(1, nlat - 1)
+        amax = 20.0
+        zf, zh = np.zeros_like(U), np.zeros_like(V)
+
+        def rows(a, shift, lo, hi):
+            """a[row + shift] with zeros outside rows [lo, hi]"""
+            out = np.zeros_like(a)
+            n = a.shape[0]
+            for r in range(n):
+                q = r + shift
+                if lo <= q <= hi:
+                    out[r] = a[q]
+            return out
+        # ---- zonal (:69-158)
+        fpu, fnu = zf.copy(), zf.copy()
+        fpu[J] = 0.5 * (u[J] + amax) * U[J]
+        fnu[J] = 0.5 * (u[J] - amax) * U[J]
+        ub = 0.25 * (W(u)[:-1] + W(u)[1:] + u[:-1] + u[1:])
+        fpv, fnv = 0.5 * (ub + amax) * V, 0.5 * (ub - amax) * V
+        fu = zf.copy()
+        fu[J] = self._weno2(W(fpu), fpu, E(fpu), fnu, E(fnu), E(E(fnu)))[J]
+        fv = self._weno2(W(fpv), fpv, E(fpv), fnv, E(fnv), E(E(fnv)))
+        # B8: the u-row metric is half_dlon(j), sic (:153-154)
+        ual = ((fu - W(fu) - (E(u) - W(u)) * U * 0.25)[J]) / self.dlon_h[1: nlat - 1, None]
+        val = (fv - W(fv) - (u[:-1] + u[1:] - W(u)[:-1] - W(u)[1:]) * V * 0.25) / self.dlon_h[:, None]
+        # ---- meridional (:160-233)
+        nh = nlat - 1
+        vp = self._padrows(v)                      # vp[h + 1] = v[h]
+        vb = 0.25 * (vp[:-1] + vp[1:] + E(vp)[:-1] + E(vp)[1:])     # at full row j: half rows j-1, j
+        fpu, fnu = zf.copy(), zf.copy()
+        fpu[J] = 0.5 * (vb[J] + amax) * U[J]
+        fnu[J] = 0.5 * (vb[J] - amax) * U[J]
+        fpv, fnv = 0.5 * (v + amax) * V, 0.5 * (v - amax) * V
+        fu = zf.copy()
+        fu[J] = self._weno2(rows(fpu, -1, 1, nlat - 2), fpu, rows(fpu, 1, 1, nlat - 2), fnu, rows(fnu, 1, 1, nlat - 2),
+                            rows(fnu, 2, 1, nlat - 2))[J]
+        fv = self._weno2(rows(fpv, -1, 0, nh - 1), fpv, rows(fpv, 1, 0, nh - 1), fnv, rows(fnv, 1, 0, nh - 1),
+                         rows(fnv, 2, 0, nh - 1))
+        dv_u = (W(vp)[1:] + vp[1:] - W(vp)[:-1] - vp[:-1])          # at full row j: v(i-1,j)+v(i,j)-v(i-1,j-1)-v(i,j-1)
+        uat = ((fu - rows(fu, -1, 1, nlat - 2) - dv_u * U * 0.25)[J]) / self.dlat_f[J, None]
+        vat = (fv - rows(fv, -1, 0, nh - 1) - (vp[2:] - vp[:-2]) * V * 0.25) / self.dlat_h[:, None]
+        return ual, val, uat, vat
+
     def update(self, dt, td, old):
         du, dv, dgd = td
         u0, v0, gd0, U0, V0, s0 = old
@@ -217,9 +277,62 @@ class NpModel:
         self.beta = ip1 / ip2 if (self.qcon and ip1 != 0.0 and ip2 != 0.0) else 1.0
         return self.update(dt * self.beta, t_new, old)
 
+    def inner_state(self, t, st):
+        """inner_product_tend_state (src/types_mod.F90:373-397): (du, U), (dv, V), (dgd, gd)"""
+        return self.inner(t, (st[3], st[4], st[2]))
+
+    def isp(self, F):
+        """isp_splitting (src/dycore_mod.F90:689-752)"""
+        S, dt = self.S, self.dt
+        fast_dt, half_dt = dt / S, dt * 0.5
+        add = lambda a, b: tuple(x + y for x, y in zip(a, b))
+        slow = self.tend(F, "slow")
+        acc = tuple(np.zeros_like(x) for x in slow)
+        P = F
+        for _ in range(S):
+            t = add(self.tend(P, "fast"), slow)
+            P1 = self.update(fast_dt * 0.5, t, P)
+            t = add(self.tend(P1, "fast"), slow)
+            P2 = self.update(fast_dt * 0.5, t, P)
+            t2 = self.tend(P2, "fast")
+            acc = add(acc, t2)
+            P = self.update(fast_dt, add(t2, slow), P)
+        acc = tuple(x * (2.0 / S) for x in acc)
+        sub = lambda a, b: tuple(x - y for x, y in zip(a, b))
+        Q1 = self.update(half_dt, sub(self.tend(P, "slow"), slow), P)
+        Q2 = self.update(half_dt, sub(self.tend(Q1, "slow"), slow), P)
+        R = add(add(self.tend(Q2, "slow"), slow), acc)
+        ip1, ip2 = self.inner_state(R, F), self.inner(R, R)
+        beta = ip1 / ip2 if (self.qcon and ip1 != 0.0 and ip2 != 0.0) else 1.0
+        self.beta = beta * 4.0 / dt
+        return self.update(half_dt * self.beta, R, F)
+
     def diffusion(self, dt, st):
-        assert self.diffusion_order == 2
+        """ordinary_diffusion (src/diffusion_mod.F90:74-217), order 2 or 4"""
         u, v, gd, U, V, s = st
+        if self.diffusion_order == 2:
+            gdd, ud, vd = self._laplace(gd, u, v)
+            sign = 1.0
+        else:
+            assert self.diffusion_order == 4
+            g1, u1, v1 = self._laplace(gd, u, v)
+            gdd, ud, vd = self._laplace(g1, u1, v1)   # the work copies become the first Laplacian (:172-179)
+            sign = -1.0
+        nlat = self.nlat
+        for j, c in self.full_cut.items():
+            if 1 <= j <= nlat - 2:
+                gdd[j] = self.filt(gdd[j], c)
+                ud[j] = self.filt(ud[j], c)
+        for h, c in self.half_cut.items():
+            vd[h] = self.filt(vd[h], c)
+        gd = gd + sign * dt * self.nu * gdd
+        u = u + sign * dt * self.nu * ud
+        v = v + sign * dt * self.nu * vd
+        U, V, s = self.iap(u, v, gd)
+        return u, v, gd, U, V, s
+
+    def _laplace(self, gd, u, v):
+        """one scalar-Laplacian pass on gd, u, v (src/diffusion_mod.F90:107-171)"""
         nlat, nlon = self.nlat, self.nlon
         ch, cf = self.ch, self.cf
         J = slice(1, nlat - 1)
@@ -237,20 +350,12 @@ class NpModel:
         vd[1:-1] += ((v[2:] - v[1:-1]) * cf[2:-1, None] - (v[1:-1] - v[:-2]) * cf[1:-2, None]) / self.dlat_h[1:-1, None] ** 2 * ch[1:-1, None]
         vd[0] += (v[1] - v[0]) * cf[1] / self.dlat_h[0] ** 2 * ch[0]
         vd[-1] -= (v[-1] - v[-2]) * cf[-2] / self.dlat_h[-1] ** 2 * ch[-1]
-        for j, c in self.full_cut.items():
-            if 1 <= j <= nlat - 2:
-                gdd[j] = self.filt(gdd[j], c)
-                ud[j] = self.filt(ud[j], c)
-        for h, c in self.half_cut.items():
-            vd[h] = self.filt(vd[h], c)
-        gd = gd + dt * self.nu * gdd
-        u = u + dt * self.nu * ud
-        v = v + dt * self.nu * vd
-        U, V, s = self.iap(u, v, gd)
-        return u, v, gd, U, V, s
+        return gdd, ud, vd
 
     def step(self, st):
-        if self.split == "csp2":
+        if self.split == "isp":
+            new = self.isp(st)
+        elif self.split == "csp2":
             st1 = self.predict_correct(0.5 * self.dt, st, "slow")
             for _ in range(self.S):
                 st1 = self.predict_correct(self.dt / self.S, st1, "fast")

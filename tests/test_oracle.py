@@ -96,7 +96,7 @@ def test_filter_row_map_and_projection():
 
 
 # ------------------------------------------------------------------------------------------- operators
-@pytest.mark.parametrize("adv", ["center_diff", "upwind"])
+@pytest.mark.parametrize("adv", ["center_diff", "upwind", "weno"])
 @pytest.mark.parametrize("pass_", ["all", "fast", "slow"])
 def test_space_operators_match_numpy(adv, pass_):
     nlon, nlat = 72, 37
@@ -155,6 +155,71 @@ def test_step_matches_numpy(case, adv, diff):
     assert rel(ou, st[0]) < 1e-12 and rel(ogd, st[2]) < 1e-12
     assert np.abs(ov - st[1]).max() < 1e-11 * max(1.0, np.abs(ou).max())
     assert abs(o.diag()[2] - npm.beta) < 1e-12
+
+
+def test_weno_step_matches_numpy():
+    """WENO advection (src/weno_mod.F90:69-300) through whole csp2 steps, second reading in tests/np_restatement.py"""
+    nlon, nlat = 96, 49
+    cfg = OracleConfig(num_lon=nlon, num_lat=nlat, time_step_size=600, subcycles=4, uv_adv_scheme="weno",
+                       zonal_tend_filter_cutoff_wavenumber=[4, 4])
+    o = Oracle(cfg)
+    o.set_initial_condition("mountain_zonal_flow")
+    u, v, gd = o.state()
+    ghs = o.ghs()
+    o.run_init()
+    npm = NpModel(nlon, nlat, 600, 4, adv="weno", cutoff=[4, 4])
+    npm.ghs = ghs
+    st = npm.make_state(u, v, gd)
+    for _ in range(3):
+        o.step(1)
+        st = npm.step(st)
+    ou, ov, ogd = o.state()
+    assert rel(ou, st[0]) < 1e-12 and rel(ogd, st[2]) < 1e-12
+    assert np.abs(ov - st[1]).max() < 1e-11 * max(1.0, np.abs(ou).max())
+    assert abs(o.diag()[2] - npm.beta) < 1e-12
+
+
+@pytest.mark.parametrize("case", ["steady_geostrophic_flow", "mountain_zonal_flow"])
+def test_isp_step_matches_numpy(case):
+    """isp_splitting (src/dycore_mod.F90:689-752) incl. its beta * 4 / dt, second reading in tests/np_restatement.py"""
+    nlon, nlat = 96, 49
+    cfg = OracleConfig(num_lon=nlon, num_lat=nlat, time_step_size=600, subcycles=4, split_scheme="isp",
+                       zonal_tend_filter_cutoff_wavenumber=[3, 3])
+    o = Oracle(cfg)
+    o.set_initial_condition(case)
+    u, v, gd = o.state()
+    ghs = o.ghs()
+    o.run_init()
+    npm = NpModel(nlon, nlat, 600, 4, split="isp", cutoff=[3, 3])
+    npm.ghs = ghs
+    st = npm.make_state(u, v, gd)
+    for _ in range(2):
+        o.step(1)
+        st = npm.step(st)
+    ou, ov, ogd = o.state()
+    assert rel(ou, st[0]) < 1e-12 and rel(ogd, st[2]) < 1e-12
+    assert np.abs(ov - st[1]).max() < 1e-11 * max(1.0, np.abs(ou).max())
+    assert abs(o.diag()[2] / npm.beta - 1) < 1e-10
+
+
+@pytest.mark.parametrize("order,coef", [(2, 1.0e5), (4, 1.0e15)])
+def test_diffusion_matches_numpy(order, coef):
+    """ordinary_diffusion alone (src/diffusion_mod.F90:74-217), order 2 and order 4 (two Laplacian passes, sign -1)"""
+    nlon, nlat = 72, 37
+    u, v, gd, ghs = generic_state(nlon, nlat, seed=7)
+    cfg = OracleConfig(num_lon=nlon, num_lat=nlat, time_step_size=600, use_diffusion=True, diffusion_order=order,
+                       diffusion_coef=coef, zonal_tend_filter_cutoff_wavenumber=[4, 3])
+    o = Oracle(cfg)
+    o.set_state(u, v, gd, ghs)
+    o.run_init()
+    npm = NpModel(nlon, nlat, 600, cutoff=[4, 3], use_diffusion=True, diffusion_order=order, diffusion_coef=coef)
+    npm.ghs = ghs
+    st = npm.diffusion(600.0, npm.make_state(u, v, gd))
+    o.ordinary_diffusion(600.0)
+    got = o.state()
+    for x, y, x0 in zip(got, st[:3], (u, v, gd)):
+        assert rel(x - x0, y - x0) < 1e-11, order     # the increment itself, not the state it is added to
+        assert rel(x, y) < 1e-14
 
 
 def test_unsplit_step_matches_numpy():
