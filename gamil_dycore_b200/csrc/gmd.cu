@@ -155,6 +155,7 @@ struct gmd_model {
 
   // stage launch geometry
   int nbx = 0, nchunks = 0, rows_per_cta = 0;
+  int rows_per_cta_s3a = 0;   // S3a launches: their own one-wave geometry (the S3a kernels may be capped at fewer CTAs per SM)
   size_t stage_smem = 0;  // dynamic shared memory of k_stage: (rows_per_cta + 2) row records
   // boundary / interior split: rows [r0, r0+bs) and [r1-bn, r1) are evaluated first on the
   // main stream, followed by the polar-row kernel and the halo exchange, while rows [r0+bs, r1-bn) run on stream2
@@ -841,7 +842,9 @@ static int stage(gmd_model *m, int pass, int mode, const State &E, const State *
   const bool split = use_split(m);
   // launch geometry
   const int I0 = split ? (poleS ? r0 + m->bs : R0) : R0, I1 = split ? (poleN ? r1 - m->bn : R1) : R1;
-  const int nci = (I1 - I0 + m->rows_per_cta - 1) / m->rows_per_cta;
+  const int rpc = (mode == MODE_S3A) ? m->rows_per_cta_s3a : m->rows_per_cta;
+  const size_t smem_i = (size_t)(rpc + 2) * RC_N * sizeof(double);
+  const int nci = (I1 - I0 + rpc - 1) / rpc;
   const int ncb = split ? m->nchunks_b : 0;
   const int nst = 2 * m->nbx * ncb + m->nbx * nci;
   if (fold) {  // one partial pair and one ticket per CTA of the stage launch(es) and of the polar-row launch
@@ -872,24 +875,24 @@ static int stage(gmd_model *m, int pass, int mode, const State &E, const State *
       CK(cudaEventRecord(e, m->stream));
       m->ev_polar_side = e;
     }
-    a.rows_per_cta = m->rows_per_cta;
+    a.rows_per_cta = rpc;
     a.rb[0] = I0; a.re[0] = I1; a.pofs[0] = 2 * m->nbx * ncb;
     a.medge[0] = edges & ((poleS ? 0 : 1) | (poleN ? 0 : 2));
     dim3 gi((unsigned)m->nbx, (unsigned)nci, 1);
     static const char *const inames[4] = {"k_stage.S1.interior", "k_stage.S2.interior", "k_stage.S3a.interior", "k_stage.eval.interior"};
     a.tseq = tseq(m, inames[mode]);
-    if (!m->dry) fn<<<gi, BX, m->stage_smem, m->stream2>>>(a);
+    if (!m->dry) fn<<<gi, BX, smem_i, m->stream2>>>(a);
     if ((r = post_launch(m))) return r;
     if ((r = split_end(m))) return r;
   } else {
     if ((r = join(m))) return r;
-    a.rows_per_cta = m->rows_per_cta;
+    a.rows_per_cta = rpc;
     a.rb[0] = R0; a.re[0] = R1; a.pofs[0] = 0;
     a.medge[0] = edges;
     dim3 grid((unsigned)m->nbx, (unsigned)nci, 1);
     static const char *const wnames[4] = {"k_stage.S1", "k_stage.S2", "k_stage.S3a", "k_stage.eval"};
     a.tseq = tseq(m, wnames[mode]);
-    if (!m->dry) fn<<<grid, BX, m->stage_smem, m->stream>>>(a);
+    if (!m->dry) fn<<<grid, BX, smem_i, m->stream>>>(a);
     if ((r = post_launch(m))) return r;
   }
 
@@ -1587,6 +1590,16 @@ int gmd_create(const gmd_config *cfg, gmd_model **out) {
     m->nchunks = (m->nr + m->rows_per_cta - 1) / m->rows_per_cta;
     m->nchunks_i = (rows_i + m->rows_per_cta - 1) / m->rows_per_cta;
     m->stage_smem = (size_t)(m->rows_per_cta + 2) * RC_N * sizeof(double);
+    {   // S3a geometry from the occupancy of the S3a kernel itself
+      int ps = 0;
+      CKD(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ps, pick_stage(pass0, cfg->uv_adv_scheme, MODE_S3A), BX,
+                                                        (size_t)(64 + 2) * RC_N * sizeof(double)));
+      ps = std::max(ps, 1);
+      if (const char *ev = getenv("GMD_CTAS_PER_SM")) ps = std::max(1, atoi(ev));
+      const int want3 = std::max(1, nsm * ps / m->nbx);
+      m->rows_per_cta_s3a = std::min(max_rows, std::max(8, (rows_i + want3 - 1) / want3));
+      if (const char *ev = getenv("GMD_ROWS_PER_CTA")) m->rows_per_cta_s3a = std::min(max_rows, std::max(1, atoi(ev)));
+    }
     // boundary chunks: long while the interior launch hides them, short once the boundary -> polar rows -> next
     // boundary chain is what a phase waits for (measured at 900 and 225 rows per rank)
     m->rows_per_cta_b = (m->nr >= 600) ? 6 : 3;
@@ -1599,7 +1612,11 @@ int gmd_create(const gmd_config *cfg, gmd_model **out) {
   }
   const size_t total = (size_t)m->nr * nlon;
   m->ew_blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)nsm * 8);
-  m->n_partials = std::max(m->nbx * (m->nchunks + 2 * m->nchunks_b + m->nchunks_i) + m->n_items[0] + m->n_items[1], m->ew_blocks) + 16;
+  {
+    const int rmin = std::max(1, std::min(m->rows_per_cta, m->rows_per_cta_s3a));
+    const int cmax = (m->nr + rmin - 1) / rmin + 2;
+    m->n_partials = std::max(m->nbx * (2 * cmax + 2 * m->nchunks_b) + m->n_items[0] + m->n_items[1], m->ew_blocks) + 16;
+  }
   CKD(cudaMalloc(&m->d_partials, (size_t)m->n_partials * 2 * sizeof(double)));
   CKD(cudaMalloc(&m->d_ip, 8 * sizeof(double)));
   CKD(cudaMemset(m->d_ip, 0, 8 * sizeof(double)));
@@ -2300,10 +2317,11 @@ static int time_stage(gmd_model *m, int pass, int mode, int reps, float *ms_per_
   a.beta_lon = m->cfg.uv_adv_upwind_lon_beta; a.beta_lat = m->cfg.uv_adv_upwind_lat_beta;
   a.AUlon = m->w_alon_u; a.AUlat = m->w_alat_u; a.AVlon = m->w_alon_v; a.AVlat = m->w_alat_v;
   a.partials = m->d_partials;
-  a.rows_per_cta = m->rows_per_cta;
+  const int rpc = (mode == MODE_S3A) ? m->rows_per_cta_s3a : m->rows_per_cta;
+  a.rows_per_cta = rpc;
   a.rb[0] = m->geo.r0; a.re[0] = m->geo.r1; a.pofs[0] = 0;
   if ((r = join(m))) return r;
-  dim3 grid((unsigned)m->nbx, (unsigned)m->nchunks, 1);
+  dim3 grid((unsigned)m->nbx, (unsigned)((m->nr + rpc - 1) / rpc), 1);
   stage_fn fn = pick_stage(pass, m->cfg.uv_adv_scheme, mode);
   if (mode == 4) {  // MODE_S1 with the deferred update folded in: E = cur + beta dt tendNew -> A (= M), N = B
     a.LU = m->tendNew.U; a.LV = m->tendNew.V; a.Lgd = m->tendNew.gd;
@@ -2317,7 +2335,7 @@ static int time_stage(gmd_model *m, int pass, int mode, int reps, float *ms_per_
   CK(cudaEventCreate(&e1));
   CK(cudaEventRecord(e0, m->stream));
   for (int k = 0; k < reps; k++) {
-    fn<<<grid, BX, m->stage_smem, m->stream>>>(a);
+    fn<<<grid, BX, (size_t)(rpc + 2) * RC_N * sizeof(double), m->stream>>>(a);
     m->launches++;
   }
   CK(cudaEventRecord(e1, m->stream));

@@ -360,6 +360,9 @@ __device__ __forceinline__ void st2(double *p, double x, double y) {
 #ifndef GMD_S3A_UNROLL
 #define GMD_S3A_UNROLL GMD_UNROLL
 #endif
+#ifndef GMD_S2_UNROLL
+#define GMD_S2_UNROLL 1
+#endif
 #ifndef GMD_ALL_MINB
 #define GMD_ALL_MINB GMD_MINB   // unsplit pass (advection + fast terms in one sweep): the widest register window
 #endif
@@ -678,7 +681,7 @@ __global__ void __launch_bounds__(BX, (stage_minb<PASS, MODE, LAZY>())) k_stage(
 
     // measured on B200 (tools/tune_stage.py): the deferred-update variants and S2 are fastest without unrolling (no
     // spills at the 128-register cap), S1 / S3a with two rows per trip
-    constexpr int kUnroll = LAZY ? GMD_LAZY_UNROLL : (MODE == MODE_S2 ? 1 : (MODE == MODE_S3A ? GMD_S3A_UNROLL : GMD_UNROLL));
+    constexpr int kUnroll = LAZY ? GMD_LAZY_UNROLL : (MODE == MODE_S2 ? GMD_S2_UNROLL : (MODE == MODE_S3A ? GMD_S3A_UNROLL : GMD_UNROLL));
 #pragma unroll kUnroll
     for (int j = ja; j < jb; j++) {
       // ---- issue every load of this iteration first: the next row of the evaluated state (consumed one
