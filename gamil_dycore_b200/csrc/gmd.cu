@@ -168,6 +168,11 @@ struct gmd_model {
   cudaEvent_t ev_polar_side = nullptr;  // completion of the last polar-side stage launch on the main stream
   bool split = true;
   int ew_blocks = 0;  // grid of element-wise kernels
+  // fused polar cap (k_cap): the sweep over the rows next to a pole and the polar rows of that sweep in one launch
+  bool cap = false;
+  unsigned *d_bar = nullptr;   // grid barrier counters of k_cap
+  int cap_ctas = 0;            // CTAs of a k_cap launch (co-resident; a multiple of the cluster size)
+  int prio_hi = 0;             // launch priority of k_cap
 
   // comm: NCCL (optional) and the peer-memory path (gmd_peer_connect)
   void *comm = nullptr;
@@ -505,6 +510,41 @@ static stage_fn pick_stage_lazy(int pass, int adv, int lazy) {
   return lazy == 1 ? pick_stage_lazy_t<1>(pass, adv) : pick_stage_lazy_t<2>(pass, adv);
 }
 
+// the fused polar-cap kernel (never WENO: its advection terms come from separate sweeps)
+typedef void (*cap_fn)(const StageArgs, const PolarArgs, const CapArgs);
+template <int MODE, int LZ>
+static cap_fn pick_cap_t(int pass, int adv) {
+  if (pass == PASS_FAST) return k_cap<PASS_FAST, ADV_CENTER, MODE, LZ>;
+  if (pass == PASS_ALL) return adv == ADV_UPWIND ? k_cap<PASS_ALL, ADV_UPWIND, MODE, LZ> : k_cap<PASS_ALL, ADV_CENTER, MODE, LZ>;
+  return adv == ADV_UPWIND ? k_cap<PASS_SLOW, ADV_UPWIND, MODE, LZ> : k_cap<PASS_SLOW, ADV_CENTER, MODE, LZ>;
+}
+static cap_fn pick_cap(int pass, int adv, int mode, int lazy) {
+  if (adv == ADV_WENO && pass != PASS_FAST) return nullptr;
+  if (lazy) return lazy == 1 ? pick_cap_t<MODE_S1, 1>(pass, adv) : pick_cap_t<MODE_S1, 2>(pass, adv);
+  switch (mode) {
+    case MODE_S1: return pick_cap_t<MODE_S1, 0>(pass, adv);
+    case MODE_S2: return pick_cap_t<MODE_S2, 0>(pass, adv);
+    case MODE_S3A: return pick_cap_t<MODE_S3A, 0>(pass, adv);
+    default: return pick_cap_t<MODE_EVAL, 0>(pass, adv);
+  }
+}
+static int launch_cap(gmd_model *m, cap_fn fn, int grid, const StageArgs &b, const PolarArgs &p, const CapArgs &c) {
+  cudaLaunchConfig_t lc = {};
+  lc.gridDim = dim3((unsigned)grid, 1, 1);
+  lc.blockDim = dim3(BX, 1, 1);
+  lc.dynamicSmemBytes = m->stage_smem_b;
+  lc.stream = m->stream;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributePriority;
+  at[1].val.priority = m->prio_hi;
+  lc.attrs = at;
+  lc.numAttrs = 2;
+  CK(cudaLaunchKernelEx(&lc, fn, b, p, c));
+  return 0;
+}
+
 static int post_launch(gmd_model *m) {
   m->launches++;
   if (m->dry) return 0;
@@ -776,6 +816,29 @@ static void launch_polar(gmd_model *m, int mode, int nitems, PolarArgs &p, cudaS
   }
 }
 
+// arguments of the polar rows that belong to the sweep described by `a`
+static void polar_args(gmd_model *m, const StageArgs &a, bool lazy, int li, int nst, double dt, PolarArgs *pp) {
+  PolarArgs &p = *pp;
+  memset(&p, 0, sizeof p);
+  p.g = m->geo;
+  p.t = m->tab;
+  fill_items(p, m->items[li]);
+  p.EU = lazy ? a.MU : a.EU; p.EV = lazy ? a.MV : a.EV; p.Egd = lazy ? a.Mgd : a.Egd; p.ghs = a.ghs;
+  p.OU = a.OU; p.OV = a.OV; p.Ogd = a.Ogd;
+  p.NU = a.NU; p.NV = a.NV; p.Ngd = a.Ngd;
+  p.TU = a.TU; p.TV = a.TV; p.Tgd = a.Tgd;
+  p.PU = a.PU; p.PV = a.PV; p.Pgd = a.Pgd;
+  p.dt = dt;
+  p.partials = m->d_partials + 2 * (size_t)nst;
+  p.rescale = 1;
+  p.radius = m->mesh.radius;
+  p.dlat = m->mesh.dlat;
+  p.fold = a.fold;
+  p.fold_partials = m->d_partials;
+  p.basis = m->d_basis;
+  p.rot = m->d_rot;
+}
+
 // one fused operator evaluation (+ update / store / dots) of state E
 // A deferred update handed to the next MODE_S1 launch: E = base + beta ldt L, written out to M
 struct LazyIn {
@@ -846,7 +909,10 @@ static int stage(gmd_model *m, int pass, int mode, const State &E, const State *
   const size_t smem_i = (size_t)(rpc + 2) * RC_N * sizeof(double);
   const int nci = (I1 - I0 + rpc - 1) / rpc;
   const int ncb = split ? m->nchunks_b : 0;
-  const int nst = 2 * m->nbx * ncb + m->nbx * nci;
+  const cap_fn cfn = (split && m->cap && m->n_items[li]) ? pick_cap(pass, adv, mode, lz ? lz->kind : 0) : nullptr;
+  // row ranges next to a pole: the fused cap launch covers only those that exist on this band
+  const int nz = cfn ? (poleS ? 1 : 0) + (poleN ? 1 : 0) : 2;
+  const int nst = nz * m->nbx * ncb + m->nbx * nci;
   if (fold) {  // one partial pair and one ticket per CTA of the stage launch(es) and of the polar-row launch
     a.fold.ticket = reinterpret_cast<unsigned *>(m->d_ip + 7);
     a.fold.total = (unsigned)(nst + m->n_items[li]);
@@ -867,8 +933,27 @@ static int stage(gmd_model *m, int pass, int mode, const State &E, const State *
     b.rb[1] = poleN ? r1 - m->bn : r1; b.re[1] = r1; b.pofs[1] = m->nbx * ncb;
     dim3 gb((unsigned)m->nbx, (unsigned)ncb, 2);
     static const char *const bnames[4] = {"k_stage.S1.polar_side", "k_stage.S2.polar_side", "k_stage.S3a.polar_side", "k_stage.eval.polar_side"};
-    b.tseq = tseq(m, bnames[mode]);
-    if (!m->dry) fn<<<gb, BX, m->stage_smem_b, m->stream>>>(b);
+    static const char *const cnames[4] = {"k_cap.S1", "k_cap.S2", "k_cap.S3a", "k_cap.eval"};
+    if (cfn) {   // the sweep over these rows and their polar rows in one launch
+      b.tseq = tseq(m, cnames[mode]);
+      PolarArgs p;
+      polar_args(m, a, lz != nullptr, li, nst, dt, &p);
+      p.tseq = b.tseq;
+      CapArgs c;
+      c.bar = m->d_bar;
+      c.n_march = nz * m->nbx * ncb;
+      c.gx = m->nbx;
+      c.gy = ncb;
+      c.z0 = poleS ? 0 : 1;
+      c.nitems = m->n_items[li];
+      b.pofs[c.z0] = 0;                 // partial slots of the ranges the launch covers, compact
+      b.pofs[1 - c.z0] = (nz == 2) ? m->nbx * ncb : 0;
+      const int want_ctas = std::min(m->cap_ctas, std::max((c.n_march + CL - 1) / CL, c.nitems) * CL);
+      if (!m->dry && (r = launch_cap(m, cfn, want_ctas, b, p, c))) return r;
+    } else {
+      b.tseq = tseq(m, bnames[mode]);
+      if (!m->dry) fn<<<gb, BX, m->stage_smem_b, m->stream>>>(b);
+    }
     if ((r = post_launch(m))) return r;
     if (!m->dry) {   // what the NEXT sweep's interior launch has to wait for on the main stream: this launch, not the
       cudaEvent_t e = next_event(m);   // polar rows that follow it (its rows are at least two rows away from them)
@@ -876,7 +961,7 @@ static int stage(gmd_model *m, int pass, int mode, const State &E, const State *
       m->ev_polar_side = e;
     }
     a.rows_per_cta = rpc;
-    a.rb[0] = I0; a.re[0] = I1; a.pofs[0] = 2 * m->nbx * ncb;
+    a.rb[0] = I0; a.re[0] = I1; a.pofs[0] = nz * m->nbx * ncb;
     a.medge[0] = edges & ((poleS ? 0 : 1) | (poleN ? 0 : 2));
     dim3 gi((unsigned)m->nbx, (unsigned)nci, 1);
     static const char *const inames[4] = {"k_stage.S1.interior", "k_stage.S2.interior", "k_stage.S3a.interior", "k_stage.eval.interior"};
@@ -896,24 +981,9 @@ static int stage(gmd_model *m, int pass, int mode, const State &E, const State *
     if ((r = post_launch(m))) return r;
   }
 
-  if (m->n_items[li]) {
+  if (m->n_items[li] && !cfn) {
     PolarArgs p;
-    memset(&p, 0, sizeof p);
-    p.g = m->geo;
-    p.t = m->tab;
-    fill_items(p, m->items[li]);
-    p.EU = lz ? a.MU : a.EU; p.EV = lz ? a.MV : a.EV; p.Egd = lz ? a.Mgd : a.Egd; p.ghs = a.ghs;
-    p.OU = a.OU; p.OV = a.OV; p.Ogd = a.Ogd;
-    p.NU = a.NU; p.NV = a.NV; p.Ngd = a.Ngd;
-    p.TU = a.TU; p.TV = a.TV; p.Tgd = a.Tgd;
-    p.PU = a.PU; p.PV = a.PV; p.Pgd = a.Pgd;
-    p.dt = dt;
-    p.partials = m->d_partials + 2 * (size_t)nst;
-    p.rescale = 1;
-    p.radius = m->mesh.radius;
-    p.dlat = m->mesh.dlat;
-    p.fold = a.fold;
-    p.fold_partials = m->d_partials;
+    polar_args(m, a, lz != nullptr, li, nst, dt, &p);
     p.tseq = tseq(m, "k_polar");
     if (!m->dry) launch_polar(m, mode, m->n_items[li], p, m->stream);
     if ((r = post_launch(m))) return r;
@@ -1458,6 +1528,7 @@ void gmd_destroy(gmd_model *m) {
   cudaFree(m->d_flags_alloc);
   cudaFree(m->d_basis);
   cudaFree(m->d_rot);
+  cudaFree(m->d_bar);
   cudaFree(m->d_partials);
   cudaFree(m->d_ip);
   cudaFree(m->d_ring);
@@ -1569,7 +1640,21 @@ int gmd_create(const gmd_config *cfg, gmd_model **out) {
     // single band: the split buys nothing (the one-wave interior launch owns every register file, so the polar-row
     // CTAs cannot co-run; measured 4.80 vs 4.75 ms per step); with several bands the two polar ranks split off the
     // rows next to their pole, so that the polar-row kernel that follows them overlaps the rest of the sweep
-    m->split = m->wide && (m->bs + m->bn > 0);
+    // fused polar cap: every item must be one the thread-owned projector handles (cutoff < KF, nlon % 4 == 0, at most
+    // PQ element groups per thread)
+    m->cap = (m->n_items[0] + m->n_items[1] > 0) && (nlon % 4 == 0) && ((nlon / 4 + PT - 1) / PT <= PQ) &&
+             cfg->uv_adv_scheme != GMD_ADV_WENO && getenv("GMD_CAP") != nullptr;   // opt-in: measured slower
+    for (int li = 0; li < 2 && m->cap; li++)
+      for (unsigned pk : m->items[li]) {
+        const int cutoff = (int)((pk >> 16) & 0x1ffu) - 1, kind = (int)(pk >> 28);
+        const int Kk = cutoff + 1;
+        if (kind != IT_POLE_S && kind != IT_POLE_N && !(Kk >= 1 && Kk <= KF && 2 * Kk < nlon)) m->cap = false;
+      }
+    // without the fused cap a single band gains nothing from the split (the one-wave interior launch owns every
+    // register file, so the 512-thread polar-row CTAs cannot co-run; measured 4.80 vs 4.75 ms per step); the cap CTAs
+    // are ordinary stage CTAs and do overlap the interior sweep
+    static const bool cap_n1 = getenv("GMD_CAP_N1") != nullptr;
+    m->split = (m->wide || (m->cap && cfg->nranks == 1 && cap_n1)) && (m->bs + m->bn > 0);
     if (const char *ev = getenv("GMD_NO_SPLIT")) m->split = (atoi(ev) == 0) && (cfg->nranks == 1 || m->wide);
     if (m->bs + m->bn >= m->nr) m->split = false;
     const int nstrips = (nlon + WOUT - 1) / WOUT;
@@ -1606,6 +1691,31 @@ int gmd_create(const gmd_config *cfg, gmd_model **out) {
     if (const char *ev = getenv("GMD_ROWS_PER_CTA_B")) m->rows_per_cta_b = std::max(1, atoi(ev));
     m->nchunks_b = (std::max(m->bs, m->bn) + m->rows_per_cta_b - 1) / m->rows_per_cta_b;
     m->stage_smem_b = (size_t)(m->rows_per_cta_b + 2) * RC_N * sizeof(double);
+    if (m->cap) {
+      // the launch must be co-resident (grid barrier): as many clusters as there are items, within the device's limit
+      int lo = 0, hi = 0;
+      CKD(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      m->prio_hi = hi;
+      CKD(cudaMalloc(&m->d_bar, 2 * sizeof(unsigned)));
+      CKD(cudaMemset(m->d_bar, 0, 2 * sizeof(unsigned)));
+      cudaLaunchConfig_t lc = {};
+      lc.gridDim = dim3(CL * 64, 1, 1);
+      lc.blockDim = dim3(BX, 1, 1);
+      lc.dynamicSmemBytes = m->stage_smem_b;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      lc.attrs = at;
+      lc.numAttrs = 1;
+      int ncl = 0;
+      cudaError_t ce = cudaOccupancyMaxActiveClusters(&ncl, pick_cap(pass0, cfg->uv_adv_scheme, MODE_S3A, 0), &lc);
+      if (ce != cudaSuccess) { cudaGetLastError(); ncl = 0; }
+      int lim = (ncl * 3 / 4) * CL;   // leave room: other kernels of the step hold slots while the cap CTAs arrive
+      if (const char *ev = getenv("GMD_CAP_CTAS")) lim = std::min(ncl * CL, std::max(CL, atoi(ev) / CL * CL));
+      const int n_march = (2 * m->nbx * m->nchunks_b + CL - 1) / CL * CL;
+      m->cap_ctas = lim;
+      if (n_march > lim) m->cap = false, m->split = m->split && m->wide;
+    }
     CKD(cudaStreamCreateWithFlags(&m->stream2, cudaStreamNonBlocking));
     m->evpool.resize(64);
     for (auto &e : m->evpool) CKD(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -1853,18 +1963,26 @@ int gmd_set_state(gmd_model *m, const double *u, const double *v, const double *
   int r = set_dev(m);
   if (r) return r;
   const int nlon = m->geo.nlon, nlat = m->geo.nlat;
-  // pole rows of u must be zero (du is never written there, so U(pole) = 0 is an invariant of every reference IC)
+  // pole rows of u must be zero (du is never written there, so U(pole) = 0 is an invariant of every reference IC).
+  // The Shamir-Paldor wave IC evaluates cos(+-pi/2)^(sigma - 1.5) there, ~1e-146 m/s: values below GMD_POLE_U_TINY
+  // are taken as the zero they stand for (they cannot change any other binary64 result of the step).
   for (int pj = 0; pj < 2; pj++) {
     const int j = pj ? nlat - 1 : 0;
     const double *row = (layout == GMD_LAYOUT_REFERENCE) ? u + (size_t)(j + 2) * (nlon + 4) + 2 : u + (size_t)j * nlon;
     for (int i = 0; i < nlon; i++)
-      if (row[i] != 0.0) return fail(GMD_ERR_ARG, "u must be 0 on the pole rows (row %d, column %d is %g)", j, i, row[i]);
+      if (!(std::fabs(row[i]) <= GMD_POLE_U_TINY))
+        return fail(GMD_ERR_ARG, "u must be 0 on the pole rows (row %d, column %d is %g)", j, i, row[i]);
   }
   if ((r = ensure_uv(m))) return r;
   {
     XferJob jobs[4] = {up_job(u, layout, nlat, m->w_u), up_job(v, layout, nlat - 1, m->w_v),
                        up_job(gd, layout, nlat, m->cur.gd), up_job(ghs, layout, nlat, m->ghs)};
     if ((r = run_xfers(m, jobs, 4))) return r;
+  }
+  for (int pj = 0; pj < 2; pj++) {
+    const int j = pj ? nlat - 1 : 0;
+    if (j >= m->geo.r0 - GHOST && j < m->geo.r1 + GHOST)
+      CK(cudaMemsetAsync(m->w_u + (ptrdiff_t)(j - m->geo.r0) * nlon, 0, (size_t)nlon * sizeof(double), m->stream));
   }
   // iap_transform on owned + ghost rows inside the globe (src/types_mod.F90:399-426)
   Geo g = m->geo;
@@ -2277,7 +2395,25 @@ int gmd_trace_dump(gmd_model *m, const char *path) {
     }
     fprintf(f, "]}");
   }
-  fprintf(f, "]}\n");
+  fprintf(f, "]");
+  {   // phase stamps of CTA 0 of the most recent fused polar-cap launches
+    std::vector<u64> cd(64 * 12);
+    CK(cudaMemcpyFromSymbol(cd.data(), g_capdbg, cd.size() * sizeof(u64)));
+    fprintf(f, ", \"cap_phases_ns\": [");
+    bool any = false;
+    for (int q = 0; q < 64; q++) {
+      const u64 *c = cd.data() + 12 * q;
+      if (!c[0] || !c[4]) continue;
+      // sweep, grid barrier, first item, all items; inside the first item: loads + analysis, first cluster sum,
+      // synthesis, second cluster sum, stores
+      fprintf(f, "%s[%llu, %llu, %llu, %llu, %llu, %llu, %llu, %llu, %llu]", any ? ", " : "", c[1] - c[0], c[2] - c[1],
+              c[3] > c[2] ? c[3] - c[2] : 0ull, c[4] - c[2], c[5] > c[2] ? c[5] - c[2] : 0ull, c[6] > c[5] ? c[6] - c[5] : 0ull,
+              c[7] > c[6] ? c[7] - c[6] : 0ull, c[8] > c[7] ? c[8] - c[7] : 0ull, c[9] > c[8] ? c[9] - c[8] : 0ull);
+      any = true;
+    }
+    fprintf(f, "]");
+  }
+  fprintf(f, "}\n");
   fclose(f);
   TraceBuf tb = {nullptr, nullptr, 0, 0};
   CK(cudaMemcpyToSymbol(g_trace, &tb, sizeof tb));

@@ -527,27 +527,27 @@ template <int PASS, int MODE, int LAZY>
 constexpr int stage_minb() {
   return PASS == 0 /* PASS_ALL */ ? GMD_ALL_MINB : (LAZY ? GMD_LAZY_MINB : (MODE == 2 /* MODE_S3A */ ? GMD_S3A_MINB : GMD_MINB));
 }
-template <int PASS, int ADV, int MODE, int LAZY = 0, bool PUSH = false>
-__global__ void __launch_bounds__(BX, (stage_minb<PASS, MODE, LAZY>())) k_stage(const StageArgs a) {
-  __shared__ double red[2 * SW];
-  extern __shared__ double srow[];  // row records of rows ja-1 .. jb: [(jb - ja + 2)][RC_N]
+// The sweep of one CTA: (bx, by, bz) = strip group, row chunk and row range of the CTA, gx = strip groups per chunk
+// row; red: 2 SW doubles, srow: (rows_per_cta + 2) row records of shared memory.  k_stage runs it on its own block
+// index, k_cap (below) on a linear CTA index, followed by the polar rows of the same sweep.
+template <int PASS, int ADV, int MODE, int LAZY, bool PUSH>
+__device__ __forceinline__ void stage_body(const StageArgs &a, const int bx, const int by, const int bz, const int gx,
+                                           double *red, double *srow) {
   const int nlon = a.g.nlon, nlat = a.g.nlat, r0 = a.g.r0;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int strip = blockIdx.x * SW + warp;
+  const int strip = bx * SW + warp;
   const int nstrips = (nlon + WOUT - 1) / WOUT;
-  const int ja = a.rb[blockIdx.z] + blockIdx.y * a.rows_per_cta;
-  const int jb = min(ja + a.rows_per_cta, a.re[blockIdx.z]);
-  trace_in(a.tseq);
-  if (ja >= jb) {  // whole CTA: this range has fewer chunks than gridDim.y
+  const int ja = a.rb[bz] + by * a.rows_per_cta;
+  const int jb = min(ja + a.rows_per_cta, a.re[bz]);
+  if (ja >= jb) {  // whole CTA: this range has fewer chunks than the launch has chunk rows
     if (MODE == MODE_S3A && threadIdx.x == 0) {
-      const size_t b = (size_t)a.pofs[blockIdx.z] + (size_t)blockIdx.y * gridDim.x + blockIdx.x;
+      const size_t b = (size_t)a.pofs[bz] + (size_t)by * gx + bx;
       a.partials[2 * b] = 0.0;
       a.partials[2 * b + 1] = 0.0;
     }
     if (MODE == MODE_S3A && a.fold.ticket)
       fold_tail<BX>(a.fold.ticket, a.fold.total, a.partials, a.fold.n, a.fold.out, a.fold.r.page, a.fold.r.rank, a.fold.r.nranks,
                     a.fold.r.k, a.tseq);
-    trace_out(a.tseq);
     return;
   }
   const bool need_gh = (PASS != PASS_SLOW);
@@ -575,8 +575,8 @@ __global__ void __launch_bounds__(BX, (stage_minb<PASS, MODE, LAZY>())) k_stage(
     //      this CTA is responsible for (its own rows; the band's ghost rows for the CTAs at the band edges)
     double bdt = 0.0;
     if (LAZY) bdt = a.ldt * beta_from_ip(a.lip, a.lqcon);
-    const bool edgeS = LAZY && (ja == a.rb[blockIdx.z]) && (a.medge[blockIdx.z] & 1);
-    const bool edgeN = LAZY && (jb == a.re[blockIdx.z]) && (a.medge[blockIdx.z] & 2);
+    const bool edgeS = LAZY && (ja == a.rb[bz]) && (a.medge[bz] & 1);
+    const bool edgeN = LAZY && (jb == a.re[bz]) && (a.medge[bz] & 2);
     auto mineUV = [&](int r) { return (r >= ja && r < jb) || (edgeS && r == ja - 1) || (edgeN && r == jb); };
     auto mineG = [&](int r) { return (r >= ja && r < jb) || (edgeS && r == ja - 1) || (edgeN && (r == jb || r == jb + 1)); };
     auto combU = [&](D2 b, D2 t, int r) -> D2 {
@@ -905,7 +905,7 @@ __global__ void __launch_bounds__(BX, (stage_minb<PASS, MODE, LAZY>())) k_stage(
         q1 += red[2 * w];
         q2 += red[2 * w + 1];
       }
-      const size_t b = (size_t)a.pofs[blockIdx.z] + (size_t)blockIdx.y * gridDim.x + blockIdx.x;
+      const size_t b = (size_t)a.pofs[bz] + (size_t)by * gx + bx;
       a.partials[2 * b] = q1;
       a.partials[2 * b + 1] = q2;
       // this CTA's peer stores (all issued before the barrier above) must be visible to the neighbours before the ticket
@@ -916,6 +916,14 @@ __global__ void __launch_bounds__(BX, (stage_minb<PASS, MODE, LAZY>())) k_stage(
       fold_tail<BX>(a.fold.ticket, a.fold.total, a.partials, a.fold.n, a.fold.out, a.fold.r.page, a.fold.r.rank, a.fold.r.nranks,
                     a.fold.r.k, a.tseq);
   }
+}
+
+template <int PASS, int ADV, int MODE, int LAZY = 0, bool PUSH = false>
+__global__ void __launch_bounds__(BX, (stage_minb<PASS, MODE, LAZY>())) k_stage(const StageArgs a) {
+  __shared__ double red[2 * SW];
+  extern __shared__ double srow[];  // row records of rows ja-1 .. jb: [(jb - ja + 2)][RC_N]
+  trace_in(a.tseq);
+  stage_body<PASS, ADV, MODE, LAZY, PUSH>(a, blockIdx.x, blockIdx.y, blockIdx.z, gridDim.x, red, srow);
   trace_out(a.tseq);
 }
 
@@ -1346,6 +1354,397 @@ __global__ void __launch_bounds__(PT) k_polar(const __grid_constant__ PolarArgs 
       fold_tail<PT>(a.fold.ticket, a.fold.total, a.fold_partials, a.fold.n, a.fold.out, a.fold.r.page, a.fold.r.rank,
                     a.fold.r.nranks, a.fold.r.k, a.tseq);
   }
+  trace_out(a.tseq);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Fused polar cap (k_cap): the sweep over the rows next to a pole AND the polar rows of the same sweep -- filter +
+// rescale + update of the flagged rows, pole caps -- in ONE launch.  On a short latitude band the chain
+//   cap sweep -> polar rows -> cap sweep of the next operator evaluation -> ...
+// is what a polar rank waits for (36 links per model step with csp2 x 10): as two launches a link costs
+// 7-10 us + 10-13 us + two launch gaps (profiles/r2_d_timeline_*), and the 512-thread, one-per-SM CTAs of k_polar cannot
+// co-run with the interior sweep.  Here
+//  * CTAs [0, n_march) run stage_body on the cap rows (same code as k_stage), then every CTA of the launch meets at
+//    a grid barrier (arrive / depart counters in global memory, self-resetting, so a captured graph replays it);
+//    the launch is sized to be co-resident and is given the highest launch priority;
+//  * the polar items are then dealt to CLUSTERS of CL = 4 CTAs x 128 threads: the PT = 512 threads of one item are
+//    the same thread-owned-element projector as k_polar's fast path (element b + q n/4 of thread b; one (cos, sin)
+//    pair per wavenumber serves four elements), but every row element stays in REGISTERS -- no row in shared memory,
+//    so a cap CTA occupies one ordinary stage-CTA slot -- and the block reductions become cluster reductions over
+//    distributed shared memory (fixed order: deterministic, and the same bits in each CTA of the cluster).
+// Only the cutoffs / row lengths of the fast projector are supported (the host falls back to k_stage + k_polar).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int CL = 4;   // CTAs per cluster
+static_assert(CL * BX == PT, "the rotation table of the fast projector is built for PT threads per item");
+constexpr int GR = 2;   // element groups of a thread held in registers (rows of up to 4 GR PT elements; longer: reloaded)
+
+struct CapArgs {
+  unsigned *bar;     // {arrived, departed}
+  int n_march;       // CTAs [0, n_march) run the sweep: linear index = ((bz - z0) * gy + by) * gx + bx
+  int gx, gy, z0;    // z0: first row range of StageArgs this launch covers (a band with one pole has one range)
+  int nitems;        // polar items, dealt round-robin to the launch's clusters
+};
+#if GMD_TRACE
+// phase stamps of CTA 0 of the last k_cap launches (slot = timeline slot % 64): start, sweep done, barrier passed,
+// first item done, end
+__device__ u64 g_capdbg[64 * 12];
+#define GMD_CAP_STAMP(k) do { if (blockIdx.x == 0 && threadIdx.x == 0 && a.tseq > 0) g_capdbg[(a.tseq % 64) * 12 + (k)] = gtimer(); } while (0)
+#else
+#define GMD_CAP_STAMP(k) do { } while (0)
+#endif
+
+__device__ __forceinline__ unsigned cluster_ctarank() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ double ld_cluster(const double *p, unsigned rank) {
+  const unsigned la = (unsigned)__cvta_generic_to_shared(p);
+  unsigned ra;
+  double v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(rank));
+  asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(ra) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned *p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// Sum NVAL values over the CL * BX threads of a cluster in a fixed order: warp shuffles, one shared-memory slot per
+// warp, then every CTA adds the CL * SW slots of the cluster in (rank, warp) order.  `part` ([NVAL][SW]) must not be
+// written again before the cluster has passed another barrier; the result is in out[0 .. NVAL) for every thread.
+template <int NVAL>
+__device__ __forceinline__ void cluster_sum(double (&v)[NVAL], double *part, double *out) {
+  warp_sum_n<NVAL>(v);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) {
+#pragma unroll
+    for (int m = 0; m < NVAL; m++) part[m * SW + warp] = v[m];
+  }
+  cluster_sync_all();
+  if ((int)threadIdx.x < NVAL) {
+    double q[CL * SW];
+#pragma unroll
+    for (int r = 0; r < CL; r++)
+#pragma unroll
+      for (int w = 0; w < SW; w++) q[r * SW + w] = ld_cluster(part + threadIdx.x * SW + w, (unsigned)r);
+    double sum = 0.0;
+#pragma unroll
+    for (int k = 0; k < CL * SW; k++) sum += q[k];
+    out[threadIdx.x] = sum;
+  }
+  __syncthreads();
+}
+
+struct CapSmem {
+  double partA[(2 + 2 * KF) * SW], outA[2 + 2 * KF];
+  double partB[SW], outB[1];
+  double partC[2 * SW], outC[2];
+  double rot[PQ * KF * 2];
+};
+
+// one polar item worked on by the PT threads of a cluster; gtid = thread index inside the cluster
+template <int MODE>
+__device__ __noinline__ void cap_item(const PolarArgs &a, const int it, const int gtid, CapSmem &sm) {
+  const unsigned pk = a.items[it];
+  const int j = (int)(pk & 0xffffu), cutoff = (int)((pk >> 16) & 0x1ffu) - 1, kind = (int)(pk >> 28);
+  const int n = a.g.nlon, r0 = a.g.r0;
+  const ptrdiff_t off = (ptrdiff_t)(j - r0) * (ptrdiff_t)n;
+  double ip1 = 0.0, ip2 = 0.0;
+
+  if (kind == IT_POLE_S || kind == IT_POLE_N) {
+    // src/dycore_mod.F90:572-596: zonal sum of the single adjacent flux, broadcast along the pole row
+    const double *g0 = a.Egd + off;
+    const double *g1 = (kind == IT_POLE_S) ? a.Egd + off + n : a.Egd + off - n;
+    const double *vv = (kind == IT_POLE_S) ? a.EV + off : a.EV + off - n;
+    const double *Q = (MODE == MODE_S3A) ? a.Pgd : a.Ogd;
+    double acc[1] = {0.0};
+    for (int i0 = gtid; i0 < n; i0 += PT * 8) {
+      double av[8], bv[8], cv[8];
+#pragma unroll
+      for (int e = 0; e < 8; e++) {
+        const int i = i0 + e * PT;
+        const bool ok = i < n;
+        av[e] = ok ? __ldcg(g0 + i) : 0.0;
+        bv[e] = ok ? __ldcg(g1 + i) : 0.0;
+        cv[e] = ok ? __ldcg(vv + i) : 0.0;
+      }
+#pragma unroll
+      for (int e = 0; e < 8; e++) {
+        if (i0 + e * PT < n) {
+          const double f = (sqrt(av[e]) + sqrt(bv[e])) * cv[e];
+          acc[0] = (kind == IT_POLE_S) ? acc[0] + f : acc[0] - f;
+        }
+      }
+    }
+    cluster_sum<1>(acc, sm.partB, sm.outB);
+    const double dG = -(sm.outB[0] * 2.0 / n / a.radius / a.dlat);  // dgd = -mass_div_lon(=0) - mass_div_lat
+    const double cw = a.t.cosf[j];
+    for (int i = gtid; i < n; i += PT) {
+      double o = 0.0;
+      if (MODE != MODE_EVAL) o = __ldcg(Q + off + i);
+      if (MODE == MODE_S1 || MODE == MODE_S2) a.Ngd[off + i] = o + a.dt * dG;
+      if (MODE != MODE_S1) a.Tgd[off + i] = dG;
+      if (MODE == MODE_S3A) {
+        ip1 = ip1 + dG * o * cw;
+        ip2 = ip2 + dG * dG * cw;
+      }
+    }
+  } else {
+    double *T = (kind == IT_DU) ? a.TU : (kind == IT_DV) ? a.TV : a.Tgd;
+    const double *W = (kind == IT_DU) ? a.EU : (kind == IT_DV) ? a.EV : a.Egd;
+    const double *O = (kind == IT_DU) ? a.OU : (kind == IT_DV) ? a.OV : a.Ogd;
+    double *N = (kind == IT_DU) ? a.NU : (kind == IT_DV) ? a.NV : a.Ngd;
+    const double *P = (kind == IT_DU) ? a.PU : (kind == IT_DV) ? a.PV : a.Pgd;
+    const double *Q = (MODE == MODE_S1 || MODE == MODE_S2) ? O : (MODE == MODE_S3A) ? P : nullptr;
+    const bool isG = (kind == IT_DGD);
+    const int K = cutoff + 1;
+    const int n4 = n >> 2;
+    const int G = (n4 + PT - 1) / PT;
+    constexpr int NV = 2 + 2 * KF;
+    double bcv[KF], bsv[KF];
+#pragma unroll
+    for (int k = 0; k < KF; k++) {
+      bcv[k] = bsv[k] = 0.0;
+      if (k < K && gtid < n4) {
+        bcv[k] = __ldg(a.basis + (size_t)(2 * k + 1) * n + gtid);
+        bsv[k] = __ldg(a.basis + (size_t)(2 * k + 2) * n + gtid);
+      }
+    }
+    // the (cos, sin) pairs of wavenumber k+1 at element b = gtid + g PT
+    auto turn = [&](int g, int k, double &cr, double &sr) {
+      const double ec = sm.rot[g * (KF * 2) + 2 * k], es = sm.rot[g * (KF * 2) + 2 * k + 1];
+      cr = bcv[k] * ec - bsv[k] * es;
+      sr = bsv[k] * ec + bcv[k] * es;
+    };
+    double v[NV];
+#pragma unroll
+    for (int m = 0; m < NV; m++) v[m] = 0.0;
+    // s1 and the 2K+1 dot products of the four elements b + q n/4 of one group
+    auto analyse = [&](int g, const double (&x)[4], const double (&w)[4]) {
+#pragma unroll
+      for (int q = 0; q < 4; q++) v[0] = v[0] + x[q] * w[q];
+      const double e0 = x[0] + x[2], e1 = x[1] + x[3], d0 = x[0] - x[2], d1 = x[1] - x[3];
+      const double a0 = e0 + e1, a2 = e0 - e1;
+      v[1] += a0;
+#pragma unroll
+      for (int k = 0; k < KF; k++) {
+        if (k < K) {
+          double cr, sr;
+          turn(g, k, cr, sr);
+          switch ((k + 1) & 3) {  // quarter turns of the other three elements
+            case 1: v[2 + 2 * k] += cr * d0 - sr * d1; v[3 + 2 * k] += sr * d0 + cr * d1; break;
+            case 2: v[2 + 2 * k] += cr * a2;           v[3 + 2 * k] += sr * a2;           break;
+            case 3: v[2 + 2 * k] += cr * d0 + sr * d1; v[3 + 2 * k] += sr * d0 - cr * d1; break;
+            default: v[2 + 2 * k] += cr * a0;          v[3 + 2 * k] += sr * a0;           break;
+          }
+        }
+      }
+    };
+    auto load4 = [&](const double *f, int b, double (&o)[4]) {
+#pragma unroll
+      for (int q = 0; q < 4; q++) o[q] = __ldcg(f + off + b + q * n4);
+    };
+    // ---- every load of the register groups first (one memory round trip), then the analysis ------------------
+    double xk[GR][4], wk[GR][4], qk[GR][4];
+    {
+      double gk[GR][4];
+#pragma unroll
+      for (int g = 0; g < GR; g++) {
+        const int b = gtid + g * PT;
+        const bool ok = (g < G) && (b < n4);
+#pragma unroll
+        for (int q = 0; q < 4; q++) xk[g][q] = wk[g][q] = qk[g][q] = gk[g][q] = 0.0;
+        if (ok) {
+          load4(T, b, xk[g]);
+          if (a.rescale) load4(W, b, wk[g]);
+          if (a.rescale && isG) load4(a.ghs, b, gk[g]);
+        }
+      }
+#pragma unroll
+      for (int g = 0; g < GR; g++) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) wk[g][q] = wk[g][q] + gk[g][q];
+        if ((g < G) && (gtid + g * PT < n4)) analyse(g, xk[g], wk[g]);
+      }
+    }
+    // the base-state / previous-tendency row travels while the cluster reduces
+    if (MODE != MODE_EVAL) {
+#pragma unroll
+      for (int g = 0; g < GR; g++)
+        if ((g < G) && (gtid + g * PT < n4)) load4(Q, gtid + g * PT, qk[g]);
+    }
+    for (int g = GR; g < G; g++) {   // rows longer than 4 GR PT elements
+      const int b = gtid + g * PT;
+      if (b < n4) {
+        double x[4], w[4] = {0.0, 0.0, 0.0, 0.0}, gh[4] = {0.0, 0.0, 0.0, 0.0};
+        load4(T, b, x);
+        if (a.rescale) load4(W, b, w);
+        if (a.rescale && isG) load4(a.ghs, b, gh);
+#pragma unroll
+        for (int q = 0; q < 4; q++) w[q] = w[q] + gh[q];
+        analyse(g, x, w);
+      }
+    }
+    GMD_CAP_STAMP(5);
+    cluster_sum<NV>(v, sm.partA, sm.outA);
+    GMD_CAP_STAMP(6);
+    const double s1 = sm.outA[0];
+    double s2 = 1.0;
+    bool do_filter = true;
+    if (a.rescale) do_filter = fabs(s1) > 1.0e-16;  // filter_inner_product_threshold, src/filter_mod.F90:31
+    // ---- reconstruction from entries 0 .. 2K-1 (sin(K x) is dropped: quirk B3) -------------------------------
+    const double c0 = sm.outA[1] * (1.0 / n);       // rfftf1.f:87-107 normalisation
+    double cc[KF], cs[KF];
+#pragma unroll
+    for (int k = 0; k < KF; k++) {
+      cc[k] = (k < K) ? sm.outA[2 + 2 * k] * (2.0 / n) : 0.0;
+      cs[k] = (k < K - 1) ? sm.outA[3 + 2 * k] * (2.0 / n) : 0.0;
+    }
+    auto synth = [&](int g, double (&y)[4]) {
+      double S0 = c0, Pa = 0.0, Ra = 0.0, P2 = 0.0;
+#pragma unroll
+      for (int k = 0; k < KF; k++) {
+        if (k < K) {
+          double cr, sr;
+          turn(g, k, cr, sr);
+          const double Pk = cc[k] * cr + cs[k] * sr;   // value at b; a quarter turn further: Rk, -Pk, -Rk
+          const double Rk = cs[k] * cr - cc[k] * sr;
+          switch ((k + 1) & 3) {
+            case 1: Pa += Pk; Ra += Rk; break;
+            case 2: P2 += Pk; break;
+            case 3: Pa += Pk; Ra -= Rk; break;
+            default: S0 += Pk; break;
+          }
+        }
+      }
+      y[0] = (S0 + P2) + Pa;
+      y[2] = (S0 + P2) - Pa;
+      y[1] = (S0 - P2) + Ra;
+      y[3] = (S0 - P2) - Ra;
+    };
+    if (do_filter) {
+      double s2p[1] = {0.0};
+#pragma unroll
+      for (int g = 0; g < GR; g++) {
+        if ((g < G) && (gtid + g * PT < n4)) {
+          synth(g, xk[g]);   // the filtered row replaces the tendency
+#pragma unroll
+          for (int q = 0; q < 4; q++) s2p[0] = s2p[0] + xk[g][q] * wk[g][q];
+        }
+      }
+      for (int g = GR; g < G; g++) {
+        const int b = gtid + g * PT;
+        if (b < n4) {
+          double y[4], w[4] = {0.0, 0.0, 0.0, 0.0}, gh[4] = {0.0, 0.0, 0.0, 0.0};
+          if (a.rescale) load4(W, b, w);
+          if (a.rescale && isG) load4(a.ghs, b, gh);
+          synth(g, y);
+#pragma unroll
+          for (int q = 0; q < 4; q++) s2p[0] = s2p[0] + y[q] * (w[q] + gh[q]);
+        }
+      }
+      GMD_CAP_STAMP(7);
+      if (a.rescale) {
+        cluster_sum<1>(s2p, sm.partB, sm.outB);
+        s2 = sm.outB[0];
+      }
+      GMD_CAP_STAMP(8);
+    }
+    const double cw = (kind == IT_DV) ? a.t.cosh[j] : a.t.cosf[j];
+    // src/dycore_mod.F90:218.  s2 == 0 exactly: the filtered row is left unscaled (see k_polar)
+    const bool scale = do_filter && a.rescale && (s2 != 0.0);
+#if !GMD_STRICT
+    const double ratio = scale ? s1 / s2 : 1.0;
+#endif
+    auto finish = [&](int b, const double (&y)[4], const double (&o)[4]) {
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const ptrdiff_t e = off + b + q * n4;
+        double d = y[q];
+#if GMD_STRICT
+        if (scale) d = d * s1 / s2;
+#else
+        d = d * ratio;
+#endif
+        if (MODE == MODE_S1 || MODE == MODE_S2) N[e] = o[q] + a.dt * d;
+        if (MODE != MODE_S1) T[e] = d;
+        if (MODE == MODE_S3A) {
+          ip1 = ip1 + d * o[q] * cw;
+          ip2 = ip2 + d * d * cw;
+        }
+      }
+    };
+#pragma unroll
+    for (int g = 0; g < GR; g++) {
+      const int b = gtid + g * PT;
+      if ((g < G) && (b < n4)) finish(b, xk[g], qk[g]);
+    }
+    for (int g = GR; g < G; g++) {
+      const int b = gtid + g * PT;
+      if (b < n4) {
+        double y[4], o[4] = {0.0, 0.0, 0.0, 0.0};
+        if (MODE != MODE_EVAL) load4(Q, b, o);
+        if (do_filter) synth(g, y);
+        else load4(T, b, y);
+        finish(b, y, o);
+      }
+    }
+  }
+  GMD_CAP_STAMP(9);
+  if (MODE == MODE_S3A) {
+    double w2[2] = {ip1, ip2};
+    cluster_sum<2>(w2, sm.partC, sm.outC);
+    if (gtid == 0) {
+      a.partials[2 * it] = sm.outC[0];
+      a.partials[2 * it + 1] = sm.outC[1];
+    }
+    if (a.fold.ticket && gtid < BX)   // the first CTA of the cluster
+      fold_tail<BX>(a.fold.ticket, a.fold.total, a.fold_partials, a.fold.n, a.fold.out, a.fold.r.page, a.fold.r.rank,
+                    a.fold.r.nranks, a.fold.r.k, a.tseq);
+  }
+}
+
+template <int PASS, int ADV, int MODE, int LAZY>
+__global__ void __launch_bounds__(BX, (stage_minb<PASS, MODE, LAZY>()))
+k_cap(const StageArgs a, const __grid_constant__ PolarArgs p, const CapArgs c) {
+  __shared__ double red[2 * SW];
+  __shared__ CapSmem sm;
+  extern __shared__ double srow[];
+  trace_in(a.tseq);
+  GMD_CAP_STAMP(0);
+  const int tid = threadIdx.x, b = blockIdx.x;
+  for (int k = tid; k < PQ * KF * 2; k += BX) sm.rot[k] = __ldg(p.rot + k);
+  if (b < c.n_march) {
+    const int bx = b % c.gx, by = (b / c.gx) % c.gy, bz = c.z0 + b / (c.gx * c.gy);
+    stage_body<PASS, ADV, MODE, LAZY, false>(a, bx, by, bz, c.gx, red, srow);
+  }
+  GMD_CAP_STAMP(1);
+  // ---- grid barrier: the polar items read rows written by any CTA of the sweep --------------------------------
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    atomicAdd(c.bar, 1u);
+    while (ld_acquire_gpu_u32(c.bar) < gridDim.x) { }
+    if (atomicAdd(c.bar + 1, 1u) == gridDim.x - 1) {  // everybody has seen the count: reset for the next launch
+      c.bar[1] = 0u;
+      c.bar[0] = 0u;
+    }
+  }
+  __syncthreads();
+  GMD_CAP_STAMP(2);
+  const int gtid = (int)cluster_ctarank() * BX + tid;
+  const int ncl = (int)gridDim.x / CL;
+  for (int it = b / CL; it < c.nitems; it += ncl) {
+    cap_item<MODE>(p, it, gtid, sm);
+    cluster_sync_all();   // nobody overwrites its reduction slots or leaves while a neighbour still reads them
+    if (it == b / CL) GMD_CAP_STAMP(3);
+  }
+  GMD_CAP_STAMP(4);
   trace_out(a.tseq);
 }
 

@@ -2,6 +2,8 @@
 
 #include <algorithm>
 #include <cmath>
+#include <complex>
+#include <cstdio>
 
 #include "../csrc/gmd_mesh.h"
 
@@ -226,6 +228,63 @@ double integrate_gk21(double (*f)(double), double a, double b, double epsabs, do
   return result;
 }
 
+// shallow_water_waves_test_mod.F90 (Shamir & Paldor 2016 analytic wave, gH = 5e4, (n, k) = (5, 10), Rossby branch).
+// getPhaseSpeed :130-171: the three roots of the cubic dispersion relation by Cardano's formula in complex arithmetic.
+double swe_phase_speed(int wave_flag) {
+  const double omega = 7.29212e-5, g = 9.80616, a = 6371220.0, H0 = 5.0e3, pi = 3.14159265358979323;
+  const int n = 5, k = 10;
+  const double sigma = 0.5 + std::pow(0.25 + k * k, 0.5);
+  const double En = g * H0 / (a * a) * ((n + sigma) * (n + sigma));
+  const double Delta0 = 3.0 * (k * k) * En;
+  const double Delta4 = -54.0 * (k * k * k * k) * g * H0 * omega / (a * a);
+  double Cj[3];
+  for (int j = 1; j <= 3; j++) {
+    std::complex<double> D = std::pow(std::complex<double>(Delta4 * Delta4 - 4.0 * (Delta0 * Delta0 * Delta0), 0.0), 0.5);
+    D = std::pow(0.5 * (Delta4 + D), 1.0 / 3.0);
+    D = D * std::exp(2.0 * pi * std::complex<double>(0.0, 1.0) * (double)j * (1.0 / 3.0));
+    Cj[j - 1] = std::real(-(1.0 / 3.0) / (k * k) * (D + Delta0 / D));
+  }
+  if (wave_flag == 0) return -std::min(std::fabs(Cj[0]), std::min(std::fabs(Cj[1]), std::fabs(Cj[2])));
+  if (wave_flag == 1) return std::max(Cj[0], std::max(Cj[1], Cj[2]));
+  return std::min(Cj[0], std::min(Cj[1], Cj[2]));
+}
+
+// shallow_water_waves_test_set_initial_condition :95-135 with getFields :276-321, getAmplitudes :215-271 (waveFlag 0)
+// and getPsi :176-210.  As the reference calls it, the latitude-dependent amplitudes are evaluated at the FULL
+// latitudes only, so v on half row j carries the amplitude of full row j (:307-313 index vTilde(j) over size(ilat)).
+void shallow_water_waves(const LonLat &gr, Fields &f) {
+  const int nlon = f.nlon, nlat = f.nlat;
+  const double omega = 7.29212e-5, g = 9.80616, a = 6371220.0, H0 = 5.0e3, pi = 3.14159265358979323;
+  const int k = 10;
+  const double sigma = 0.5 + std::pow(0.25 + k * k, 0.5), amp = 1.0e-8, o2 = 2.0 * omega;
+  const double a3 = sigma * (sigma + 1) * (sigma + 2), a4 = a3 * (sigma + 3), a5 = a4 * (sigma + 4);
+  const double C = swe_phase_speed(0);
+  std::vector<double> ut(nlat), vt(nlat), ht(nlat);
+  for (int j = 0; j < nlat; j++) {
+    const double lat = gr.flat(j);
+    const double sl = std::sin(lat), cl = std::cos(lat), tl = std::tan(lat);
+    const double s2 = sl * sl, s4 = s2 * s2;
+    const double C5 = (4.0 * a5 * s4 - 20.0 * a4 * s2 + 15.0 * a3) * sl / 15.0;
+    const double C5p = (4.0 * a5 * s4 - 12.0 * a4 * s2 + 3.0 * a3) * cl / 3.0;
+    const double psi = amp * std::pow(cl, sigma) * C5;
+    const double dpsi = amp * std::pow(cl, sigma) * (-sigma * tl * C5 + C5p);
+    const double Kp = (g * H0 + a * a * (C * C) * (cl * cl)) / (C * cl);
+    const double Km = (g * H0 - a * a * (C * C) * (cl * cl)) / (C * cl);
+    double v = std::pow(o2 * std::fabs(Km) / (cl * cl), 0.5) * psi;
+    const double h = std::pow(o2 * std::fabs(Km) * (a * a) * (H0 * H0), 0.5) / Km * (dpsi + tl * (0.5 * Kp / Km - o2 / C) * psi);
+    ut[j] = (o2 * sl / C) * v + (g / a / cl / C) * h;
+    vt[j] = k * v;
+    ht[j] = h;
+  }
+  for (int j = 0; j < nlat; j++)
+    for (int i = 0; i < nlon; i++) {
+      f.u[(size_t)j * nlon + i] = ut[j] * std::cos(k * gr.half_lon[i] - k * C * 0.0);
+      f.gd[(size_t)j * nlon + i] = g * (ht[j] * std::cos(k * gr.full_lon[i] - k * C * 0.0)) + 5.0e4;
+    }
+  for (int j = 0; j < nlat - 1; j++)
+    for (int i = 0; i < nlon; i++) f.v[(size_t)j * nlon + i] = vt[j] * std::cos(k * gr.full_lon[i] - k * C * 0.0 - 0.5 * pi);
+}
+
 bool set_initial_condition(const Params &p, Fields &f, std::string &notice, std::string &err) {
   f.nlon = p.num_lon;
   f.nlat = p.num_lat;
@@ -246,6 +305,11 @@ bool set_initial_condition(const Params &p, Fields &f, std::string &notice, std:
   } else if (p.test_case == "jet_zonal_flow") {
     jet(g, f);
     notice = "Use jet zonal flow initial condition.";
+  } else if (p.test_case == "shallow_water_waves") {
+    shallow_water_waves(g, f);
+    char buf[96];
+    snprintf(buf, sizeof buf, "%.20g", swe_phase_speed(0));
+    notice = std::string("Use shallow water waves initial condition.\n[Notice]: Phase speed is ") + buf;
   } else {
     err = "Unknown test case " + p.test_case + "!";  // src/dycore_test.F90:41
     return false;

@@ -36,6 +36,9 @@ extern "C" {
 #endif
 
 #define GMD_VERSION 100
+/* |u| on a pole row up to this bound (m/s) is accepted by gmd_set_state and stored as the 0 it stands for (the
+   Shamir-Paldor wave IC evaluates ~1e-146 there, shallow_water_waves_test_mod.F90:215-271) */
+#define GMD_POLE_U_TINY 1.0e-100
 
 enum { GMD_OK = 0, GMD_ERR_NAN = 1, GMD_ERR_ARG = 2, GMD_ERR_CUDA = 3, GMD_ERR_COMM = 4, GMD_ERR_STATE = 5 };
 
@@ -112,7 +115,8 @@ int gmd_get_band(const gmd_model *m, int *row_begin, int *row_end);
 
 /* The IC plugins / restart_read write state(old)%{u,v,gd} and static%ghs (e.g.
    rossby_haurwitz_wave_test_mod.F90:45-83); this uploads them.  ghs may be NULL (= 0).
-   u on the two pole rows must be 0 (true for every reference IC; see DESIGN.md "pole rows"). */
+   u on the two pole rows must be 0 (true for every reference IC; |u| <= GMD_POLE_U_TINY is taken as 0; see
+   DESIGN.md "pole rows"). */
 int gmd_set_state(gmd_model *m, const double *u, const double *v, const double *gd, const double *ghs,
                   int layout);
 /* head of dycore_run (src/dycore_mod.F90:121-129): reset_cos_lat_at_poles, iap_transform, diag_run */

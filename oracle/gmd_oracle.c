@@ -1176,6 +1176,78 @@ void orc_destroy(orc_model *m) {
   free(m);
 }
 
+/* shallow_water_waves_test_mod.F90: Shamir & Paldor (2016) analytic Rossby wave, gH = 5e4, (n, k) = (5, 10).
+   getPhaseSpeed :130-171 (Cardano's formula in complex binary64, as the reference computes it), getPsi :176-210,
+   getAmplitudes :215-271 (waveFlag 0), getFields :276-321 at time 0, set_initial_condition :95-135.
+   The amplitudes are evaluated at the FULL latitudes only; v on half row j uses vTilde(j) of full row j (:307-313). */
+#include <complex.h>
+double orc_swe_phase_speed(int wave_flag) {
+  const double omega = 7.29212e-5, g = 9.80616, a = 6371220.0, H0 = 5.0e3, pi = 3.14159265358979323;
+  const int n = 5, k = 10;
+  const double sigma = 0.5 + pow(0.25 + k * k, 0.5);
+  const double En = g * H0 / (a * a) * ((n + sigma) * (n + sigma));
+  const double Delta0 = 3.0 * (k * k) * En;
+  const double Delta4 = -54.0 * (k * k * k * k) * g * H0 * omega / (a * a);
+  const double r2 = 0.5, r3 = 1.0 / 3.0;
+  double Cj[3], mn, mx, mabs;
+  int j;
+  for (j = 1; j <= 3; j++) {
+    double complex D = cpow((double complex)(Delta4 * Delta4 - 4.0 * (Delta0 * Delta0 * Delta0)), r2);
+    D = cpow(r2 * (Delta4 + D), r3);
+    D = D * cexp(2.0 * pi * I * j * r3);
+    Cj[j - 1] = creal(-r3 / (k * k) * (D + Delta0 / D));
+  }
+  mn = mx = Cj[0];
+  mabs = fabs(Cj[0]);
+  for (j = 1; j < 3; j++) {
+    if (Cj[j] < mn) mn = Cj[j];
+    if (Cj[j] > mx) mx = Cj[j];
+    if (fabs(Cj[j]) < mabs) mabs = fabs(Cj[j]);
+  }
+  return wave_flag == 0 ? -mabs : (wave_flag == 1 ? mx : mn);
+}
+static void ic_shallow_water_waves(orc_model *m) {
+  const int nlon = m->nlon, nlat = m->nlat;
+  const real omega = R_LIT(7.29212e-5), g = R_LIT(9.80616), a = R_LIT(6371220.0), H0 = R_LIT(5.0e3);
+  const real pi = R_LIT(3.14159265358979323);
+  const int k = 10;
+  const real sigma = R_LIT(0.5) + R_POW(R_LIT(0.25) + k * k, R_LIT(0.5)), amp = R_LIT(1.0e-8), o2 = 2 * omega;
+  const real a3 = sigma * (sigma + 1) * (sigma + 2), a4 = a3 * (sigma + 3), a5 = a4 * (sigma + 4);
+  const real C = (real)orc_swe_phase_speed(0);
+  state_t *s = STATE(m, 1);
+  real *ut = alloc1(nlat), *vt = alloc1(nlat), *ht = alloc1(nlat);
+  int i, j;
+  zero2(m, m->ghs);
+  for (j = 1; j <= nlat; j++) {
+    const real lat = m->full_lat[j];
+    const real sl = R_SIN(lat), cl = R_COS(lat), tl = R_TAN(lat);
+    const real s2 = sl * sl, s4 = s2 * s2;   /* sin(lat)**2, **4: integer powers */
+    const real C5 = (4 * a5 * s4 - 20 * a4 * s2 + 15 * a3) * sl / 15;
+    const real C5p = (4 * a5 * s4 - 12 * a4 * s2 + 3 * a3) * cl / 3;
+    const real psi = amp * R_POW(cl, sigma) * C5;
+    const real dpsi = amp * R_POW(cl, sigma) * (-sigma * tl * C5 + C5p);
+    const real Kp = (g * H0 + a * a * (C * C) * (cl * cl)) / (C * cl);
+    const real Km = (g * H0 - a * a * (C * C) * (cl * cl)) / (C * cl);
+    real v = R_POW(o2 * R_FABS(Km) / (cl * cl), R_LIT(0.5)) * psi;
+    const real h = R_POW(o2 * R_FABS(Km) * (a * a) * (H0 * H0), R_LIT(0.5)) / Km *
+                   (dpsi + tl * (R_LIT(0.5) * Kp / Km - o2 / C) * psi);
+    ut[j] = (o2 * sl / C) * v + (g / a / cl / C) * h;
+    vt[j] = k * v;
+    ht[j] = h;
+  }
+  for (j = 1; j <= nlat; j++)
+    for (i = 1; i <= nlon; i++) {
+      A2(s->u, i, j) = ut[j] * R_COS(k * m->half_lon[i] - k * C * 0);
+      A2(s->gd, i, j) = g * (ht[j] * R_COS(k * m->full_lon[i] - k * C * 0)) + R_LIT(5.0e4);
+    }
+  for (j = 1; j <= nlat - 1; j++)
+    for (i = 1; i <= nlon; i++) A2(s->v, i, j) = vt[j] * R_COS(k * m->full_lon[i] - k * C * 0 - R_LIT(0.5) * pi);
+  fill_halo(m, s->gd);
+  fill_halo(m, s->u);
+  fill_halo(m, s->v);
+  free(ut); free(vt); free(ht);
+}
+
 int orc_set_initial_condition(orc_model *m, int test_case, const double *params, int nparams) {
   if (m->pole_reset) {
     snprintf(g_err, sizeof g_err, "initial condition must be set before orc_run_init (B11)");
@@ -1191,6 +1263,7 @@ int orc_set_initial_condition(orc_model *m, int test_case, const double *params,
     case ORC_IC_STEADY_GEOSTROPHIC: ic_steady_geostrophic(m); break;
     case ORC_IC_MOUNTAIN_ZONAL: ic_mountain_zonal(m, (params && nparams >= 1) ? (params[0] != 0.0) : 0); break;
     case ORC_IC_JET_ZONAL: ic_jet_zonal(m); break;
+    case ORC_IC_SHALLOW_WATER_WAVES: ic_shallow_water_waves(m); break;
     default:
       snprintf(g_err, sizeof g_err, "Unknown test case %d!", test_case);
       return 2;

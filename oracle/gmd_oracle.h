@@ -31,7 +31,8 @@ enum {
   ORC_IC_ROSSBY_HAURWITZ = 0,
   ORC_IC_STEADY_GEOSTROPHIC = 1,
   ORC_IC_MOUNTAIN_ZONAL = 2,
-  ORC_IC_JET_ZONAL = 3
+  ORC_IC_JET_ZONAL = 3,
+  ORC_IC_SHALLOW_WATER_WAVES = 4
 };
 
 /* mirrors /dycore_params/ (params_mod.F90:13-98), numeric keys only */
@@ -63,6 +64,8 @@ const char *orc_last_error(void);
 /* test-case plugins (src/test_cases/barotropic/...): write u,v,gd into state(1), ghs into static.
    params: RH -> {R, omg, gd0} (NULL = defaults); mountain -> {smooth_mountain}. */
 int orc_set_initial_condition(orc_model *m, int test_case, const double *params, int nparams);
+/* phase speed (rad/s) of the Shamir-Paldor wave: wave_flag -1 WIG, 0 Rossby, 1 EIG (shallow_water_waves_test_mod.F90:130-171) */
+double orc_swe_phase_speed(int wave_flag);
 /* arbitrary state in compact layout; fills the periodic lon halos as the plugins do */
 int orc_set_state(orc_model *m, const double *u, const double *v, const double *gd, const double *ghs);
 

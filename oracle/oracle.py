@@ -19,7 +19,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 SPLIT = {"none": 0, "": 0, "csp1": 1, "csp2": 2, "isp": 3}
 ADV = {"center_diff": 0, "upwind": 1, "weno": 2}
 PASS = {"all": 0, "fast": 1, "slow": 2}
-IC = {"rossby_haurwitz_wave": 0, "steady_geostrophic_flow": 1, "mountain_zonal_flow": 2, "jet_zonal_flow": 3}
+IC = {"rossby_haurwitz_wave": 0, "steady_geostrophic_flow": 1, "mountain_zonal_flow": 2, "jet_zonal_flow": 3,
+      "shallow_water_waves": 4}
 
 
 class _Cfg(C.Structure):

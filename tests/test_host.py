@@ -149,6 +149,27 @@ def test_ic_plugins_match_oracle(tmp_path, tc, extra, tol):
     assert not u[0].any() and not u[-1].any()   # u = 0 on the pole rows: the invariant gmd_set_state checks
 
 
+def test_shallow_water_waves_plugin_matches_oracle(tmp_path):
+    """shallow_water_waves_test_mod.F90 (Shamir-Paldor Rossby wave): the host plugin against the oracle, and the phase
+    speed notice the reference logs (:109-110)."""
+    nlon, nlat = 72, 37
+    text = f"&dycore_params\n test_case='shallow_water_waves'\n case_name='t'\n num_lon={nlon}\n num_lat={nlat}\n time_step_size=100\n/\n"
+    out_bin = str(tmp_path / "ic.bin")
+    rc, out = selftest("ic", write(tmp_path, text), out_bin)
+    assert rc == 0 and out.startswith("Use shallow water waves initial condition."), out
+    assert "Phase speed is -" in out
+    a = np.fromfile(out_bin)
+    nf, nh = nlon * nlat, nlon * (nlat - 1)
+    u, v, gd, ghs = a[:nf].reshape(nlat, nlon), a[nf:nf + nh].reshape(nlat - 1, nlon), a[nf + nh:2 * nf + nh].reshape(nlat, nlon), a[2 * nf + nh:]
+    o = Oracle(OracleConfig(num_lon=nlon, num_lat=nlat, time_step_size=100.0))
+    o.set_initial_condition("shallow_water_waves")
+    for x, y in zip((u, v, gd), o.state()):
+        assert np.abs(x - y).max() <= 1e-13 * np.abs(y).max()
+    assert not ghs.any()
+    # pole rows: cos(+-pi/2)^(sigma - 1.5) -- not 0, but below GMD_POLE_U_TINY (include/gmd.h)
+    assert 0 < np.abs(u[0]).max() < 1e-100 and 0 < np.abs(u[-1]).max() < 1e-100
+
+
 def test_unknown_test_case_message(tmp_path):
     text = "&dycore_params\n test_case='nope'\n case_name='t'\n num_lon=36\n num_lat=19\n time_step_size=100\n/\n"
     rc, out = selftest("ic", write(tmp_path, text), str(tmp_path / "x"))

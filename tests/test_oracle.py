@@ -341,6 +341,50 @@ def test_jet_profile_matches_scipy_live():
         assert abs(orc.jet_gd_profile(lat) - (g * 1e4 - r)) < 1e-9
 
 
+def test_shallow_water_waves_ic_second_reading():
+    """shallow_water_waves_test_mod.F90 read a second time, in NumPy: the phase speed is the smallest-magnitude root
+    of the cubic dispersion relation (:130-171, solved there by Cardano's formula, here by numpy.roots), the
+    amplitudes :176-271 vectorised, v on half row j with the amplitude of FULL row j (:307-313)."""
+    omega, g, a, H0, n, k = 7.29212e-5, 9.80616, 6371220.0, 5.0e3, 5, 10
+    sigma = 0.5 + np.sqrt(0.25 + k * k)
+    En = g * H0 / a ** 2 * (n + sigma) ** 2
+    # Cj = -(D + Delta0 / D) / (3 k^2) are the roots of  k^2 C^3 - En C - (2 omega g H0 / a^2) = 0
+    roots = np.roots([k * k, 0.0, -En, -2.0 * omega * g * H0 / a ** 2])
+    assert np.abs(roots.imag).max() < 1e-20
+    C = -np.abs(roots.real).min()
+    lib = orc.load("strict")
+    lib.orc_swe_phase_speed.restype = __import__("ctypes").c_double
+    for flag, want in ((0, C), (1, roots.real.max()), (-1, roots.real.min())):
+        assert abs(lib.orc_swe_phase_speed(flag) / want - 1) < 1e-12
+    nlon, nlat = 48, 25
+    o = Oracle(OracleConfig(num_lon=nlon, num_lat=nlat, time_step_size=100.0))
+    o.set_initial_condition("shallow_water_waves")
+    u, v, gd = o.state()
+    pi = 4 * np.arctan(1.0)
+    lat = -0.5 * pi + np.arange(nlat) * (pi / (nlat - 1))
+    lat[-1] = 0.5 * pi
+    lon = np.arange(nlon) * (2 * pi / nlon)
+    sl, cl, tl = np.sin(lat), np.cos(lat), np.tan(lat)
+    a3 = sigma * (sigma + 1) * (sigma + 2)
+    a4 = a3 * (sigma + 3)
+    a5 = a4 * (sigma + 4)
+    C5 = (4 * a5 * sl ** 4 - 20 * a4 * sl ** 2 + 15 * a3) * sl / 15
+    C5p = (4 * a5 * sl ** 4 - 12 * a4 * sl ** 2 + 3 * a3) * cl / 3
+    psi = 1e-8 * cl ** sigma * C5
+    dpsi = 1e-8 * cl ** sigma * (-sigma * tl * C5 + C5p)
+    Kp = (g * H0 + a ** 2 * C ** 2 * cl ** 2) / (C * cl)
+    Km = (g * H0 - a ** 2 * C ** 2 * cl ** 2) / (C * cl)
+    vt = np.sqrt(2 * omega * np.abs(Km) / cl ** 2) * psi
+    ht = np.sqrt(2 * omega * np.abs(Km) * a ** 2 * H0 ** 2) / Km * (dpsi + tl * (0.5 * Kp / Km - 2 * omega / C) * psi)
+    ut = (2 * omega * sl / C) * vt + (g / a / cl / C) * ht
+    want_u = ut[:, None] * np.cos(k * (lon + 0.5 * (2 * pi / nlon)))[None, :]
+    want_v = (k * vt)[:-1, None] * np.cos(k * lon - 0.5 * pi)[None, :]
+    want_gd = g * ht[:, None] * np.cos(k * lon)[None, :] + 5.0e4
+    for got, want in ((u, want_u), (v, want_v), (gd, want_gd)):
+        assert np.abs(got - want).max() <= 1e-11 * np.abs(want).max()
+    assert np.abs(u).max() > 1e-3 and np.abs(gd - 5e4).max() > 0.1   # the wave is there
+
+
 @pytest.mark.parametrize("name", ["rh_36x19_csp2", "rh_72x37_nosplit", "mz_60x31_upwind", "jz_72x37_diffusion",
                                   "sg_48x25_isp", "mz_48x25_weno"])
 def test_oracle_reproduces_committed_golden(name, golden_dir):

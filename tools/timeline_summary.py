@@ -47,6 +47,15 @@ def main():
             a[2] += x["wait_ns"]
         for k, (n, t, w) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             print(f"    {k:28s} x{n:4d}  total {1e-3 * t:8.1f} us  mean {1e-3 * t / n:6.2f} us  mean wait {1e-3 * w / n:6.2f} us")
+        cp = d.get("cap_phases_ns") or []
+        if cp:
+            n = len(cp)
+            m = [sum(r[k] for r in cp) / n * 1e-3 for k in range(len(cp[0]))]
+            print(f"    k_cap phases of CTA 0 (mean of {n} launches): sweep {m[0]:.2f} us, grid barrier {m[1]:.2f} us, "
+                  f"first polar item {m[2]:.2f} us, all items {m[3]:.2f} us")
+            if len(m) >= 9:
+                print(f"      inside the first item: loads + analysis {m[4]:.2f}, cluster sum {m[5]:.2f}, synthesis {m[6]:.2f}, "
+                      f"cluster sum {m[7]:.2f}, stores {m[8]:.2f} us")
         # chain of one fast predict_correct in the middle of the step
         mid = L[len(L) // 2: len(L) // 2 + 12]
         print("    sample (us since step start: kernel start-end wait):")
