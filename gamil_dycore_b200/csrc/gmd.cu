@@ -16,6 +16,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <set>
 #include <string>
 #include <thread>
 #include <vector>
@@ -472,6 +473,18 @@ static int build_tables(gmd_model *m) {
 // launchers
 // ---------------------------------------------------------------------------------------------------------
 typedef void (*stage_fn)(const StageArgs);
+// dynamic shared memory of a stage launch: the row records of rows ja-1 .. jb and the CTA's packet ring
+static inline size_t stage_smem_bytes(int rows_per_cta) {
+  return (size_t)(rows_per_cta + 2) * RC_N * sizeof(double) + (GMD_RING ? RING_BYTES : 0);
+}
+// more than 48 KB of dynamic shared memory is opt-in per kernel
+static int allow_smem(const void *fn) {
+  static std::set<const void *> done;
+  if (!fn || done.count(fn)) return 0;
+  CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+  done.insert(fn);
+  return 0;
+}
 // PUSH instantiations exist for MODE_S3A of the schemes a wide-halo predict_correct supports (not WENO)
 template <int MODE, bool PUSH>
 static stage_fn pick_stage_mode(int pass, int adv) {
@@ -541,6 +554,7 @@ static int launch_cap(gmd_model *m, cap_fn fn, int grid, const StageArgs &b, con
   at[1].val.priority = m->prio_hi;
   lc.attrs = at;
   lc.numAttrs = 2;
+  if (int r = allow_smem((const void *)fn)) return r;
   CK(cudaLaunchKernelEx(&lc, fn, b, p, c));
   return 0;
 }
@@ -899,6 +913,7 @@ static int stage(gmd_model *m, int pass, int mode, const State &E, const State *
       a.push_n_begin = r1 - HALO_S;
     }
   }
+  if ((r = allow_smem((const void *)fn))) return r;
   const bool poleS = (r0 == 0), poleN = (r1 == m->geo.nlat);
   const int R0 = r0 - es, R1 = r1 + en;   // rows of this sweep
   const int li = (pass == PASS_SLOW) ? 1 : 0;
@@ -906,7 +921,7 @@ static int stage(gmd_model *m, int pass, int mode, const State &E, const State *
   // launch geometry
   const int I0 = split ? (poleS ? r0 + m->bs : R0) : R0, I1 = split ? (poleN ? r1 - m->bn : R1) : R1;
   const int rpc = (mode == MODE_S3A) ? m->rows_per_cta_s3a : m->rows_per_cta;
-  const size_t smem_i = (size_t)(rpc + 2) * RC_N * sizeof(double);
+  const size_t smem_i = stage_smem_bytes(rpc);
   const int nci = (I1 - I0 + rpc - 1) / rpc;
   const int ncb = split ? m->nchunks_b : 0;
   const cap_fn cfn = (split && m->cap && m->n_items[li]) ? pick_cap(pass, adv, mode, lz ? lz->kind : 0) : nullptr;
@@ -1662,23 +1677,38 @@ int gmd_create(const gmd_config *cfg, gmd_model **out) {
     // interior (or whole band): one wave of CTAs, as many row chunks as the resident-CTA slots allow
     int per_sm = 0;
     const int pass0 = (cfg->split_scheme == GMD_SPLIT_CSP2 || cfg->split_scheme == GMD_SPLIT_ISP) ? PASS_FAST : PASS_ALL;
+    {   // every stage-kernel variant this configuration can launch (not during a graph capture later on)
+      const int adv = cfg->uv_adv_scheme;
+      bool bad = false;
+      for (int pass = 0; pass < 3 && !bad; pass++) {
+        for (int mode = 0; mode < 4; mode++) bad = bad || allow_smem((const void *)pick_stage(pass, adv, mode));
+        bad = bad || allow_smem((const void *)pick_stage(pass, adv, MODE_S3A, true));
+        if (adv != ADV_WENO)
+          for (int lz = 1; lz <= 2; lz++) bad = bad || allow_smem((const void *)pick_stage_lazy(pass, adv, lz));
+        if (m->cap)
+          for (int mode = 0; mode < 4; mode++)
+            for (int lz = 0; lz <= (mode == MODE_S1 ? 2 : 0); lz++) bad = bad || allow_smem((const void *)pick_cap(pass, adv, mode, lz));
+      }
+      if (bad) { gmd_destroy(m); return GMD_ERR_CUDA; }
+    }
     CKD(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pick_stage(pass0, cfg->uv_adv_scheme, MODE_S2), BX,
-                                                      (size_t)(64 + 2) * RC_N * sizeof(double)));
+                                                      stage_smem_bytes(64)));
     per_sm = std::max(per_sm, 1);
     if (const char *ev = getenv("GMD_CTAS_PER_SM")) per_sm = std::max(1, atoi(ev));
     const int slots = nsm * per_sm;
-    const int max_rows = 48 * 1024 / (RC_N * (int)sizeof(double)) - 2;  // row records must fit 48 KB of smem
+    // row records + packet ring of four resident CTAs must fit the SM's shared memory (taller bands: several waves)
+    const int max_rows = GMD_RING ? 96 : 48 * 1024 / (RC_N * (int)sizeof(double)) - 2;
     const int rows_i = m->split ? m->nr - m->bs - m->bn : m->nr;
     int want = std::max(1, slots / m->nbx);
     m->rows_per_cta = std::min(max_rows, std::max(8, (rows_i + want - 1) / want));
     if (const char *ev = getenv("GMD_ROWS_PER_CTA")) m->rows_per_cta = std::min(max_rows, std::max(1, atoi(ev)));
     m->nchunks = (m->nr + m->rows_per_cta - 1) / m->rows_per_cta;
     m->nchunks_i = (rows_i + m->rows_per_cta - 1) / m->rows_per_cta;
-    m->stage_smem = (size_t)(m->rows_per_cta + 2) * RC_N * sizeof(double);
+    m->stage_smem = stage_smem_bytes(m->rows_per_cta);
     {   // S3a geometry from the occupancy of the S3a kernel itself
       int ps = 0;
       CKD(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ps, pick_stage(pass0, cfg->uv_adv_scheme, MODE_S3A), BX,
-                                                        (size_t)(64 + 2) * RC_N * sizeof(double)));
+                                                        stage_smem_bytes(64)));
       ps = std::max(ps, 1);
       if (const char *ev = getenv("GMD_CTAS_PER_SM")) ps = std::max(1, atoi(ev));
       const int want3 = std::max(1, nsm * ps / m->nbx);
@@ -1690,7 +1720,7 @@ int gmd_create(const gmd_config *cfg, gmd_model **out) {
     m->rows_per_cta_b = (m->nr >= 600) ? 6 : 3;
     if (const char *ev = getenv("GMD_ROWS_PER_CTA_B")) m->rows_per_cta_b = std::max(1, atoi(ev));
     m->nchunks_b = (std::max(m->bs, m->bn) + m->rows_per_cta_b - 1) / m->rows_per_cta_b;
-    m->stage_smem_b = (size_t)(m->rows_per_cta_b + 2) * RC_N * sizeof(double);
+    m->stage_smem_b = stage_smem_bytes(m->rows_per_cta_b);
     if (m->cap) {
       // the launch must be co-resident (grid barrier): as many clusters as there are items, within the device's limit
       int lo = 0, hi = 0;
@@ -2466,12 +2496,13 @@ static int time_stage(gmd_model *m, int pass, int mode, int reps, float *ms_per_
     a.lip = m->d_ip; a.ldt = dt; a.lqcon = m->cfg.qcon_modified;
     fn = pick_stage_lazy(pass, m->cfg.uv_adv_scheme == ADV_WENO ? ADV_CENTER : m->cfg.uv_adv_scheme, slow ? 2 : 1);
   }
+  if ((r = allow_smem((const void *)fn))) return r;
   cudaEvent_t e0, e1;
   CK(cudaEventCreate(&e0));
   CK(cudaEventCreate(&e1));
   CK(cudaEventRecord(e0, m->stream));
   for (int k = 0; k < reps; k++) {
-    fn<<<grid, BX, (size_t)(rpc + 2) * RC_N * sizeof(double), m->stream>>>(a);
+    fn<<<grid, BX, stage_smem_bytes(rpc), m->stream>>>(a);
     m->launches++;
   }
   CK(cudaEventRecord(e1, m->stream));

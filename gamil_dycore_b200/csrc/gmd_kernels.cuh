@@ -527,12 +527,49 @@ template <int PASS, int MODE, int LAZY>
 constexpr int stage_minb() {
   return PASS == 0 /* PASS_ALL */ ? GMD_ALL_MINB : (LAZY ? GMD_LAZY_MINB : (MODE == 2 /* MODE_S3A */ ? GMD_S3A_MINB : GMD_MINB));
 }
+// ---- row-packet ring (cp.async) ---------------------------------------------------------------------------------
+// Everything one iteration of the row loop consumes from global memory -- gd(j+2), U(j+1), V(j+1), ghs(j+1) of the
+// evaluated state, the deferred update's tendency rows, the base-state / previous-tendency rows of row j -- is one
+// PACKET of up to 7 x 16 bytes per lane.  Packets are copied to a per-warp shared-memory ring with cp.async
+// (LDGSTS.128, L2 only) RING_DEPTH - 1 iterations ahead and read back by the lane that copied them, so the only
+// synchronisation is the lane's own cp.async.wait_group.  Against the register prefetch this replaces (one row
+// ahead, 7 double2 of live registers) the loads are in flight 2 rows ahead and the row loop has ~28 registers more.
+#ifndef GMD_RING
+#define GMD_RING 0   // measured slower than the register prefetch (profiles/r2_h_stage_ring_tuning.txt)
+#endif
+#ifndef GMD_RING_DEPTH
+#define GMD_RING_DEPTH 3
+#endif
+constexpr int RING_DEPTH = GMD_RING_DEPTH;
+template <int PASS, int MODE, int LAZY>
+struct Packet {
+  static constexpr bool gh = (PASS != PASS_SLOW);
+  static constexpr bool upd = (MODE == MODE_S1 || MODE == MODE_S2);
+  static constexpr bool q = (upd && !LAZY) || (MODE == MODE_S3A);   // base state (update) or previous tendency (dots)
+  static constexpr int GD2 = 0, U1 = 1, V1 = 2, HS = 3;
+  static constexpr int nE = 3 + (gh ? 1 : 0);
+  static constexpr int TG = nE, TU = nE + (LAZY == 1 ? 1 : 0), TV = TU + 1;
+  static constexpr int nL = LAZY ? (LAZY == 1 ? 3 : 2) : 0;
+  static constexpr int QU = nE + nL, QV = QU + 1, QG = QU + 2;
+  static constexpr int nQ = q ? (gh ? 3 : 2) : 0;
+  static constexpr int NF = nE + nL + nQ;
+};
+constexpr int RING_NF_MAX = 7;
+constexpr size_t RING_BYTES = (size_t)SW * RING_DEPTH * RING_NF_MAX * 32 * 16;   // per CTA
+__device__ __forceinline__ void cp16(unsigned dst, const double *src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
 // The sweep of one CTA: (bx, by, bz) = strip group, row chunk and row range of the CTA, gx = strip groups per chunk
 // row; red: 2 SW doubles, srow: (rows_per_cta + 2) row records of shared memory.  k_stage runs it on its own block
 // index, k_cap (below) on a linear CTA index, followed by the polar rows of the same sweep.
 template <int PASS, int ADV, int MODE, int LAZY, bool PUSH>
 __device__ __forceinline__ void stage_body(const StageArgs &a, const int bx, const int by, const int bz, const int gx,
-                                           double *red, double *srow) {
+                                           double *red, double *srow, double *ringmem) {
   const int nlon = a.g.nlon, nlat = a.g.nlat, r0 = a.g.r0;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int strip = bx * SW + warp;
@@ -591,6 +628,37 @@ __device__ __forceinline__ void stage_body(const StageArgs &a, const int bx, con
       if (r >= 0 && r <= nlat - 1) { b.x = fma(bdt, t.x, b.x); b.y = fma(bdt, t.y, b.y); }
       return b;
     };
+#if GMD_RING
+    typedef Packet<PASS, MODE, LAZY> PK;
+    // this lane's slot of (stage, field): lanes 16 bytes apart => conflict-free LDS.128 / LDGSTS.128
+    D2 *const ring = reinterpret_cast<D2 *>(ringmem) + (size_t)warp * (RING_DEPTH * PK::NF * 32) + lane;
+    const unsigned ring_sa = (unsigned)__cvta_generic_to_shared(ring);
+    // packet of iteration r (the loop below is at row j; AT addresses relative to it) into ring stage st
+    auto issue_packet = [&](const int r, const int st, const int j) {
+      const unsigned d = ring_sa + (unsigned)(st * PK::NF * 32 * 16);
+      cp16(d + PK::GD2 * 512, AT(a.Egd, r + 2));
+      cp16(d + PK::U1 * 512, AT(a.EU, r + 1));
+      cp16(d + PK::V1 * 512, AT(a.EV, r + 1));
+      if (PK::gh) cp16(d + PK::HS * 512, AT(a.ghs, r + 1));
+      if (LAZY) {
+        if (LAZY == 1) cp16(d + PK::TG * 512, AT(a.Lgd, r + 2));
+        cp16(d + PK::TU * 512, AT(a.LU, r + 1));
+        cp16(d + PK::TV * 512, AT(a.LV, r + 1));
+      }
+      if (PK::q && out) {
+        const double *qU = PK::upd ? a.OU : a.PU, *qV = PK::upd ? a.OV : a.PV, *qG = PK::upd ? a.Ogd : a.Pgd;
+        cp16(d + PK::QU * 512, AT(qU, r));
+        cp16(d + PK::QV * 512, AT(qV, r));
+        if (PK::gh) cp16(d + PK::QG * 512, AT(qG, r));
+      }
+    };
+#pragma unroll
+    for (int q = 0; q < RING_DEPTH - 1; q++) {   // the first packets travel with the prologue's own loads
+      if (ja + q < jb) issue_packet(ja + q, q, ja);
+      cp_commit();
+    }
+    int rst = 0;   // ring stage of the current iteration's packet
+#endif
     // ---- prologue: rows ja-1, ja, ja+1 of sqrt(gd); rows ja-1, ja of U, V; gh row ja --------------------
     D2 sm_, s0, sp, sq, u0, up, vm, v0, vp, Um, U0, Up, Vm, V0, Vp;
     D2 g0 = zero2, gp = zero2;
@@ -632,8 +700,8 @@ __device__ __forceinline__ void stage_body(const StageArgs &a, const int bx, con
           st2(AT(a.MV, ja), V0.x, V0.y);
         }
         graw = a1;
-        a2keep = a2;
       }
+      a2keep = a2;
       sm_.x = fast_sqrt(a0.x); sm_.y = fast_sqrt(a0.y);
       s0.x = fast_sqrt(a1.x); s0.y = fast_sqrt(a1.y);
       sp.x = fast_sqrt(a2.x); sp.y = fast_sqrt(a2.y);
@@ -663,6 +731,9 @@ __device__ __forceinline__ void stage_body(const StageArgs &a, const int bx, con
     double Vse_b = shfl_dn1(Vm.x);   // V(i+1, j-1) for column b
     double vse_b = shfl_dn1(vm.x);   // v(i+1, j-1)
     double se_b = shfl_dn1(s0.x);    // s(i+1, j)
+#if GMD_RING
+    D2 n_gd1 = a2keep;   // gd(ja+1) (with the deferred update applied)
+#else
     // first prefetch: gd(ja+2), U(ja+1), V(ja+1), gd(ja+1), ghs(ja+1)
     D2 n_gd2 = ld2(ATK(a.Egd, 2));
     D2 n_U = ld2(ATK(a.EU, 1));
@@ -678,6 +749,7 @@ __device__ __forceinline__ void stage_body(const StageArgs &a, const int bx, con
       n_gd1 = LAZY ? a2keep : ld2(ATK(a.Egd, 1));
       n_hs = ld2(ATK(a.ghs, 1));
     }
+#endif
 
     // measured on B200 (tools/tune_stage.py): the deferred-update variants and S2 are fastest without unrolling (no
     // spills at the 128-register cap), S1 / S3a with two rows per trip
@@ -686,6 +758,25 @@ __device__ __forceinline__ void stage_body(const StageArgs &a, const int bx, con
     for (int j = ja; j < jb; j++) {
       // ---- issue every load of this iteration first: the next row of the evaluated state (consumed one
       //      iteration later) and the operands of this row's update (consumed at the end of this iteration) ---
+#if GMD_RING
+      {   // packet j + DEPTH - 1 goes into the stage read one iteration ago; then this iteration's packet must have landed
+        const int ist = (rst == 0) ? RING_DEPTH - 1 : rst - 1;
+        if (j + (RING_DEPTH - 1) < jb) issue_packet(j + (RING_DEPTH - 1), ist, j);
+        cp_commit();
+        cp_wait<RING_DEPTH - 1>();
+      }
+      const D2 *const pk = ring + rst * (PK::NF * 32);
+      rst = (rst == RING_DEPTH - 1) ? 0 : rst + 1;
+      D2 c_gd2 = pk[PK::GD2 * 32], c_U = pk[PK::U1 * 32], c_V = pk[PK::V1 * 32];
+      const D2 c_gd1 = n_gd1;
+      const D2 c_hs = PK::gh ? pk[PK::HS * 32] : zero2;
+      D2 c_tg = zero2, c_tU = zero2, c_tV = zero2;
+      if (LAZY) {
+        if (LAZY == 1) c_tg = pk[PK::TG * 32];
+        c_tU = pk[PK::TU * 32];
+        c_tV = pk[PK::TV * 32];
+      }
+#else
       D2 c_gd2 = n_gd2, c_U = n_U, c_V = n_V;
       const D2 c_gd1 = n_gd1, c_hs = n_hs;
       const D2 c_tg = n_tg, c_tU = n_tU, c_tV = n_tV;
@@ -700,6 +791,7 @@ __device__ __forceinline__ void stage_body(const StageArgs &a, const int bx, con
           n_tV = ld2(AT(a.LV, j + 2));
         }
       }
+#endif
       if (LAZY) {
         if (LAZY == 1) {
           c_gd2 = combG(c_gd2, c_tg, j + 2);
@@ -721,20 +813,33 @@ __device__ __forceinline__ void stage_body(const StageArgs &a, const int bx, con
       D2 oU = zero2, oV = zero2, oG = zero2, pU = zero2, pV = zero2, pG = zero2;
       D2 wul = zero2, wut = zero2, wvl = zero2, wvt = zero2;
       if (out) {
+#if GMD_RING
+        if (upd && !LAZY) {
+          oU = pk[PK::QU * 32];
+          oV = pk[PK::QV * 32];
+          if (PK::gh) oG = pk[PK::QG * 32];
+        }
+        if (MODE == MODE_S3A) {
+          pU = pk[PK::QU * 32];
+          pV = pk[PK::QV * 32];
+          if (PK::gh) pG = pk[PK::QG * 32];
+        }
+#else
         if (upd && !LAZY) {
           oU = ld2(AT(a.OU, j));
           if (rowV) oV = ld2(AT(a.OV, j));
           if (rowG) oG = ld2(AT(a.Ogd, j));
         }
-        if (upd && LAZY) {  // old state == evaluated state, already on chip
-          oU = U0;
-          oV = V0;
-          oG = graw;
-        }
         if (MODE == MODE_S3A) {
           if (rowU) pU = ld2(AT(a.PU, j));
           if (rowV) pV = ld2(AT(a.PV, j));
           if (rowG) pG = ld2(AT(a.Pgd, j));
+        }
+#endif
+        if (upd && LAZY) {  // old state == evaluated state, already on chip
+          oU = U0;
+          oV = V0;
+          oG = graw;
         }
         if (ADV == ADV_WENO && PASS != PASS_FAST) {
           if (rowU) {
@@ -921,9 +1026,10 @@ __device__ __forceinline__ void stage_body(const StageArgs &a, const int bx, con
 template <int PASS, int ADV, int MODE, int LAZY = 0, bool PUSH = false>
 __global__ void __launch_bounds__(BX, (stage_minb<PASS, MODE, LAZY>())) k_stage(const StageArgs a) {
   __shared__ double red[2 * SW];
-  extern __shared__ double srow[];  // row records of rows ja-1 .. jb: [(jb - ja + 2)][RC_N]
+  extern __shared__ __align__(16) double srow[];  // row records of rows ja-1 .. jb: [(rows_per_cta + 2)][RC_N], then the ring
   trace_in(a.tseq);
-  stage_body<PASS, ADV, MODE, LAZY, PUSH>(a, blockIdx.x, blockIdx.y, blockIdx.z, gridDim.x, red, srow);
+  stage_body<PASS, ADV, MODE, LAZY, PUSH>(a, blockIdx.x, blockIdx.y, blockIdx.z, gridDim.x, red, srow,
+                                          srow + (size_t)(a.rows_per_cta + 2) * RC_N);
   trace_out(a.tseq);
 }
 
@@ -1714,14 +1820,14 @@ __global__ void __launch_bounds__(BX, (stage_minb<PASS, MODE, LAZY>()))
 k_cap(const StageArgs a, const __grid_constant__ PolarArgs p, const CapArgs c) {
   __shared__ double red[2 * SW];
   __shared__ CapSmem sm;
-  extern __shared__ double srow[];
+  extern __shared__ __align__(16) double srow[];
   trace_in(a.tseq);
   GMD_CAP_STAMP(0);
   const int tid = threadIdx.x, b = blockIdx.x;
   for (int k = tid; k < PQ * KF * 2; k += BX) sm.rot[k] = __ldg(p.rot + k);
   if (b < c.n_march) {
     const int bx = b % c.gx, by = (b / c.gx) % c.gy, bz = c.z0 + b / (c.gx * c.gy);
-    stage_body<PASS, ADV, MODE, LAZY, false>(a, bx, by, bz, c.gx, red, srow);
+    stage_body<PASS, ADV, MODE, LAZY, false>(a, bx, by, bz, c.gx, red, srow, srow + (size_t)(a.rows_per_cta + 2) * RC_N);
   }
   GMD_CAP_STAMP(1);
   // ---- grid barrier: the polar items read rows written by any CTA of the sweep --------------------------------
