@@ -61,7 +61,15 @@ contains
     cfg%subcycles = subcycles
     cfg%time_step_size = time_step_size
     cfg%qcon_modified = merge(1, 0, qcon_modified)
-    if (time_scheme /= 'predict_correct') call log_error('Unknown time_scheme ' // trim(time_scheme) // '!')
+    select case (time_scheme)
+    case ('predict_correct')
+      cfg%time_scheme = GMD_TIME_PREDICT_CORRECT
+    case ('runge_kutta')
+      cfg%time_scheme = GMD_TIME_RUNGE_KUTTA
+    case default
+      call log_error('Unknown time_scheme ' // trim(time_scheme) // '!')
+    end select
+    if (time_order /= 0) cfg%time_order = time_order
     select case (split_scheme_in)
     case ('csp1')
       cfg%split_scheme = GMD_SPLIT_CSP1

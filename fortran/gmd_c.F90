@@ -14,6 +14,7 @@ module gmd_c
   integer(c_int), parameter :: GMD_SPLIT_NONE = 0, GMD_SPLIT_CSP1 = 1, GMD_SPLIT_CSP2 = 2, GMD_SPLIT_ISP = 3
   integer(c_int), parameter :: GMD_ADV_CENTER_DIFF = 0, GMD_ADV_UPWIND = 1, GMD_ADV_WENO = 2
   integer(c_int), parameter :: GMD_LAYOUT_COMPACT = 0, GMD_LAYOUT_REFERENCE = 1
+  integer(c_int), parameter :: GMD_TIME_PREDICT_CORRECT = 0, GMD_TIME_RUNGE_KUTTA = 1
 
   ! struct gmd_config (include/gmd.h): numeric keys of /dycore_params/ (src/params_mod.F90:13-98)
   type, bind(c) :: gmd_config
@@ -35,6 +36,12 @@ module gmd_c
     integer(c_int) nranks
     integer(c_int) device
     integer(c_int) polar_band_rows
+    integer(c_int) time_scheme
+    integer(c_int) time_order
+    integer(c_int) use_zonal_reduce
+    integer(c_int) reduce_adv_lon
+    integer(c_int) use_reduce_tend_smooth
+    integer(c_int) zonal_reduce_factors(20)
   end type gmd_config
 
   interface

@@ -21,6 +21,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 SPLIT = {"none": 0, "": 0, "csp1": 1, "csp2": 2, "isp": 3}
 ADV = {"center_diff": 0, "upwind": 1, "weno": 2}
 PASS = {"all": 0, "fast": 1, "slow": 2}
+TIME = {"predict_correct": 0, "runge_kutta": 1}
 LAYOUT_COMPACT, LAYOUT_REFERENCE = 0, 1
 OK, ERR_NAN, ERR_ARG, ERR_CUDA, ERR_COMM, ERR_STATE = range(6)
 
@@ -33,7 +34,9 @@ class _Cfg(C.Structure):
         ("uv_adv_upwind_lat_beta", C.c_double), ("use_zonal_tend_filter", C.c_int),
         ("cutoff", C.c_int * 20), ("use_diffusion", C.c_int), ("diffusion_order", C.c_int),
         ("diffusion_coef", C.c_double), ("rank", C.c_int), ("nranks", C.c_int), ("device", C.c_int),
-        ("polar_band_rows", C.c_int),
+        ("polar_band_rows", C.c_int), ("time_scheme", C.c_int), ("time_order", C.c_int),
+        ("use_zonal_reduce", C.c_int), ("reduce_adv_lon", C.c_int), ("use_reduce_tend_smooth", C.c_int),
+        ("zonal_reduce_factors", C.c_int * 20),
     ]
 
 
@@ -58,6 +61,12 @@ class Config:
     nranks: int = 1
     device: int = -1
     polar_band_rows: int = 0
+    time_scheme: str = "predict_correct"     # or "runge_kutta" (specified extension)
+    time_order: int = 3
+    use_zonal_reduce: bool = False           # moving reduced tendency (specified extension)
+    reduce_adv_lon: bool = False
+    use_reduce_tend_smooth: bool = False
+    zonal_reduce_factors: List[int] = field(default_factory=list)
 
     def to_c(self) -> _Cfg:
         c = _Cfg()
@@ -77,6 +86,13 @@ class Config:
         c.diffusion_coef = self.diffusion_coef
         c.rank, c.nranks, c.device = self.rank, self.nranks, self.device
         c.polar_band_rows = self.polar_band_rows
+        c.time_scheme = TIME[self.time_scheme]
+        c.time_order = self.time_order
+        c.use_zonal_reduce = int(self.use_zonal_reduce)
+        c.reduce_adv_lon = int(self.reduce_adv_lon)
+        c.use_reduce_tend_smooth = int(self.use_reduce_tend_smooth)
+        for k in range(20):
+            c.zonal_reduce_factors[k] = self.zonal_reduce_factors[k] if k < len(self.zonal_reduce_factors) else 0
         return c
 
 

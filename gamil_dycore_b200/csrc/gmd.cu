@@ -174,6 +174,7 @@ struct gmd_model {
   unsigned *d_bar = nullptr;   // grid barrier counters of k_cap
   int cap_ctas = 0;            // CTAs of a k_cap launch (co-resident; a multiple of the cluster size)
   int prio_hi = 0;             // launch priority of k_cap
+  int pdl = 0;                 // GMD_PDL: bit 0: polar rows after their sweep, bit 1: the next sweep after the polar rows
 
   // comm: NCCL (optional) and the peer-memory path (gmd_peer_connect)
   void *comm = nullptr;
@@ -818,16 +819,30 @@ static size_t polar_smem(const gmd_model *m, int *use_q) {
 static void fill_items(PolarArgs &p, const std::vector<unsigned> &v) {
   for (size_t k = 0; k < v.size() && k < (size_t)MAX_ITEMS; k++) p.items[k] = v[k];
 }
-static void launch_polar(gmd_model *m, int mode, int nitems, PolarArgs &p, cudaStream_t st) {
+// launch with the programmatic-stream-serialization attribute (the kernel must call pdl_wait())
+template <typename A>
+static void launch_pdl(void (*fn)(const A), dim3 grid, dim3 block, size_t smem, cudaStream_t st, const A &args) {
+  cudaLaunchConfig_t lc = {};
+  lc.gridDim = grid;
+  lc.blockDim = block;
+  lc.dynamicSmemBytes = smem;
+  lc.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  lc.attrs = at;
+  lc.numAttrs = 1;
+  cudaLaunchKernelEx(&lc, fn, args);
+}
+static void launch_polar(gmd_model *m, int mode, int nitems, PolarArgs &p, cudaStream_t st, bool pdl = false) {
   p.basis = m->d_basis;
   p.rot = m->d_rot;
+  p.pdl = pdl ? 1 : 0;
   const size_t sh = polar_smem(m, &p.use_q);
-  switch (mode) {
-    case MODE_S1: k_polar<MODE_S1><<<nitems, PT, sh, st>>>(p); break;
-    case MODE_S2: k_polar<MODE_S2><<<nitems, PT, sh, st>>>(p); break;
-    case MODE_S3A: k_polar<MODE_S3A><<<nitems, PT, sh, st>>>(p); break;
-    default: k_polar<MODE_EVAL><<<nitems, PT, sh, st>>>(p); break;
-  }
+  void (*fn)(const PolarArgs) = (mode == MODE_S1) ? k_polar<MODE_S1> : (mode == MODE_S2) ? k_polar<MODE_S2>
+                              : (mode == MODE_S3A) ? k_polar<MODE_S3A> : k_polar<MODE_EVAL>;
+  if (pdl) launch_pdl<PolarArgs>(fn, dim3((unsigned)nitems), dim3(PT), sh, st, p);
+  else fn<<<nitems, PT, sh, st>>>(p);
 }
 
 // arguments of the polar rows that belong to the sweep described by `a`
@@ -967,7 +982,13 @@ static int stage(gmd_model *m, int pass, int mode, const State &E, const State *
       if (!m->dry && (r = launch_cap(m, cfn, want_ctas, b, p, c))) return r;
     } else {
       b.tseq = tseq(m, bnames[mode]);
-      if (!m->dry) fn<<<gb, BX, m->stage_smem_b, m->stream>>>(b);
+      // the polar chain (this launch -> polar rows -> the next sweep's launch) with programmatic dependent launches:
+      // S2 / S3a follow the polar rows of the previous sweep with nothing but stream waits in between
+      b.pdl = (m->pdl & 2) && (mode == MODE_S2 || mode == MODE_S3A) && m->n_items[li] ? 1 : 0;
+      if (!m->dry) {
+        if (b.pdl) launch_pdl<StageArgs>(fn, gb, dim3(BX), m->stage_smem_b, m->stream, b);
+        else fn<<<gb, BX, m->stage_smem_b, m->stream>>>(b);
+      }
     }
     if ((r = post_launch(m))) return r;
     if (!m->dry) {   // what the NEXT sweep's interior launch has to wait for on the main stream: this launch, not the
@@ -1000,7 +1021,7 @@ static int stage(gmd_model *m, int pass, int mode, const State &E, const State *
     PolarArgs p;
     polar_args(m, a, lz != nullptr, li, nst, dt, &p);
     p.tseq = tseq(m, "k_polar");
-    if (!m->dry) launch_polar(m, mode, m->n_items[li], p, m->stream);
+    if (!m->dry) launch_polar(m, mode, m->n_items[li], p, m->stream, split && (m->pdl & 1));
     if ((r = post_launch(m))) return r;
   }
   if (mode == MODE_S3A && !fold) {
@@ -1129,24 +1150,32 @@ static int predict_correct(gmd_model *m, double dts, const Carry &in, int pass, 
   return 0;
 }
 
+static int runge_kutta(gmd_model *m, double dts, const State &in, int pass, State *out);
 // csp2_splitting, src/dycore_mod.F90:671-687
 static int csp2(gmd_model *m, const State &in, State *out) {
   int r;
   const double dtm = m->cfg.time_step_size;
   const double fast_dt = dtm / m->cfg.subcycles;
   static const bool no_lazy = getenv("GMD_NO_LAZY") != nullptr;
-  const bool lazy = !no_lazy && m->cfg.uv_adv_scheme != ADV_WENO;
+  const bool rk = (m->cfg.time_scheme == GMD_TIME_RUNGE_KUTTA);
+  const bool lazy = !no_lazy && m->cfg.uv_adv_scheme != ADV_WENO && !rk;
+  // the integrator slot of src/dycore_mod.F90:43-53
+  auto integrator = [&](double dts, const Carry &cin, int pass, bool defer, Carry *cout) -> int {
+    if (!rk) return predict_correct(m, dts, cin, pass, defer, cout);
+    cout->deferred = false;
+    return runge_kutta(m, dts, cin.base, pass, &cout->base);
+  };
   Carry c0, c1;
   c0.base = in;
-  if ((r = predict_correct(m, 0.5 * dtm, c0, PASS_SLOW, lazy, &c1))) return r;
+  if ((r = integrator(0.5 * dtm, c0, PASS_SLOW, lazy, &c1))) return r;
   for (int k = 0; k < m->cfg.subcycles; k++) {
     Carry c2;
-    if ((r = predict_correct(m, fast_dt, c1, PASS_FAST, lazy, &c2))) return r;
+    if ((r = integrator(fast_dt, c1, PASS_FAST, lazy, &c2))) return r;
     release_state(m, &c1.base);
     c1 = c2;
   }
   Carry c3;
-  if ((r = predict_correct(m, 0.5 * dtm, c1, PASS_SLOW, false, &c3))) return r;
+  if ((r = integrator(0.5 * dtm, c1, PASS_SLOW, false, &c3))) return r;
   release_state(m, &c1.base);
   *out = c3.base;
   return 0;
@@ -1163,6 +1192,68 @@ static int dot(gmd_model *m, const double *aU, const double *aV, const double *a
   if (int rj = join(m)) return rj;
   if (!m->dry) k_dot<<<m->ew_blocks, 256, 0, m->stream>>>(m->geo, m->tab, aU, aV, aG, bU, bV, bG, 1, m->d_partials, slot);
   return post_launch(m);
+}
+
+// runge_kutta(dt, in -> *out, pass): the SPECIFIED extension of DESIGN.md section 8 (time_scheme = 'runge_kutta',
+// params_mod.F90:40-44; the reference commit has no such integrator).  Explicit RK in increment form with the energy
+// fix of predict_correct: out = in + beta dt K, K = sum b_i L(phi_i), beta = -2 <K, in> / (dt <K, K>).  Operator
+// evaluations are the fused stage kernel in its store-the-tendency mode, the rest is the tendency algebra of isp.
+static int runge_kutta(gmd_model *m, double dts, const State &in, int pass, State *out) {
+  int r;
+  const bool slow = (pass == PASS_SLOW);
+  Tend &k = m->tendOld, &K = m->tendNew;
+  const size_t bytes = (size_t)m->nr * m->geo.nlon * sizeof(double);
+  State A, B;
+  if ((r = new_state(m, &A, slow ? in.gd : nullptr))) return r;
+  if ((r = new_state(m, &B, slow ? in.gd : nullptr))) return r;
+  auto eval = [&](const State &s) -> int {   // k = L(s); a slow pass leaves dgd = 0 (src/dycore_mod.F90:297)
+    int q;
+    if (slow) {
+      if ((q = join(m))) return q;
+      if (!m->dry) CK(cudaMemsetAsync(k.gd, 0, bytes, m->stream));
+    }
+    return stage(m, pass, MODE_EVAL, s, nullptr, 0, nullptr, &k, nullptr);
+  };
+  auto advance = [&](const Tend &t, double dt, State *to) -> int {
+    int q;
+    if ((q = update(m, in, t, dt, 0, 0, !slow, to))) return q;
+    return exchange_state(m, *to, !slow);
+  };
+  if ((r = eval(in))) return r;                             // k1
+  if ((r = axpby(m, 1.0, k, 0.0, K))) return r;
+  if (m->cfg.time_order == 4) {
+    if ((r = advance(k, dts * 0.5, &A))) return r;
+    if ((r = eval(A))) return r;                            // k2
+    if ((r = axpby(m, 2.0, k, 1.0, K))) return r;
+    if ((r = advance(k, dts * 0.5, &B))) return r;
+    if ((r = eval(B))) return r;                            // k3
+    if ((r = axpby(m, 2.0, k, 1.0, K))) return r;
+    if ((r = advance(k, dts, &A))) return r;
+    if ((r = eval(A))) return r;                            // k4
+    if ((r = axpby(m, 1.0 / 6.0, k, 1.0 / 6.0, K))) return r;
+  } else {
+    if ((r = advance(k, dts, &A))) return r;
+    if ((r = eval(A))) return r;                            // k2
+    if ((r = axpby(m, 1.0, k, 1.0, K))) return r;
+    if ((r = advance(K, dts * 0.25, &B))) return r;
+    if ((r = eval(B))) return r;                            // k3
+    if ((r = axpby(m, 2.0 / 3.0, k, 1.0 / 6.0, K))) return r;
+  }
+  // ip1 = <K, in> (tend-state product, src/types_mod.F90:373-397), ip2 = <K, K>
+  if ((r = dot(m, K.U, K.V, K.gd, in.U, in.V, in.gd, 0))) return r;
+  if ((r = dot(m, K.U, K.V, K.gd, K.U, K.V, K.gd, 1))) return r;
+  {
+    RedArgs ra = red_args(m);
+    ra.tseq = tseq(m, "k_reduce_pairs.rk");
+    if (!m->dry) k_reduce_pairs<<<1, 256, 0, m->stream>>>(m->d_partials, m->ew_blocks, m->d_ip, ra);
+  }
+  if ((r = post_launch(m))) return r;
+  if ((r = allreduce2(m, m->d_ip))) return r;
+  if ((r = update(m, in, K, dts, 3, dts, !slow, &A))) return r;
+  if ((r = exchange_state(m, A, !slow))) return r;
+  release_state(m, &B);
+  *out = A;
+  return 0;
 }
 
 // isp_splitting, src/dycore_mod.F90:689-752 (tend algebra on du, dv, dgd only)
@@ -1345,6 +1436,10 @@ static int one_step_body(gmd_model *m) {
     case GMD_SPLIT_CSP2: r = csp2(m, m->cur, &next); break;
     case GMD_SPLIT_ISP: r = isp(m, m->cur, &next); break;
     default: {
+      if (m->cfg.time_scheme == GMD_TIME_RUNGE_KUTTA) {
+        r = runge_kutta(m, m->cfg.time_step_size, m->cur, PASS_ALL, &next);
+        break;
+      }
       Carry ci, co;
       ci.base = m->cur;
       r = predict_correct(m, m->cfg.time_step_size, ci, PASS_ALL, false, &co);
@@ -1527,6 +1622,8 @@ void gmd_config_defaults(gmd_config *c) {
   c->rank = 0;
   c->nranks = 1;
   c->device = -1;
+  c->time_scheme = GMD_TIME_PREDICT_CORRECT;
+  c->time_order = 3;
 }
 
 void gmd_destroy(gmd_model *m) {
@@ -1571,6 +1668,10 @@ int gmd_create(const gmd_config *cfg, gmd_model **out) {
   if (cfg->uv_adv_scheme < 0 || cfg->uv_adv_scheme > 2)
     return fail(GMD_ERR_ARG, "Unknown uv_adv_scheme %d!", cfg->uv_adv_scheme);  // dycore_mod.F90:104-106
   if (cfg->subcycles < 1) return fail(GMD_ERR_ARG, "subcycles must be >= 1");
+  if (cfg->time_scheme != GMD_TIME_PREDICT_CORRECT && cfg->time_scheme != GMD_TIME_RUNGE_KUTTA)
+    return fail(GMD_ERR_ARG, "Unknown time_scheme %d!", cfg->time_scheme);  // dycore_mod.F90:78-83
+  if (cfg->time_scheme == GMD_TIME_RUNGE_KUTTA && cfg->time_order != 3 && cfg->time_order != 4)
+    return fail(GMD_ERR_ARG, "runge_kutta: time_order must be 3 or 4, got %d", cfg->time_order);
   if (cfg->use_diffusion && cfg->diffusion_order != 2 && cfg->diffusion_order != 4)
     return fail(GMD_ERR_ARG, "diffusion_order must be 2 or 4");
   {  // FFTPACK accepts any n, but the reference's grids are 2^a 3^b 5^c; the projector needs no factorisation
@@ -1643,7 +1744,7 @@ int gmd_create(const gmd_config *cfg, gmd_model **out) {
     m->bn = (m->geo.r1 == nlat) ? K + 3 : 0;
     // wide-halo predict_correct: every band edge needs HALO_N plain rows (no filtered row, no pole row) on both sides
     // -- the rows a neighbour recomputes / receives.  Decided from the configuration alone, so every rank agrees.
-    m->wide = cfg->nranks > 1 && cfg->uv_adv_scheme != GMD_ADV_WENO;
+    m->wide = cfg->nranks > 1 && cfg->uv_adv_scheme != GMD_ADV_WENO && cfg->time_scheme == GMD_TIME_PREDICT_CORRECT;
     for (int q = 1; q < cfg->nranks && m->wide; q++) {
       int e0, e1;
       band_rows(nlat, cfg->nranks, cfg->polar_band_rows, q, &e0, &e1);   // edge between band q-1 and band q: row e0
@@ -1672,6 +1773,9 @@ int gmd_create(const gmd_config *cfg, gmd_model **out) {
     m->split = (m->wide || (m->cap && cfg->nranks == 1 && cap_n1)) && (m->bs + m->bn > 0);
     if (const char *ev = getenv("GMD_NO_SPLIT")) m->split = (atoi(ev) == 0) && (cfg->nranks == 1 || m->wide);
     if (m->bs + m->bn >= m->nr) m->split = false;
+    // measured on two 226-row polar bands (profiles/r2_i_*): 1 -> 0.915 ms per step, 0 -> 0.962, 3 -> 1.015
+    m->pdl = 1;
+    if (const char *ev = getenv("GMD_PDL")) m->pdl = atoi(ev);
     const int nstrips = (nlon + WOUT - 1) / WOUT;
     m->nbx = (nstrips + SW - 1) / SW;
     // interior (or whole band): one wave of CTAs, as many row chunks as the resident-CTA slots allow

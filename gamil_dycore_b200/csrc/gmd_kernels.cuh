@@ -172,6 +172,7 @@ struct StageArgs {
   int medge[2];
   Fold fold;   // MODE_S3A
   int tseq;    // timeline slot + 1 of the launch (GMD_TRACE builds), 0 = none
+  int pdl;     // launched with programmatic stream serialization: wait for the predecessor inside the kernel
 };
 
 // beta of predict_correct (src/dycore_mod.F90:784-785) from the device-resident inner products
@@ -185,6 +186,12 @@ __device__ __forceinline__ double warp_sum(double v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
+
+// programmatic dependent launch (the polar chain of a short band): a kernel launched with the programmatic stream
+// serialization attribute may start before its predecessor in the stream has finished; pdl_wait() returns once the
+// predecessor has completed and its writes are visible (no-op for an ordinary launch)
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // ---------------------------------------------------------------------------------------------------------
 // Peer-memory signalling (latitude bands on the GPUs of one NVLink / NVSwitch node, one process per GPU).
@@ -1028,6 +1035,10 @@ __global__ void __launch_bounds__(BX, (stage_minb<PASS, MODE, LAZY>())) k_stage(
   __shared__ double red[2 * SW];
   extern __shared__ __align__(16) double srow[];  // row records of rows ja-1 .. jb: [(rows_per_cta + 2)][RC_N], then the ring
   trace_in(a.tseq);
+  if (a.pdl) {
+    pdl_trigger();
+    pdl_wait();
+  }
   stage_body<PASS, ADV, MODE, LAZY, PUSH>(a, blockIdx.x, blockIdx.y, blockIdx.z, gridDim.x, red, srow,
                                           srow + (size_t)(a.rows_per_cta + 2) * RC_N);
   trace_out(a.tseq);
@@ -1075,6 +1086,7 @@ struct PolarArgs {
   Fold fold;              // MODE_S3A: see k_stage
   const double *fold_partials;   // start of the whole partials array (this kernel's own pairs start at `partials`)
   int tseq;               // timeline slot + 1 (GMD_TRACE builds), 0 = none
+  int pdl;                // see StageArgs
   unsigned items[MAX_ITEMS];
 };
 
@@ -1199,6 +1211,10 @@ __global__ void __launch_bounds__(PT) k_polar(const __grid_constant__ PolarArgs 
   const ptrdiff_t off = (ptrdiff_t)(j - r0) * (ptrdiff_t)n;
   const bool useq = (MODE != MODE_EVAL) && a.use_q;
   double ip1 = 0.0, ip2 = 0.0;
+  if (a.pdl) {
+    pdl_trigger();
+    pdl_wait();
+  }
 
   if (kind == IT_POLE_S || kind == IT_POLE_N) {
     // src/dycore_mod.F90:572-596: zonal sum of the single adjacent flux, broadcast along the pole row
@@ -1953,6 +1969,7 @@ struct UpdateArgs {
   double dt;
   const double *ip;   // device {ip1, ip2} or NULL
   int qcon, beta_mode;  // beta_mode 0: dt ; 1: dt*beta (predict_correct :786-790) ; 2: dt * (beta*4/dt0) (isp :745-750)
+                        // 3: runge_kutta (specified extension): beta = -2 ip1 / (dt0 ip2), ip1 = <K, state>
   double dt0;
   double *beta_out;   // device scalar, written by one thread
   int with_gd;        // 0: slow pass, gd is shared
@@ -1968,6 +1985,10 @@ __global__ void __launch_bounds__(256) k_update(const UpdateArgs a) {
   if (a.beta_mode) {
     double beta = beta_from_ip(a.ip, a.qcon);
     if (a.beta_mode == 2) beta = beta * 4.0 / a.dt0;
+    if (a.beta_mode == 3) {
+      const double ip1 = a.ip[0], ip2 = a.ip[1];
+      beta = (a.qcon && ip1 != 0.0 && ip2 != 0.0) ? -2.0 * ip1 / (a.dt0 * ip2) : 1.0;
+    }
     dt = a.dt * beta;
     if (blockIdx.x == 0 && threadIdx.x == 0 && a.beta_out) *a.beta_out = beta;
   }

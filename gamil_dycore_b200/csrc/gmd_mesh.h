@@ -7,6 +7,7 @@
 // full rows h and h+1 (0..nlat-2).
 #pragma once
 #include <cmath>
+#include <algorithm>
 #include <vector>
 
 namespace gmd {
@@ -22,6 +23,8 @@ struct HostMesh {
   // filter map
   std::vector<int> flag_full, flag_half, cut_full, cut_half;  // [nlat], [nlat] (half uses nlat-1)
   int cutoff_max = -1;
+  // moving reduced tendency: zonal reduction factor per full / half row, 0 = not reduced
+  std::vector<int> red_full, red_half;
 
   double &at(std::vector<double> &v, int j) { return v[(size_t)(j + TPAD)]; }
   double at(const std::vector<double> &v, int j) const { return v[(size_t)(j + TPAD)]; }
@@ -103,6 +106,26 @@ struct HostMesh {
       if (nlat - k >= 1) flag_full[(size_t)(nlat - k - 1)] = 1;
       if (nlat - k + 1 >= 1 && nlat - k + 1 <= nhalf) flag_half[(size_t)(nlat - k)] = 1;
     }
+  }
+
+  // Row map of the moving reduced tendency: factor r_k of zonal_reduce_factors(k) applies to the k-th full row next to
+  // each pole (the pole row itself has no du and a zonally uniform dgd) and to the k-th half row from each pole.
+  // Returns 0, or the 1-based k of the first factor that is negative or does not divide nlon.
+  int reduce_init(bool use_reduce, const int *rf) {
+    const int nhalf = nlat - 1;
+    red_full.assign((size_t)nlat, 0);
+    red_half.assign((size_t)nlat, 0);
+    if (!use_reduce) return 0;
+    for (int k = 1; k <= 20; k++) {
+      const int r = rf[k - 1];
+      if (r < 0 || (r > 1 && nlon % r != 0)) return k;
+      if (r <= 1) continue;
+      if (k <= nlat - 2) red_full[(size_t)k] = std::max(red_full[(size_t)k], r);                       // south, 0-based row k
+      if (nlat - 1 - k >= 1) red_full[(size_t)(nlat - 1 - k)] = std::max(red_full[(size_t)(nlat - 1 - k)], r);
+      if (k - 1 < nhalf) red_half[(size_t)(k - 1)] = std::max(red_half[(size_t)(k - 1)], r);
+      if (nhalf - k >= 0) red_half[(size_t)(nhalf - k)] = std::max(red_half[(size_t)(nhalf - k)], r);
+    }
+    return 0;
   }
 };
 

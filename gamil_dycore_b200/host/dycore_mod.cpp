@@ -58,8 +58,10 @@ void dycore_init() {
   c.subcycles = params.subcycles;
   c.time_step_size = params.time_step_size;
   c.qcon_modified = params.qcon_modified ? 1 : 0;
-  if (params.time_scheme != "predict_correct")
-    log_error("Unknown time_scheme " + params.time_scheme + "!");  // :78-83
+  if (params.time_scheme == "predict_correct") c.time_scheme = GMD_TIME_PREDICT_CORRECT;
+  else if (params.time_scheme == "runge_kutta") c.time_scheme = GMD_TIME_RUNGE_KUTTA;   // params_mod.F90:40-44 (specified)
+  else log_error("Unknown time_scheme " + params.time_scheme + "!");  // :78-83
+  if (params.time_order) c.time_order = params.time_order;
   if (params.split_scheme == "csp1") c.split_scheme = GMD_SPLIT_CSP1;
   else if (params.split_scheme == "csp2") c.split_scheme = GMD_SPLIT_CSP2;
   else if (params.split_scheme == "isp") c.split_scheme = GMD_SPLIT_ISP;
@@ -75,6 +77,10 @@ void dycore_init() {
   c.uv_adv_upwind_lat_beta = params.uv_adv_upwind_lat_beta;
   c.use_zonal_tend_filter = params.use_zonal_tend_filter ? 1 : 0;
   memcpy(c.zonal_tend_filter_cutoff_wavenumber, params.zonal_tend_filter_cutoff_wavenumber, sizeof(int) * 20);
+  c.use_zonal_reduce = params.use_zonal_reduce ? 1 : 0;
+  c.reduce_adv_lon = params.reduce_adv_lon ? 1 : 0;
+  c.use_reduce_tend_smooth = params.use_reduce_tend_smooth ? 1 : 0;
+  memcpy(c.zonal_reduce_factors, params.zonal_reduce_factors, sizeof(int) * 20);
   c.use_diffusion = params.use_diffusion ? 1 : 0;
   c.diffusion_order = params.diffusion_order;
   c.diffusion_coef = params.diffusion_coef;

@@ -158,7 +158,11 @@ bool params_from_text(const std::string &text, Params &p, std::string &err) {
       }
       continue;
     }
-    if (k == "zonal_tend_filter_cutoff_wavenumber") {
+    if (k == "use_zonal_reduce") LOG(use_zonal_reduce)
+    if (k == "reduce_adv_lon") LOG(reduce_adv_lon)
+    if (k == "use_reduce_tend_smooth") LOG(use_reduce_tend_smooth)
+    if (k == "zonal_tend_filter_cutoff_wavenumber" || k == "zonal_reduce_factors") {
+      int *dst = (k == "zonal_reduce_factors") ? p.zonal_reduce_factors : p.zonal_tend_filter_cutoff_wavenumber;
       if (v.size() > 20) { err = "too many values for " + k; return false; }
       size_t q = 0;
       for (const std::string &tok : v) {  // r*c repeat form allowed
@@ -167,7 +171,7 @@ bool params_from_text(const std::string &text, Params &p, std::string &err) {
         std::string val = tok;
         if (star != std::string::npos) { rep = std::atoi(tok.substr(0, star).c_str()); val = tok.substr(star + 1); }
         if (!to_num(val, x)) { err = "bad value for " + k; return false; }
-        for (int r = 0; r < rep && q < 20; r++) p.zonal_tend_filter_cutoff_wavenumber[q++] = (int)x;
+        for (int r = 0; r < rep && q < 20; r++) dst[q++] = (int)x;
       }
       continue;
     }

@@ -30,6 +30,9 @@ struct Params {
   double uv_adv_upwind_lon_beta = 0.0, uv_adv_upwind_lat_beta = 0.5;
   bool use_zonal_tend_filter = true;
   int zonal_tend_filter_cutoff_wavenumber[20] = {0};
+  // moving reduced tendency (run/namelist.jz_test:16-19 of the reference; specified in DESIGN.md section 8)
+  bool use_zonal_reduce = false, reduce_adv_lon = false, use_reduce_tend_smooth = false;
+  int zonal_reduce_factors[20] = {0};
   bool is_restart_run = false;
   // test-case groups
   double rh_R = 4.0, rh_omg = 7.848e-6, rh_gd0 = 8.0e3 * 9.80616;  // rossby_haurwitz_wave_test_mod.F90:14-18

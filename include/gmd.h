@@ -73,7 +73,18 @@ typedef struct gmd_config {
   int polar_band_rows;             /* nranks >= 3: rows of the first and the last band (they also carry the polar
                                       filter rows and pole caps, whose cost does not shrink with the band), the
                                       other ranks share the rest evenly; 0 = all bands even (default) */
+  /* time_scheme (params_mod.F90:40-44 names 'predict-correct' and 'runge-kutta'; the reference commit implements the
+     first only, dycore_mod.F90:78-83).  GMD_TIME_RUNGE_KUTTA is the specified extension of DESIGN.md section 8. */
+  int time_scheme;                 /* GMD_TIME_*, default predict_correct */
+  int time_order;                  /* params_mod.F90:45; runge_kutta: 3 = SSP-RK3 (default), 4 = classical RK4 */
+  /* moving reduced tendency near the poles (README.md:13, run/namelist.jz_test:16-19; absent from the reference
+     commit: specified in DESIGN.md section 8) */
+  int use_zonal_reduce;            /* default 0 */
+  int reduce_adv_lon;              /* the slow (advection) pass is reduced too; default 0 */
+  int use_reduce_tend_smooth;      /* inner-product rescale of the reduced rows, as the filter blocks do; default 0 */
+  int zonal_reduce_factors[20];    /* factor of the k-th row from each pole; 0 or 1 = not reduced */
 } gmd_config;
+enum { GMD_TIME_PREDICT_CORRECT = 0, GMD_TIME_RUNGE_KUTTA = 1 };
 
 typedef struct gmd_model gmd_model;
 

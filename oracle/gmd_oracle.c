@@ -73,6 +73,8 @@ struct orc_model {
   /* filter */
   int *filter_full, *filter_half;   /* flags, 1-based */
   int *cutoff_full, *cutoff_half;   /* mask cutoff per row, -1 = all-zero mask */
+  int *reduce_full, *reduce_half;   /* zonal reduction factor per row, 0 = none (specified extension) */
+  real *reduce_tmp;
   orc_rfft_plan *plan;
   real *local_x;
   /* diffusion work arrays */
@@ -225,6 +227,30 @@ static int filter_init(orc_model *m) {
       if (nlat - j >= 1 && c > m->cutoff_full[nlat - j]) m->cutoff_full[nlat - j] = c;
       if (nhalf - j + 1 >= 1 && c > m->cutoff_half[nhalf - j + 1]) m->cutoff_half[nhalf - j + 1] = c;
     }
+  }
+  /* moving reduced tendency (specified extension): factor of the k-th full row next to each pole (pole row excluded)
+     and of the k-th half row from each pole; a row is either filtered or reduced */
+  m->reduce_full = (int *)calloc((size_t)nlat + 3, sizeof(int));
+  m->reduce_half = (int *)calloc((size_t)nlat + 3, sizeof(int));
+  m->reduce_tmp = (real *)calloc((size_t)m->nlon + 3, sizeof(real));
+  if (m->cfg.use_zonal_reduce) {
+    for (j = 1; j <= 20; j++) {
+      const int r = m->cfg.zonal_reduce_factors[j - 1];
+      if (r < 0 || (r > 1 && m->nlon % r != 0)) {
+        snprintf(g_err, sizeof g_err, "zonal_reduce_factors(%d)=%d must be >= 0 and divide num_lon=%d", j, r, m->nlon);
+        return 2;
+      }
+      if (r <= 1) continue;
+      if (1 + j <= nlat - 1 && r > m->reduce_full[1 + j]) m->reduce_full[1 + j] = r;
+      if (nlat - j >= 2 && r > m->reduce_full[nlat - j]) m->reduce_full[nlat - j] = r;
+      if (j <= nhalf && r > m->reduce_half[j]) m->reduce_half[j] = r;
+      if (nhalf - j + 1 >= 1 && r > m->reduce_half[nhalf - j + 1]) m->reduce_half[nhalf - j + 1] = r;
+    }
+    for (j = 1; j <= nlat; j++)
+      if ((m->reduce_full[j] > 1 && m->filter_full[j]) || (j <= nhalf && m->reduce_half[j] > 1 && m->filter_half[j])) {
+        snprintf(g_err, sizeof g_err, "row %d is both a zonal filter row and a reduced row", j);
+        return 2;
+      }
   }
   return 0;
 }
@@ -615,6 +641,52 @@ static void smooth_row(orc_model *m, int half, int j, real *d, const real *w1, c
   }
 }
 
+/* Moving reduced tendency of one row -- SPECIFIED extension, not in the reference commit.
+   On a row with reduction factor r the tendency is averaged over the nlon / r cells of the zonally reduced grid and
+   handed back to the fine cells, for each of the r possible offsets of the reduced grid, and the r results are
+   averaged ("moving"): T'(i) = sum_{|d| < r} (r - |d|) T(i + d) / r^2, periodic in i.  sum_i T' = sum_i T.
+   With use_reduce_tend_smooth the row is then rescaled by s1 / s2 exactly as the filter blocks do
+   (src/dycore_mod.F90:212-219), including the |s1| threshold around the whole block. */
+static void reduce_average(orc_model *m, int j, int r, real *d) {
+  const int nlon = m->nlon;
+  real acc;
+  int i, dd, ii;
+  for (i = 1; i <= nlon; i++) {
+    acc = 0;
+    for (dd = -(r - 1); dd <= r - 1; dd++) {
+      ii = i + dd;
+      if (ii < 1) ii += nlon;
+      if (ii > nlon) ii -= nlon;
+      acc = acc + (real)(r - (dd < 0 ? -dd : dd)) * A2(d, ii, j);
+    }
+    m->reduce_tmp[i] = acc / (real)(r * r);
+  }
+  for (i = 1; i <= nlon; i++) A2(d, i, j) = m->reduce_tmp[i];
+}
+static void reduce_row(orc_model *m, int j, int r, real *d, const real *w1, const real *w2) {
+  const int nlon = m->nlon, smooth = m->cfg.use_reduce_tend_smooth;
+  real s1 = 0, s2 = 0;
+  int i;
+  if (smooth) {
+    for (i = 1; i <= nlon; i++)
+      s1 = s1 + A2(d, i, j) * (w2 ? (A2(w1, i, j) + A2(w2, i, j)) : A2(w1, i, j));
+    if (!(R_FABS(s1) > filter_inner_product_threshold)) return;
+  }
+  reduce_average(m, j, r, d);
+  if (smooth) {
+    for (i = 1; i <= nlon; i++)
+      s2 = s2 + A2(d, i, j) * (w2 ? (A2(w1, i, j) + A2(w2, i, j)) : A2(w1, i, j));
+    for (i = 1; i <= nlon; i++) A2(d, i, j) = A2(d, i, j) * s1 / s2;
+  }
+}
+/* what space_operators does with a finished tendency row: the reference's SMOOTHING block on a filter row, the
+   moving reduced tendency on a reduced row (fast and unsplit passes; the slow pass only with reduce_adv_lon) */
+static void finish_row(orc_model *m, int half, int j, int pass, real *d, const real *w1, const real *w2) {
+  const int r = half ? m->reduce_half[j] : m->reduce_full[j];
+  if (half ? m->filter_half[j] : m->filter_full[j]) smooth_row(m, half, j, d, w1, w2);
+  else if (r > 1 && (pass != ORC_PASS_SLOW || m->cfg.reduce_adv_lon)) reduce_row(m, j, r, d, w1, w2);
+}
+
 static void zero2(const orc_model *m, real *a) { memset(a, 0, m->NE * sizeof(real)); }
 
 static void space_operators(orc_model *m, state_t *s, tend_t *t, int pass) {
@@ -632,17 +704,17 @@ static void space_operators(orc_model *m, state_t *s, tend_t *t, int pass) {
       for (j = 2; j <= nlat - 1; j++) {
         for (i = 1; i <= nlon; i++)
           A2(t->du, i, j) = -A2(t->u_adv_lon, i, j) - A2(t->u_adv_lat, i, j) + A2(t->fv, i, j) - A2(t->u_pgf, i, j);
-        if (m->filter_full[j]) smooth_row(m, 0, j, t->du, s->iu, NULL);
+        finish_row(m, 0, j, pass, t->du, s->iu, NULL);
       }
       for (j = 1; j <= nlat - 1; j++) {
         for (i = 1; i <= nlon; i++)
           A2(t->dv, i, j) = -A2(t->v_adv_lon, i, j) - A2(t->v_adv_lat, i, j) - A2(t->fu, i, j) - A2(t->v_pgf, i, j);
-        if (m->filter_half[j]) smooth_row(m, 1, j, t->dv, s->iv, NULL);
+        finish_row(m, 1, j, pass, t->dv, s->iv, NULL);
       }
       for (j = 1; j <= nlat; j++) {
         for (i = 1; i <= nlon; i++)
           A2(t->dgd, i, j) = -A2(t->mass_div_lon, i, j) - A2(t->mass_div_lat, i, j);
-        if (m->filter_full[j]) smooth_row(m, 0, j, t->dgd, s->gd, m->ghs);
+        finish_row(m, 0, j, pass, t->dgd, s->gd, m->ghs);
       }
       break;
     case ORC_PASS_SLOW:
@@ -650,11 +722,11 @@ static void space_operators(orc_model *m, state_t *s, tend_t *t, int pass) {
       meridional_momentum_advection_operator(m, s, t);
       for (j = 2; j <= nlat - 1; j++) {
         for (i = 1; i <= nlon; i++) A2(t->du, i, j) = -A2(t->u_adv_lon, i, j) - A2(t->u_adv_lat, i, j);
-        if (m->filter_full[j]) smooth_row(m, 0, j, t->du, s->iu, NULL);
+        finish_row(m, 0, j, pass, t->du, s->iu, NULL);
       }
       for (j = 1; j <= nlat - 1; j++) {
         for (i = 1; i <= nlon; i++) A2(t->dv, i, j) = -A2(t->v_adv_lon, i, j) - A2(t->v_adv_lat, i, j);
-        if (m->filter_half[j]) smooth_row(m, 1, j, t->dv, s->iv, NULL);
+        finish_row(m, 1, j, pass, t->dv, s->iv, NULL);
       }
       zero2(m, t->dgd);
       break;
@@ -667,15 +739,15 @@ static void space_operators(orc_model *m, state_t *s, tend_t *t, int pass) {
       for (j = 1; j <= nlat; j++) {
         for (i = 1; i <= nlon; i++)
           A2(t->dgd, i, j) = -A2(t->mass_div_lon, i, j) - A2(t->mass_div_lat, i, j);
-        if (m->filter_full[j]) smooth_row(m, 0, j, t->dgd, s->gd, m->ghs);
+        finish_row(m, 0, j, pass, t->dgd, s->gd, m->ghs);
       }
       for (j = 2; j <= nlat - 1; j++) {
         for (i = 1; i <= nlon; i++) A2(t->du, i, j) = A2(t->fv, i, j) - A2(t->u_pgf, i, j);
-        if (m->filter_full[j]) smooth_row(m, 0, j, t->du, s->iu, NULL);
+        finish_row(m, 0, j, pass, t->du, s->iu, NULL);
       }
       for (j = 1; j <= nlat - 1; j++) {
         for (i = 1; i <= nlon; i++) A2(t->dv, i, j) = -A2(t->fu, i, j) - A2(t->v_pgf, i, j);
-        if (m->filter_half[j]) smooth_row(m, 1, j, t->dv, s->iv, NULL);
+        finish_row(m, 1, j, pass, t->dv, s->iv, NULL);
       }
       break;
   }
@@ -769,17 +841,76 @@ static void state_copy(const orc_model *m, const state_t *a, state_t *b) {
   memcpy(b->iu, a->iu, nb); memcpy(b->iv, a->iv, nb); memcpy(b->igd, a->igd, nb);
 }
 
+static void tend_copy(const orc_model *m, const tend_t *a, tend_t *b) {
+  const size_t nb = m->NE * sizeof(real);
+  memcpy(b->du, a->du, nb); memcpy(b->dv, a->dv, nb); memcpy(b->dgd, a->dgd, nb);
+}
+static void tend_axpby(const orc_model *m, real alpha, const tend_t *x, real beta, tend_t *y) { /* y = beta y + alpha x */
+  size_t k;
+  for (k = 0; k < m->NE; k++) {
+    y->du[k] = beta * y->du[k] + alpha * x->du[k];
+    y->dv[k] = beta * y->dv[k] + alpha * x->dv[k];
+    y->dgd[k] = beta * y->dgd[k] + alpha * x->dgd[k];
+  }
+}
+
+/* ---- runge_kutta: SPECIFIED extension, not in the reference commit -------------
+   The integrator slot of dycore_mod.F90:43-53,78-83 (`time_scheme = 'runge_kutta'`, params_mod.F90:40-44) filled with
+   an explicit Runge-Kutta step in increment form, phi' = phi + beta dt K, K = sum b_i k_i, k_i = L(phi_i) from the same
+   space_operators / update_state / tend algebra the reference has, and the energy fix of predict_correct carried
+   over:  E(phi + beta dt K) = E(phi) + 2 beta dt <K, phi> + beta^2 dt^2 <K, K>  (E = the quadratic form of
+   inner_product_tend_state, types_mod.F90:373-397), so beta = -2 <K, phi> / (dt <K, K>) keeps it (qcon_modified).
+     time_order 3 (Shu-Osher SSP-RK3): phi1 = phi + dt k1; phi2 = phi + dt/4 (k1 + k2); K = 1/6 (k1 + k2) + 2/3 k3
+     time_order 4 (classical RK4):     phi1 = phi + dt/2 k1; phi2 = phi + dt/2 k2; phi3 = phi + dt k3;
+                                       K = 1/6 ((k1 + 2 k2 + 2 k3) + k4)
+   Scratch: tend slots -2 (K) and -1 (k_i) -- isp's, which never runs through the integrator slot. */
+static void runge_kutta(orc_model *m, real dt, int old, int new_, int pass) {
+  tend_t *K = TEND(m, -2), *k = TEND(m, -1);
+  state_t *S0 = STATE(m, old);
+  state_t *S1 = STATE(m, new_);
+  real ip1, ip2, beta;
+  space_operators(m, S0, k, pass);                       /* k1 */
+  tend_copy(m, k, K);
+  if (m->cfg.time_order == 4) {
+    update_state(m, dt * R_LIT(0.5), k, S0, S1);
+    space_operators(m, S1, k, pass);                     /* k2 */
+    tend_axpby(m, R_LIT(2.0), k, R_LIT(1.0), K);
+    update_state(m, dt * R_LIT(0.5), k, S0, S1);
+    space_operators(m, S1, k, pass);                     /* k3 */
+    tend_axpby(m, R_LIT(2.0), k, R_LIT(1.0), K);
+    update_state(m, dt, k, S0, S1);
+    space_operators(m, S1, k, pass);                     /* k4 */
+    tend_axpby(m, R_LIT(1.0) / R_LIT(6.0), k, R_LIT(1.0) / R_LIT(6.0), K);
+  } else {
+    update_state(m, dt, k, S0, S1);
+    space_operators(m, S1, k, pass);                     /* k2 */
+    tend_axpby(m, R_LIT(1.0), k, R_LIT(1.0), K);
+    update_state(m, dt * R_LIT(0.25), K, S0, S1);
+    space_operators(m, S1, k, pass);                     /* k3 */
+    tend_axpby(m, R_LIT(2.0) / R_LIT(3.0), k, R_LIT(1.0) / R_LIT(6.0), K);
+  }
+  ip1 = inner_product_tend_state(m, K, S0);
+  ip2 = inner_product_tend_tend(m, K, K);
+  beta = (m->cfg.qcon_modified && ip1 != 0 && ip2 != 0) ? -R_LIT(2.0) * ip1 / (dt * ip2) : R_LIT(1.0);
+  m->beta = beta;
+  update_state(m, dt * beta, K, S0, S1);
+}
+static void integrator(orc_model *m, real dt, int old, int new_, int pass) {   /* dycore_mod.F90:43-53 */
+  if (m->cfg.time_scheme == ORC_TIME_RUNGE_KUTTA) runge_kutta(m, dt, old, new_, pass);
+  else predict_correct(m, dt, old, new_, pass);
+}
+
 /* ---- csp2_splitting, src/dycore_mod.F90:671-687 ---------------------------------------------------- */
 static void csp2_splitting(orc_model *m) {
   const real dtm = (real)m->cfg.time_step_size;
   const real fast_dt = dtm / m->cfg.subcycles;
   int t1 = 0, t2 = m->old_idx, sub, tmp;
-  predict_correct(m, R_LIT(0.5) * dtm, m->old_idx, t1, ORC_PASS_SLOW);
+  integrator(m, R_LIT(0.5) * dtm, m->old_idx, t1, ORC_PASS_SLOW);
   for (sub = 1; sub <= m->cfg.subcycles; sub++) {
-    predict_correct(m, fast_dt, t1, t2, ORC_PASS_FAST);
+    integrator(m, fast_dt, t1, t2, ORC_PASS_FAST);
     tmp = t1; t1 = t2; t2 = tmp;
   }
-  predict_correct(m, R_LIT(0.5) * dtm, t1, m->new_idx, ORC_PASS_SLOW);
+  integrator(m, R_LIT(0.5) * dtm, t1, m->new_idx, ORC_PASS_SLOW);
 }
 
 /* ---- isp_splitting, src/dycore_mod.F90:689-752 ----------------------------------------------------- */
@@ -883,6 +1014,15 @@ static void ordinary_diffusion(orc_model *m, real dt, state_t *s) {
     }
   for (j = 1; j <= nlat - 1; j++)
     if (m->filter_half[j]) filter_array_at_half_lat(m, j, vd);
+  /* specified extension: the diffusion tendencies of reduced rows get the moving reduced average (no rescale), as the
+     filter rows get the plain filter above */
+  for (j = 2; j <= nlat - 1; j++)
+    if (m->reduce_full[j] > 1) {
+      reduce_average(m, j, m->reduce_full[j], gdd);
+      reduce_average(m, j, m->reduce_full[j], ud);
+    }
+  for (j = 1; j <= nlat - 1; j++)
+    if (m->reduce_half[j] > 1) reduce_average(m, j, m->reduce_half[j], vd);
   sign = ((norder + 1) % 2 == 0) ? 1 : -1;
   for (j = 1; j <= nlat; j++) {
     for (i = 1; i <= nlon; i++) A2(s->gd, i, j) = A2(s->gd, i, j) + sign * dt * coef * A2(gdd, i, j);
@@ -899,7 +1039,7 @@ static void time_integrate(orc_model *m) {
   switch (m->cfg.split_scheme) {
     case ORC_SPLIT_CSP2: csp2_splitting(m); break;
     case ORC_SPLIT_ISP: isp_splitting(m); break;
-    default: predict_correct(m, (real)m->cfg.time_step_size, m->old_idx, m->new_idx, ORC_PASS_ALL);
+    default: integrator(m, (real)m->cfg.time_step_size, m->old_idx, m->new_idx, ORC_PASS_ALL);
   }
   if (m->cfg.use_diffusion) ordinary_diffusion(m, (real)m->cfg.time_step_size, STATE(m, m->new_idx));
 }
@@ -1168,6 +1308,7 @@ void orc_destroy(orc_model *m) {
   for (k = 0; k < 5; k++) free_tend(&m->tend_[k]);
   free(m->ghs);
   free(m->filter_full); free(m->filter_half); free(m->cutoff_full); free(m->cutoff_half);
+  free(m->reduce_full); free(m->reduce_half); free(m->reduce_tmp);
   orc_rfft_plan_destroy(m->plan);
   free(m->local_x);
   free(m->dud); free(m->dvd); free(m->dgdd); free(m->du_); free(m->dv_); free(m->dgd_);

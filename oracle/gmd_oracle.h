@@ -51,7 +51,18 @@ typedef struct orc_config {
   int use_diffusion;
   int diffusion_order;         /* default 2 */
   double diffusion_coef;
+  /* time_scheme (params_mod.F90:40-44 lists 'predict-correct' and 'runge-kutta'; the commit implements the first only,
+     dycore_mod.F90:78-83).  ORC_TIME_RUNGE_KUTTA is the SPECIFIED extension of DESIGN.md section 8: parity unpinned. */
+  int time_scheme;             /* ORC_TIME_* ; default predict_correct */
+  int time_order;              /* runge_kutta: 3 (SSP-RK3, default) or 4 (classical RK4) */
+  /* moving reduced tendency (README.md:13, run/namelist.jz_test:16-19; absent from the commit: SPECIFIED extension of
+     DESIGN.md section 8, parity unpinned) */
+  int use_zonal_reduce;
+  int reduce_adv_lon;
+  int use_reduce_tend_smooth;
+  int zonal_reduce_factors[20];
 } orc_config;
+enum { ORC_TIME_PREDICT_CORRECT = 0, ORC_TIME_RUNGE_KUTTA = 1 };
 
 typedef struct orc_model orc_model;
 typedef struct orc_rfft_plan orc_rfft_plan;

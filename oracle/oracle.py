@@ -19,6 +19,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 SPLIT = {"none": 0, "": 0, "csp1": 1, "csp2": 2, "isp": 3}
 ADV = {"center_diff": 0, "upwind": 1, "weno": 2}
 PASS = {"all": 0, "fast": 1, "slow": 2}
+TIME = {"predict_correct": 0, "runge_kutta": 1}
 IC = {"rossby_haurwitz_wave": 0, "steady_geostrophic_flow": 1, "mountain_zonal_flow": 2, "jet_zonal_flow": 3,
       "shallow_water_waves": 4}
 
@@ -30,7 +31,9 @@ class _Cfg(C.Structure):
         ("uv_adv_scheme", C.c_int), ("uv_adv_upwind_lon_beta", C.c_double),
         ("uv_adv_upwind_lat_beta", C.c_double), ("use_zonal_tend_filter", C.c_int),
         ("cutoff", C.c_int * 20), ("use_diffusion", C.c_int), ("diffusion_order", C.c_int),
-        ("diffusion_coef", C.c_double),
+        ("diffusion_coef", C.c_double), ("time_scheme", C.c_int), ("time_order", C.c_int),
+        ("use_zonal_reduce", C.c_int), ("reduce_adv_lon", C.c_int), ("use_reduce_tend_smooth", C.c_int),
+        ("zonal_reduce_factors", C.c_int * 20),
     ]
 
 
@@ -51,6 +54,12 @@ class OracleConfig:
     use_diffusion: bool = False
     diffusion_order: int = 2
     diffusion_coef: float = 0.0
+    time_scheme: str = "predict_correct"     # or "runge_kutta" (specified extension)
+    time_order: int = 3                      # runge_kutta: 3 (SSP-RK3) or 4 (classical)
+    use_zonal_reduce: bool = False           # moving reduced tendency (specified extension)
+    reduce_adv_lon: bool = False
+    use_reduce_tend_smooth: bool = False
+    zonal_reduce_factors: List[int] = field(default_factory=list)
 
     def to_c(self) -> _Cfg:
         c = _Cfg()
@@ -67,6 +76,13 @@ class OracleConfig:
         c.use_diffusion = int(self.use_diffusion)
         c.diffusion_order = self.diffusion_order
         c.diffusion_coef = self.diffusion_coef
+        c.time_scheme = TIME[self.time_scheme]
+        c.time_order = self.time_order
+        c.use_zonal_reduce = int(self.use_zonal_reduce)
+        c.reduce_adv_lon = int(self.reduce_adv_lon)
+        c.use_reduce_tend_smooth = int(self.use_reduce_tend_smooth)
+        for k in range(20):
+            c.zonal_reduce_factors[k] = self.zonal_reduce_factors[k] if k < len(self.zonal_reduce_factors) else 0
         return c
 
 
@@ -131,6 +147,8 @@ def load(kind: str = "strict") -> C.CDLL:
     lib.orc_rfft_backward_f64.argtypes = [C.c_int, D]
     lib.orc_rfft_factors.argtypes = [C.c_int, I, C.c_int]
     lib.orc_real_bytes.restype = C.c_int
+    lib.orc_swe_phase_speed.argtypes = [C.c_int]
+    lib.orc_swe_phase_speed.restype = C.c_double
     _LIBS[kind] = lib
     return lib
 

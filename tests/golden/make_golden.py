@@ -47,6 +47,13 @@ CASES = {
     "mz_60x32_diff4": (dict(num_lon=60, num_lat=32, time_step_size=600.0, split_scheme="none", use_diffusion=True,
                             diffusion_order=4, diffusion_coef=1.0e15, zonal_tend_filter_cutoff_wavenumber=[4, 4]),
                        "mountain_zonal_flow", 4),
+    # runge_kutta: the specified extension of DESIGN.md section 8 (not a reference feature; pins CUDA to the oracle)
+    "mz_60x31_rk3_csp2": (dict(num_lon=60, num_lat=31, time_step_size=900.0, subcycles=4, split_scheme="csp2",
+                               time_scheme="runge_kutta", time_order=3, zonal_tend_filter_cutoff_wavenumber=[4, 4, 4]),
+                          "mountain_zonal_flow", 4),
+    "sw_72x37_rk4_nosplit": (dict(num_lon=72, num_lat=37, time_step_size=150.0, split_scheme="none",
+                                  time_scheme="runge_kutta", time_order=4, zonal_tend_filter_cutoff_wavenumber=[12, 12, 12]),
+                             "shallow_water_waves", 4),
 }
 
 

@@ -386,7 +386,7 @@ def test_shallow_water_waves_ic_second_reading():
 
 
 @pytest.mark.parametrize("name", ["rh_36x19_csp2", "rh_72x37_nosplit", "mz_60x31_upwind", "jz_72x37_diffusion",
-                                  "sg_48x25_isp", "mz_48x25_weno"])
+                                  "sg_48x25_isp", "mz_48x25_weno", "mz_60x31_rk3_csp2", "sw_72x37_rk4_nosplit"])
 def test_oracle_reproduces_committed_golden(name, golden_dir):
     from golden.make_golden import CASES
     d = np.load(golden_dir / f"case_{name}.npz")
