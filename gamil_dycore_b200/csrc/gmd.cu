@@ -382,6 +382,8 @@ static int build_tables(gmd_model *m) {
     unsigned char f = 0;
     if (j >= 1 && j <= nlat - 2 && M.flag_full[(size_t)j]) f |= FL_DU | FL_DGD;
     if (j <= nlat - 2 && M.flag_half[(size_t)j]) f |= FL_DV;
+    if (j >= 1 && j <= nlat - 2 && M.red_full[(size_t)j] > 1) f |= (FL_DU | FL_DGD) << FL_REDUCE_SHIFT;
+    if (j <= nlat - 2 && M.red_half[(size_t)j] > 1) f |= FL_DV << FL_REDUCE_SHIFT;
     if (j == 0 || j == nlat - 1) f |= FL_POLE;
     fl[(size_t)(j + TPAD)] = f;
   }
@@ -458,6 +460,23 @@ static int build_tables(gmd_model *m) {
       const unsigned v = pack_item(IT_DV, j, M.cut_half[(size_t)j]);
       it[0].push_back(v);
       it[1].push_back(v);
+      it[2].push_back(v);
+    }
+    // rows of the moving reduced tendency (never also filter rows: gmd_create): fast / unsplit passes, the slow pass
+    // with reduce_adv_lon, the diffusion tendencies always
+    if (fullrow && M.red_full[(size_t)j] > 1) {
+      const unsigned a = pack_reduce_item(IT_DU, j, M.red_full[(size_t)j]);
+      const unsigned g = pack_reduce_item(IT_DGD, j, M.red_full[(size_t)j]);
+      it[0].push_back(a);
+      it[0].push_back(g);
+      if (m->cfg.reduce_adv_lon) it[1].push_back(a);
+      it[2].push_back(a);
+      it[2].push_back(g);
+    }
+    if (j <= nlat - 2 && M.red_half[(size_t)j] > 1) {
+      const unsigned v = pack_reduce_item(IT_DV, j, M.red_half[(size_t)j]);
+      it[0].push_back(v);
+      if (m->cfg.reduce_adv_lon) it[1].push_back(v);
       it[2].push_back(v);
     }
     if (j == 0) it[0].push_back(pack_item(IT_POLE_S, j, -1));
@@ -866,6 +885,7 @@ static void polar_args(gmd_model *m, const StageArgs &a, bool lazy, int li, int 
   p.fold_partials = m->d_partials;
   p.basis = m->d_basis;
   p.rot = m->d_rot;
+  p.reduce_smooth = m->cfg.use_reduce_tend_smooth;
 }
 
 // one fused operator evaluation (+ update / store / dots) of state E
@@ -900,6 +920,7 @@ static int stage(gmd_model *m, int pass, int mode, const State &E, const State *
   a.beta_lon = m->cfg.uv_adv_upwind_lon_beta;
   a.beta_lat = m->cfg.uv_adv_upwind_lat_beta;
   a.partials = m->d_partials;
+  a.flmask = 0x0fu | ((pass != PASS_SLOW || m->cfg.reduce_adv_lon) ? 0xf0u : 0u);
   // the inner products are finalised (and all-reduced over peer memory) by the last CTA of the S3a launches; over
   // NCCL the all-reduce is a library call, so the partials are reduced by a launch of their own
   // (worth it once a band is short -- measured: 3.6 % at 225 rows per rank, nothing at 900 and above, where the
@@ -1188,60 +1209,69 @@ static int axpby(gmd_model *m, double alpha, const Tend &x, double beta, Tend &y
   return post_launch(m);
 }
 static int dot(gmd_model *m, const double *aU, const double *aV, const double *aG, const double *bU, const double *bV,
-               const double *bG, int slot) {
+               const double *bG, int slot, int accumulate = 0) {
   if (int rj = join(m)) return rj;
-  if (!m->dry) k_dot<<<m->ew_blocks, 256, 0, m->stream>>>(m->geo, m->tab, aU, aV, aG, bU, bV, bG, 1, m->d_partials, slot);
+  if (!m->dry) k_dot<<<m->ew_blocks, 256, 0, m->stream>>>(m->geo, m->tab, aU, aV, aG, bU, bV, bG, 1, m->d_partials, slot, accumulate);
   return post_launch(m);
 }
 
 // runge_kutta(dt, in -> *out, pass): the SPECIFIED extension of DESIGN.md section 8 (time_scheme = 'runge_kutta',
 // params_mod.F90:40-44; the reference commit has no such integrator).  Explicit RK in increment form with the energy
-// fix of predict_correct: out = in + beta dt K, K = sum b_i L(phi_i), beta = -2 <K, in> / (dt <K, K>).  Operator
+// fix of predict_correct: out = in + beta dt K, K = sum b_i L(phi_i), beta = (sum of the stage tendency products that
+// equal -3/dt <K, in> under the stage antisymmetries) / (3 <K, K>) -- see oracle/gmd_oracle.c runge_kutta.  Operator
 // evaluations are the fused stage kernel in its store-the-tendency mode, the rest is the tendency algebra of isp.
 static int runge_kutta(gmd_model *m, double dts, const State &in, int pass, State *out) {
   int r;
   const bool slow = (pass == PASS_SLOW);
-  Tend &k = m->tendOld, &K = m->tendNew;
+  if (!m->tendA.U && (r = new_tend(m, &m->tendA))) return r;
+  Tend *ka = &m->tendOld, *kb = &m->tendA;
+  Tend &K = m->tendNew;
   const size_t bytes = (size_t)m->nr * m->geo.nlon * sizeof(double);
   State A, B;
   if ((r = new_state(m, &A, slow ? in.gd : nullptr))) return r;
   if ((r = new_state(m, &B, slow ? in.gd : nullptr))) return r;
-  auto eval = [&](const State &s) -> int {   // k = L(s); a slow pass leaves dgd = 0 (src/dycore_mod.F90:297)
+  auto eval = [&](const State &s, Tend *k) -> int {   // k = L(s); a slow pass leaves dgd = 0 (src/dycore_mod.F90:297)
     int q;
     if (slow) {
       if ((q = join(m))) return q;
-      if (!m->dry) CK(cudaMemsetAsync(k.gd, 0, bytes, m->stream));
+      if (!m->dry) CK(cudaMemsetAsync(k->gd, 0, bytes, m->stream));
     }
-    return stage(m, pass, MODE_EVAL, s, nullptr, 0, nullptr, &k, nullptr);
+    return stage(m, pass, MODE_EVAL, s, nullptr, 0, nullptr, k, nullptr);
   };
   auto advance = [&](const Tend &t, double dt, State *to) -> int {
     int q;
     if ((q = update(m, in, t, dt, 0, 0, !slow, to))) return q;
     return exchange_state(m, *to, !slow);
   };
-  if ((r = eval(in))) return r;                             // k1
-  if ((r = axpby(m, 1.0, k, 0.0, K))) return r;
+  auto tdot = [&](const Tend &x, const Tend &y, int slot, int acc) -> int {
+    return dot(m, x.U, x.V, x.gd, y.U, y.V, y.gd, slot, acc);
+  };
+  if ((r = eval(in, ka))) return r;                          // k1
+  if ((r = axpby(m, 1.0, *ka, 0.0, K))) return r;
   if (m->cfg.time_order == 4) {
-    if ((r = advance(k, dts * 0.5, &A))) return r;
-    if ((r = eval(A))) return r;                            // k2
-    if ((r = axpby(m, 2.0, k, 1.0, K))) return r;
-    if ((r = advance(k, dts * 0.5, &B))) return r;
-    if ((r = eval(B))) return r;                            // k3
-    if ((r = axpby(m, 2.0, k, 1.0, K))) return r;
-    if ((r = advance(k, dts, &A))) return r;
-    if ((r = eval(A))) return r;                            // k4
-    if ((r = axpby(m, 1.0 / 6.0, k, 1.0 / 6.0, K))) return r;
+    if ((r = advance(*ka, dts * 0.5, &A))) return r;
+    if ((r = eval(A, kb))) return r;                         // k2
+    if ((r = tdot(*ka, *kb, 0, 0))) return r;
+    if ((r = axpby(m, 2.0, *kb, 1.0, K))) return r;
+    if ((r = advance(*kb, dts * 0.5, &B))) return r;
+    if ((r = eval(B, ka))) return r;                         // k3
+    if ((r = tdot(*kb, *ka, 0, 1))) return r;
+    if ((r = axpby(m, 2.0, *ka, 1.0, K))) return r;
+    if ((r = advance(*ka, dts, &A))) return r;
+    if ((r = eval(A, kb))) return r;                         // k4
+    if ((r = tdot(*ka, *kb, 0, 1))) return r;
+    if ((r = axpby(m, 1.0 / 6.0, *kb, 1.0 / 6.0, K))) return r;
   } else {
-    if ((r = advance(k, dts, &A))) return r;
-    if ((r = eval(A))) return r;                            // k2
-    if ((r = axpby(m, 1.0, k, 1.0, K))) return r;
+    if ((r = advance(*ka, dts, &A))) return r;
+    if ((r = eval(A, ka))) return r;                         // k2
+    if ((r = tdot(K, *ka, 0, 0))) return r;                  // <k1, k2>
+    if ((r = axpby(m, 1.0, *ka, 1.0, K))) return r;
     if ((r = advance(K, dts * 0.25, &B))) return r;
-    if ((r = eval(B))) return r;                            // k3
-    if ((r = axpby(m, 2.0 / 3.0, k, 1.0 / 6.0, K))) return r;
+    if ((r = eval(B, ka))) return r;                         // k3
+    if ((r = tdot(K, *ka, 0, 1))) return r;                  // + <k1 + k2, k3>
+    if ((r = axpby(m, 2.0 / 3.0, *ka, 1.0 / 6.0, K))) return r;
   }
-  // ip1 = <K, in> (tend-state product, src/types_mod.F90:373-397), ip2 = <K, K>
-  if ((r = dot(m, K.U, K.V, K.gd, in.U, in.V, in.gd, 0))) return r;
-  if ((r = dot(m, K.U, K.V, K.gd, K.U, K.V, K.gd, 1))) return r;
+  if ((r = tdot(K, K, 1, 0))) return r;
   {
     RedArgs ra = red_args(m);
     ra.tseq = tseq(m, "k_reduce_pairs.rk");
@@ -1710,6 +1740,25 @@ int gmd_create(const gmd_config *cfg, gmd_model **out) {
   const int nlon = cfg->num_lon, nlat = cfg->num_lat;
   m->mesh.init(nlon, nlat, /*reset_poles=*/true);
   m->mesh.filter_init(cfg->use_zonal_tend_filter != 0, cfg->zonal_tend_filter_cutoff_wavenumber);
+  {   // moving reduced tendency (specified extension)
+    const int bad = m->mesh.reduce_init(cfg->use_zonal_reduce != 0, cfg->zonal_reduce_factors);
+    if (bad) {
+      fail(GMD_ERR_ARG, "zonal_reduce_factors(%d)=%d must be >= 0 and divide num_lon=%d", bad, cfg->zonal_reduce_factors[bad - 1], nlon);
+      gmd_destroy(m);
+      return GMD_ERR_ARG;
+    }
+    for (int j = 0; j < nlat; j++)
+      if ((m->mesh.red_full[(size_t)j] > 1 && m->mesh.flag_full[(size_t)j]) || (m->mesh.red_half[(size_t)j] > 1 && m->mesh.flag_half[(size_t)j])) {
+        fail(GMD_ERR_ARG, "row %d is both a zonal filter row and a reduced row", j + 1);
+        gmd_destroy(m);
+        return GMD_ERR_ARG;
+      }
+    if (cfg->use_zonal_reduce && nlon > PQ * PT) {
+      fail(GMD_ERR_ARG, "use_zonal_reduce: num_lon must be <= %d", PQ * PT);
+      gmd_destroy(m);
+      return GMD_ERR_ARG;
+    }
+  }
   // latitude bands: rows split as evenly as possible, or (polar_band_rows) shorter first and last bands
   m->geo.nlon = nlon;
   m->geo.nlat = nlat;
@@ -1740,6 +1789,9 @@ int gmd_create(const gmd_config *cfg, gmd_model **out) {
     if (cfg->use_zonal_tend_filter)
       for (int k = 0; k < 20; k++)
         if (cfg->zonal_tend_filter_cutoff_wavenumber[k]) K = k + 1;
+    if (cfg->use_zonal_reduce)
+      for (int k = 0; k < 20; k++)
+        if (cfg->zonal_reduce_factors[k] > 1) K = std::max(K, k + 1);
     m->bs = (m->geo.r0 == 0) ? K + 2 : 0;
     m->bn = (m->geo.r1 == nlat) ? K + 3 : 0;
     // wide-halo predict_correct: every band edge needs HALO_N plain rows (no filtered row, no pole row) on both sides
@@ -1749,7 +1801,8 @@ int gmd_create(const gmd_config *cfg, gmd_model **out) {
       int e0, e1;
       band_rows(nlat, cfg->nranks, cfg->polar_band_rows, q, &e0, &e1);   // edge between band q-1 and band q: row e0
       for (int j = e0 - HALO_N; j < e0 + HALO_N; j++)
-        if (j < 1 || j > nlat - 2 || m->mesh.flag_full[(size_t)j] || m->mesh.flag_half[(size_t)j]) m->wide = false;
+        if (j < 1 || j > nlat - 2 || m->mesh.flag_full[(size_t)j] || m->mesh.flag_half[(size_t)j] ||
+            m->mesh.red_full[(size_t)j] > 1 || m->mesh.red_half[(size_t)j] > 1) m->wide = false;
       if (e1 - e0 < HALO_N) m->wide = false;
     }
     if (getenv("GMD_NO_WIDE")) m->wide = false;
@@ -1762,9 +1815,10 @@ int gmd_create(const gmd_config *cfg, gmd_model **out) {
              cfg->uv_adv_scheme != GMD_ADV_WENO && getenv("GMD_CAP") != nullptr;   // opt-in: measured slower
     for (int li = 0; li < 2 && m->cap; li++)
       for (unsigned pk : m->items[li]) {
-        const int cutoff = (int)((pk >> 16) & 0x1ffu) - 1, kind = (int)(pk >> 28);
+        const int cutoff = (int)((pk >> 16) & 0x1ffu) - 1, kind = (int)((pk >> 28) & 7u);
         const int Kk = cutoff + 1;
         if (kind != IT_POLE_S && kind != IT_POLE_N && !(Kk >= 1 && Kk <= KF && 2 * Kk < nlon)) m->cap = false;
+        if (pk & ITEM_REDUCE) m->cap = false;
       }
     // without the fused cap a single band gains nothing from the split (the one-wave interior launch owns every
     // register file, so the 512-thread polar-row CTAs cannot co-run; measured 4.80 vs 4.75 ms per step); the cap CTAs
@@ -1821,7 +1875,7 @@ int gmd_create(const gmd_config *cfg, gmd_model **out) {
     }
     // boundary chunks: long while the interior launch hides them, short once the boundary -> polar rows -> next
     // boundary chain is what a phase waits for (measured at 900 and 225 rows per rank)
-    m->rows_per_cta_b = (m->nr >= 600) ? 6 : 3;
+    m->rows_per_cta_b = (m->nr >= 600) ? 6 : 2;   // 226-row polar bands: 1 -> 0.967, 2 -> 0.904, 3 -> 0.916, 4 -> 0.913 ms per step
     if (const char *ev = getenv("GMD_ROWS_PER_CTA_B")) m->rows_per_cta_b = std::max(1, atoi(ev));
     m->nchunks_b = (std::max(m->bs, m->bn) + m->rows_per_cta_b - 1) / m->rows_per_cta_b;
     m->stage_smem_b = stage_smem_bytes(m->rows_per_cta_b);
@@ -2587,6 +2641,7 @@ static int time_stage(gmd_model *m, int pass, int mode, int reps, float *ms_per_
   a.beta_lon = m->cfg.uv_adv_upwind_lon_beta; a.beta_lat = m->cfg.uv_adv_upwind_lat_beta;
   a.AUlon = m->w_alon_u; a.AUlat = m->w_alat_u; a.AVlon = m->w_alon_v; a.AVlat = m->w_alat_v;
   a.partials = m->d_partials;
+  a.flmask = 0x0fu;
   const int rpc = (mode == MODE_S3A) ? m->rows_per_cta_s3a : m->rows_per_cta;
   a.rows_per_cta = rpc;
   a.rb[0] = m->geo.r0; a.re[0] = m->geo.r1; a.pofs[0] = 0;

@@ -96,6 +96,9 @@ enum { MODE_S1 = 0,    // new = base + dt * tend               (tend stored only
 
 // row flags (global row index)
 enum { FL_DU = 1, FL_DGD = 2, FL_POLE = 4, FL_DV = 8 };
+// the same bits shifted left by FL_REDUCE_SHIFT mark the rows of the moving reduced tendency (specified extension,
+// DESIGN.md section 8); StageArgs::flmask decides per launch whether they count (the slow pass only with reduce_adv_lon)
+constexpr int FL_REDUCE_SHIFT = 4;
 
 struct Tab {  // device pointers, already offset by TPAD: valid for j in [-TPAD, nlat+TPAD)
   const double *cosf, *cosh, *ff, *fc;
@@ -173,6 +176,7 @@ struct StageArgs {
   Fold fold;   // MODE_S3A
   int tseq;    // timeline slot + 1 of the launch (GMD_TRACE builds), 0 = none
   int pdl;     // launched with programmatic stream serialization: wait for the predecessor inside the kernel
+  unsigned flmask;   // row flags honoured by this launch: 0x0f filter rows, 0xf0 reduced rows
 };
 
 // beta of predict_correct (src/dycore_mod.F90:784-785) from the device-resident inner products
@@ -813,7 +817,8 @@ __device__ __forceinline__ void stage_body(const StageArgs &a, const int bx, con
       }
       if (need_gh) n_gd1 = c_gd2;  // gd(j+2) is next iteration's gd(j'+1)
       const double *__restrict__ rc = srow + (j - ja + 1) * RC_N;
-      const unsigned fl = (unsigned)rc[RC_FLAGS];
+      const unsigned flraw = (unsigned)rc[RC_FLAGS] & a.flmask;
+      const unsigned fl = flraw | (flraw >> FL_REDUCE_SHIFT);
       const bool rowU = (j >= 1 && j <= nlat - 2);
       const bool rowV = (j <= nlat - 2);
       const bool rowG = rowU && (PASS != PASS_SLOW);
@@ -1067,6 +1072,11 @@ enum { IT_DU = 0, IT_DV = 1, IT_DGD = 2, IT_POLE_S = 3, IT_POLE_N = 4 };
 __host__ __device__ inline unsigned pack_item(int kind, int row, int cutoff) {
   return (unsigned)row | ((unsigned)(cutoff + 1) << 16) | ((unsigned)kind << 28);
 }
+// a row of the moving reduced tendency: bit 27 set, the cutoff field carries the reduction factor
+constexpr unsigned ITEM_REDUCE = 1u << 27;
+__host__ __device__ inline unsigned pack_reduce_item(int kind, int row, int factor) {
+  return (unsigned)row | ((unsigned)factor << 16) | ITEM_REDUCE | ((unsigned)kind << 28);
+}
 
 struct PolarArgs {
   Geo g;
@@ -1087,6 +1097,7 @@ struct PolarArgs {
   const double *fold_partials;   // start of the whole partials array (this kernel's own pairs start at `partials`)
   int tseq;               // timeline slot + 1 (GMD_TRACE builds), 0 = none
   int pdl;                // see StageArgs
+  int reduce_smooth;      // use_reduce_tend_smooth: reduced rows are rescaled like filter rows (when `rescale` is set)
   unsigned items[MAX_ITEMS];
 };
 
@@ -1151,6 +1162,35 @@ __device__ inline void project_row(double *x, int n, int cutoff, const double *_
   __syncthreads();
 }
 
+// Moving reduced tendency of one row (specified extension): x'(i) = sum_{|d| < r} (r - |d|) x(i + d)
+// / r^2, periodic -- the average over the r offsets of the zonally reduced grid of the cell means handed back to the
+// fine cells.  Same summation order as the oracle (d ascending).  Rows of up to PQ * PT elements.
+__device__ inline void reduce_row_dev(double *x, int n, int r) {
+  double y[PQ];
+#pragma unroll
+  for (int c = 0; c < PQ; c++) {
+    const int i = threadIdx.x + c * PT;
+    y[c] = 0.0;
+    if (i < n) {
+      double acc = 0.0;
+      for (int dd = -(r - 1); dd <= r - 1; dd++) {
+        int ii = i + dd;
+        if (ii < 0) ii += n;
+        if (ii >= n) ii -= n;
+        acc = acc + (double)(r - (dd < 0 ? -dd : dd)) * x[ii];
+      }
+      y[c] = acc / (double)(r * r);
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int c = 0; c < PQ; c++) {
+    const int i = threadIdx.x + c * PT;
+    if (i < n) x[i] = y[c];
+  }
+  __syncthreads();
+}
+
 // Latency is what this kernel is about (it sits between two stage launches, and at one CTA per SM it is a chain
 // of dependent phases, not a throughput problem):
 //  * the work item comes from the kernel parameters (no dependent global load at the head of the chain);
@@ -1203,7 +1243,9 @@ __global__ void __launch_bounds__(PT) k_polar(const __grid_constant__ PolarArgs 
   constexpr int NV = 2 + 2 * KF;  // s1, <x,1>, <x,cos k>, <x,sin k>
   static_assert(NV * NW <= 512 && (NV * NW) % 32 == 0, "second reduction stage runs on whole warps");
   const unsigned pk = a.items[blockIdx.x];
-  const int j = (int)(pk & 0xffffu), cutoff = (int)((pk >> 16) & 0x1ffu) - 1, kind = (int)(pk >> 28);
+  const int j = (int)(pk & 0xffffu), cutoff = (int)((pk >> 16) & 0x1ffu) - 1, kind = (int)((pk >> 28) & 7u);
+  const bool isred = (pk & ITEM_REDUCE) != 0;   // a reduced row: cutoff + 1 is the reduction factor
+  const int rescale = isred ? (a.rescale && a.reduce_smooth) : a.rescale;
   const int n = a.g.nlon, r0 = a.g.r0;
   const int tid = threadIdx.x;
   trace_in(a.tseq);
@@ -1269,7 +1311,7 @@ __global__ void __launch_bounds__(PT) k_polar(const __grid_constant__ PolarArgs 
     const int K = cutoff + 1;
     const int n4 = n >> 2;
     const int G = (n4 + PT - 1) / PT;  // element groups per thread on the fast path
-    const bool fast = (K >= 1) && (K <= KF) && ((n & 3) == 0) && (G <= PQ) && (2 * K < n);
+    const bool fast = !isred && (K >= 1) && (K <= KF) && ((n & 3) == 0) && (G <= PQ) && (2 * K < n);
     // element e of a batch of 8: fast path: group g0 + e/4, quarter e%4; general path: i0 + e PT
     auto elem = [&](int i0, int e) -> int {
       if (fast) {
@@ -1299,8 +1341,8 @@ __global__ void __launch_bounds__(PT) k_polar(const __grid_constant__ PolarArgs 
         const int i = elem(i0, e);
         const bool ok = i < n;
         xv[e] = ok ? T[off + i] : 0.0;
-        wv[e] = (ok && a.rescale) ? __ldg(W + off + i) : 0.0;
-        gv[e] = (ok && a.rescale && kind == IT_DGD) ? __ldg(a.ghs + off + i) : 0.0;
+        wv[e] = (ok && rescale) ? __ldg(W + off + i) : 0.0;
+        gv[e] = (ok && rescale && kind == IT_DGD) ? __ldg(a.ghs + off + i) : 0.0;
         qv[e] = (ok && useq) ? __ldg(Q + off + i) : 0.0;
       }
 #pragma unroll
@@ -1368,7 +1410,7 @@ __global__ void __launch_bounds__(PT) k_polar(const __grid_constant__ PolarArgs 
       }
       __syncthreads();
       s1 = bc[0];
-      if (a.rescale) do_filter = fabs(s1) > 1.0e-16;  // filter_inner_product_threshold, src/filter_mod.F90:31
+      if (rescale) do_filter = fabs(s1) > 1.0e-16;  // filter_inner_product_threshold, src/filter_mod.F90:31
       if (do_filter) {
         // ---- reconstruction from entries 0 .. 2K-1 (sin(K x) is dropped: quirk B3) ---------------------------
         const double c0 = coef[0];
@@ -1408,7 +1450,7 @@ __global__ void __launch_bounds__(PT) k_polar(const __grid_constant__ PolarArgs 
             s2p = s2p + y0 * w[b] + y1 * w[b + n4] + y2 * w[b + 2 * n4] + y3 * w[b + 3 * n4];
           }
         }
-        if (a.rescale) {
+        if (rescale) {
           const double r = block_sum<PT>(s2p, red);
           if (tid == 0) bc[1] = r;
           __syncthreads();
@@ -1416,7 +1458,7 @@ __global__ void __launch_bounds__(PT) k_polar(const __grid_constant__ PolarArgs 
         }
       }
     } else {
-      if (a.rescale) {
+      if (rescale) {
         const double r = block_sum<PT>(s1p, red);
         if (tid == 0) bc[0] = r;
         __syncthreads();
@@ -1424,8 +1466,9 @@ __global__ void __launch_bounds__(PT) k_polar(const __grid_constant__ PolarArgs 
         do_filter = fabs(s1) > 1.0e-16;
       }
       if (do_filter) {
-        project_row(x, n, cutoff, a.basis, coef, part);
-        if (a.rescale) {
+        if (isred) reduce_row_dev(x, n, cutoff + 1);
+        else project_row(x, n, cutoff, a.basis, coef, part);
+        if (rescale) {
           double s2p = 0.0;
           for (int i = tid; i < n; i += PT) s2p = s2p + x[i] * w[i];
           const double r = block_sum<PT>(s2p, red);
@@ -1438,7 +1481,7 @@ __global__ void __launch_bounds__(PT) k_polar(const __grid_constant__ PolarArgs 
     const double cw = (kind == IT_DV) ? a.t.cosh[j] : a.t.cosf[j];
     // src/dycore_mod.F90:218.  s2 == 0 exactly (a row whose filtered inner product cancels to the last bit; the
     // reference would divide by zero and abort with NaN, quirk B13): the filtered row is left unscaled.
-    const bool scale = do_filter && a.rescale && (s2 != 0.0);
+    const bool scale = do_filter && rescale && (s2 != 0.0);
 #if !GMD_STRICT
     const double ratio = scale ? s1 / s2 : 1.0;
 #endif
@@ -1969,7 +2012,7 @@ struct UpdateArgs {
   double dt;
   const double *ip;   // device {ip1, ip2} or NULL
   int qcon, beta_mode;  // beta_mode 0: dt ; 1: dt*beta (predict_correct :786-790) ; 2: dt * (beta*4/dt0) (isp :745-750)
-                        // 3: runge_kutta (specified extension): beta = -2 ip1 / (dt0 ip2), ip1 = <K, state>
+                        // 3: runge_kutta (specified extension): beta = ip1 / (3 ip2), ip1 = the stage tendency products
   double dt0;
   double *beta_out;   // device scalar, written by one thread
   int with_gd;        // 0: slow pass, gd is shared
@@ -1987,7 +2030,7 @@ __global__ void __launch_bounds__(256) k_update(const UpdateArgs a) {
     if (a.beta_mode == 2) beta = beta * 4.0 / a.dt0;
     if (a.beta_mode == 3) {
       const double ip1 = a.ip[0], ip2 = a.ip[1];
-      beta = (a.qcon && ip1 != 0.0 && ip2 != 0.0) ? -2.0 * ip1 / (a.dt0 * ip2) : 1.0;
+      beta = (a.qcon && ip1 != 0.0 && ip2 != 0.0) ? ip1 / (3.0 * ip2) : 1.0;
     }
     dt = a.dt * beta;
     if (blockIdx.x == 0 && threadIdx.x == 0 && a.beta_out) *a.beta_out = beta;
@@ -2099,7 +2142,7 @@ __global__ void k_diag_store(const double *sums, const double *beta, double radi
 // <a, b> with the inner-product weights (src/types_mod.F90:347-397); out partials pairs {dot, 0}
 __global__ void __launch_bounds__(256) k_dot(Geo g, Tab t, const double *aU, const double *aV, const double *aG,
                                              const double *bU, const double *bV, const double *bG, int with_gd,
-                                             double *partials, int slot) {
+                                             double *partials, int slot, int accumulate = 0) {
   __shared__ double red[32];
   const int nlon = g.nlon;
   const size_t total = (size_t)(g.r1 - g.r0) * (size_t)nlon;
@@ -2112,8 +2155,8 @@ __global__ void __launch_bounds__(256) k_dot(Geo g, Tab t, const double *aU, con
   }
   const double r = block_sum<256>(s, red);
   if (threadIdx.x == 0) {
-    partials[2 * blockIdx.x + slot] = r;
-    if (slot == 0) partials[2 * blockIdx.x + 1] = 0.0;
+    partials[2 * blockIdx.x + slot] = accumulate ? partials[2 * blockIdx.x + slot] + r : r;
+    if (slot == 0 && !accumulate) partials[2 * blockIdx.x + 1] = 0.0;
   }
 }
 

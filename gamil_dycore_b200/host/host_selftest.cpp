@@ -46,6 +46,9 @@ int main(int argc, char **argv) {
     printf("use_zonal_tend_filter=%d\nuse_diffusion=%d\ndiffusion_order=%d\ndiffusion_coef=%.17g\nsmooth_mountain=%d\ncutoff=", (int)p.use_zonal_tend_filter,
            (int)p.use_diffusion, p.diffusion_order, p.diffusion_coef, (int)p.smooth_mountain);
     for (int k = 0; k < 20; k++) printf("%d%s", p.zonal_tend_filter_cutoff_wavenumber[k], k == 19 ? "\n" : ",");
+    printf("time_order=%d\nuse_zonal_reduce=%d\nreduce_adv_lon=%d\nuse_reduce_tend_smooth=%d\nreduce_factors=", p.time_order,
+           (int)p.use_zonal_reduce, (int)p.reduce_adv_lon, (int)p.use_reduce_tend_smooth);
+    for (int k = 0; k < 20; k++) printf("%d%s", p.zonal_reduce_factors[k], k == 19 ? "\n" : ",");
     return 0;
   }
   if (cmd == "ic" && argc >= 4) {

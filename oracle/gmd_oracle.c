@@ -858,40 +858,46 @@ static void tend_axpby(const orc_model *m, real alpha, const tend_t *x, real bet
    The integrator slot of dycore_mod.F90:43-53,78-83 (`time_scheme = 'runge_kutta'`, params_mod.F90:40-44) filled with
    an explicit Runge-Kutta step in increment form, phi' = phi + beta dt K, K = sum b_i k_i, k_i = L(phi_i) from the same
    space_operators / update_state / tend algebra the reference has, and the energy fix of predict_correct carried
-   over:  E(phi + beta dt K) = E(phi) + 2 beta dt <K, phi> + beta^2 dt^2 <K, K>  (E = the quadratic form of
-   inner_product_tend_state, types_mod.F90:373-397), so beta = -2 <K, phi> / (dt <K, K>) keeps it (qcon_modified).
-     time_order 3 (Shu-Osher SSP-RK3): phi1 = phi + dt k1; phi2 = phi + dt/4 (k1 + k2); K = 1/6 (k1 + k2) + 2/3 k3
+   over.  E(phi + beta dt K) = E(phi) + 2 beta dt <K, phi> + beta^2 dt^2 <K, K> asks for beta = -2 <K, phi> / (dt <K, K>);
+   with the antisymmetry <L(psi), psi> = 0 at every stage state, <K, phi> is a combination of tendency products -- the
+   form predict_correct itself uses (beta = <k2, k3> / <k3, k3>, :779-781), free of the cancellation in <K, phi>:
+     time_order 3 (Shu-Osher SSP-RK3): phi1 = phi + dt k1; phi2 = phi + dt/4 (k1 + k2); K = 1/6 (k1 + k2) + 2/3 k3;
+                                       beta = (<k1, k2> + <k1 + k2, k3>) / (3 <K, K>)
      time_order 4 (classical RK4):     phi1 = phi + dt/2 k1; phi2 = phi + dt/2 k2; phi3 = phi + dt k3;
-                                       K = 1/6 ((k1 + 2 k2 + 2 k3) + k4)
-   Scratch: tend slots -2 (K) and -1 (k_i) -- isp's, which never runs through the integrator slot. */
+                                       K = 1/6 ((k1 + 2 k2 + 2 k3) + k4); beta = (<k1,k2> + <k2,k3> + <k3,k4>) / (3 <K, K>)
+   Scratch: tend slots -2 (K), -1 and `old` (k_i) -- the first two are isp's, which never runs through this slot. */
 static void runge_kutta(orc_model *m, real dt, int old, int new_, int pass) {
-  tend_t *K = TEND(m, -2), *k = TEND(m, -1);
+  tend_t *K = TEND(m, -2), *ka = TEND(m, -1), *kb = TEND(m, old);
   state_t *S0 = STATE(m, old);
   state_t *S1 = STATE(m, new_);
   real ip1, ip2, beta;
-  space_operators(m, S0, k, pass);                       /* k1 */
-  tend_copy(m, k, K);
+  space_operators(m, S0, ka, pass);                      /* k1 */
+  tend_copy(m, ka, K);
   if (m->cfg.time_order == 4) {
-    update_state(m, dt * R_LIT(0.5), k, S0, S1);
-    space_operators(m, S1, k, pass);                     /* k2 */
-    tend_axpby(m, R_LIT(2.0), k, R_LIT(1.0), K);
-    update_state(m, dt * R_LIT(0.5), k, S0, S1);
-    space_operators(m, S1, k, pass);                     /* k3 */
-    tend_axpby(m, R_LIT(2.0), k, R_LIT(1.0), K);
-    update_state(m, dt, k, S0, S1);
-    space_operators(m, S1, k, pass);                     /* k4 */
-    tend_axpby(m, R_LIT(1.0) / R_LIT(6.0), k, R_LIT(1.0) / R_LIT(6.0), K);
+    update_state(m, dt * R_LIT(0.5), ka, S0, S1);
+    space_operators(m, S1, kb, pass);                    /* k2 */
+    ip1 = inner_product_tend_tend(m, ka, kb);
+    tend_axpby(m, R_LIT(2.0), kb, R_LIT(1.0), K);
+    update_state(m, dt * R_LIT(0.5), kb, S0, S1);
+    space_operators(m, S1, ka, pass);                    /* k3 */
+    ip1 = ip1 + inner_product_tend_tend(m, kb, ka);
+    tend_axpby(m, R_LIT(2.0), ka, R_LIT(1.0), K);
+    update_state(m, dt, ka, S0, S1);
+    space_operators(m, S1, kb, pass);                    /* k4 */
+    ip1 = ip1 + inner_product_tend_tend(m, ka, kb);
+    tend_axpby(m, R_LIT(1.0) / R_LIT(6.0), kb, R_LIT(1.0) / R_LIT(6.0), K);
   } else {
-    update_state(m, dt, k, S0, S1);
-    space_operators(m, S1, k, pass);                     /* k2 */
-    tend_axpby(m, R_LIT(1.0), k, R_LIT(1.0), K);
+    update_state(m, dt, ka, S0, S1);
+    space_operators(m, S1, ka, pass);                    /* k2 */
+    ip1 = inner_product_tend_tend(m, K, ka);
+    tend_axpby(m, R_LIT(1.0), ka, R_LIT(1.0), K);
     update_state(m, dt * R_LIT(0.25), K, S0, S1);
-    space_operators(m, S1, k, pass);                     /* k3 */
-    tend_axpby(m, R_LIT(2.0) / R_LIT(3.0), k, R_LIT(1.0) / R_LIT(6.0), K);
+    space_operators(m, S1, ka, pass);                    /* k3 */
+    ip1 = ip1 + inner_product_tend_tend(m, K, ka);
+    tend_axpby(m, R_LIT(2.0) / R_LIT(3.0), ka, R_LIT(1.0) / R_LIT(6.0), K);
   }
-  ip1 = inner_product_tend_state(m, K, S0);
   ip2 = inner_product_tend_tend(m, K, K);
-  beta = (m->cfg.qcon_modified && ip1 != 0 && ip2 != 0) ? -R_LIT(2.0) * ip1 / (dt * ip2) : R_LIT(1.0);
+  beta = (m->cfg.qcon_modified && ip1 != 0 && ip2 != 0) ? ip1 / (R_LIT(3.0) * ip2) : R_LIT(1.0);
   m->beta = beta;
   update_state(m, dt * beta, K, S0, S1);
 }

@@ -54,6 +54,13 @@ CASES = {
     "sw_72x37_rk4_nosplit": (dict(num_lon=72, num_lat=37, time_step_size=150.0, split_scheme="none",
                                   time_scheme="runge_kutta", time_order=4, zonal_tend_filter_cutoff_wavenumber=[12, 12, 12]),
                              "shallow_water_waves", 4),
+    # moving reduced tendency: the specified extension of DESIGN.md section 8 (keys of the reference's run/namelist.jz_test)
+    "jz_72x37_reduce": (dict(num_lon=72, num_lat=37, time_step_size=900.0, subcycles=6, split_scheme="csp2",
+                             use_zonal_reduce=True, reduce_adv_lon=True, use_reduce_tend_smooth=True,
+                             zonal_reduce_factors=[8, 4, 2, 2], use_diffusion=True, diffusion_coef=1.0e5),
+                        "jet_zonal_flow", 4),
+    "mz_60x31_reduce_plain": (dict(num_lon=60, num_lat=31, time_step_size=600.0, subcycles=4, split_scheme="csp2",
+                                   use_zonal_reduce=True, zonal_reduce_factors=[6, 3, 2]), "mountain_zonal_flow", 4),
 }
 
 

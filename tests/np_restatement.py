@@ -30,7 +30,8 @@ def W(a):  # value at i-1
 class NpModel:
     def __init__(self, nlon, nlat, dt, subcycles=4, qcon_modified=True, split="csp2", adv="center_diff",
                  beta_lon=0.0, beta_lat=0.5, use_filter=True, cutoff=(), use_diffusion=False,
-                 diffusion_order=2, diffusion_coef=0.0):
+                 diffusion_order=2, diffusion_coef=0.0, time_scheme="predict_correct", time_order=3):
+        self.time_scheme, self.time_order = time_scheme, time_order
         self.nlon, self.nlat, self.dt, self.S = nlon, nlat, float(dt), subcycles
         self.qcon, self.split, self.adv = qcon_modified, split, adv
         self.beta_lon, self.beta_lat = beta_lon, beta_lat
@@ -277,6 +278,31 @@ class NpModel:
         self.beta = ip1 / ip2 if (self.qcon and ip1 != 0.0 and ip2 != 0.0) else 1.0
         return self.update(dt * self.beta, t_new, old)
 
+    def runge_kutta(self, dt, old, pass_):
+        """the specified runge_kutta integrator (oracle/gmd_oracle.c runge_kutta), second reading:
+        increment form with the energy fix beta = -2 <K, phi> / (dt <K, K>), <K, phi> written with the tendency products
+        the stage antisymmetries <L(psi), psi> = 0 turn it into"""
+        k1 = self.tend(old, pass_)
+        if self.time_order == 4:
+            k2 = self.tend(self.update(0.5 * dt, k1, old), pass_)
+            k3 = self.tend(self.update(0.5 * dt, k2, old), pass_)
+            k4 = self.tend(self.update(dt, k3, old), pass_)
+            K = tuple((1.0 / 6.0) * d + (1.0 / 6.0) * ((a + 2.0 * b) + 2.0 * c) for a, b, c, d in zip(k1, k2, k3, k4))
+            ip1 = self.inner(k1, k2) + self.inner(k2, k3) + self.inner(k3, k4)
+        else:
+            k2 = self.tend(self.update(dt, k1, old), pass_)
+            k12 = tuple(a + b for a, b in zip(k1, k2))
+            k3 = self.tend(self.update(0.25 * dt, k12, old), pass_)
+            K = tuple((2.0 / 3.0) * c + (1.0 / 6.0) * ab for ab, c in zip(k12, k3))
+            ip1 = self.inner(k1, k2) + self.inner(k12, k3)
+        ip2 = self.inner(K, K)
+        self.beta = ip1 / (3.0 * ip2) if (self.qcon and ip1 != 0.0 and ip2 != 0.0) else 1.0
+        self.beta_direct = -2.0 * self.inner_state(K, old) / (dt * ip2)   # the ill-conditioned form, for the tests
+        return self.update(dt * self.beta, K, old)
+
+    def integrator(self, dt, old, pass_):
+        return self.runge_kutta(dt, old, pass_) if self.time_scheme == "runge_kutta" else self.predict_correct(dt, old, pass_)
+
     def inner_state(self, t, st):
         """inner_product_tend_state (src/types_mod.F90:373-397): (du, U), (dv, V), (dgd, gd)"""
         return self.inner(t, (st[3], st[4], st[2]))
@@ -356,12 +382,12 @@ class NpModel:
         if self.split == "isp":
             new = self.isp(st)
         elif self.split == "csp2":
-            st1 = self.predict_correct(0.5 * self.dt, st, "slow")
+            st1 = self.integrator(0.5 * self.dt, st, "slow")
             for _ in range(self.S):
-                st1 = self.predict_correct(self.dt / self.S, st1, "fast")
-            new = self.predict_correct(0.5 * self.dt, st1, "slow")
+                st1 = self.integrator(self.dt / self.S, st1, "fast")
+            new = self.integrator(0.5 * self.dt, st1, "slow")
         else:
-            new = self.predict_correct(self.dt, st, "all")
+            new = self.integrator(self.dt, st, "all")
         if self.use_diffusion:
             new = self.diffusion(self.dt, new)
         return new

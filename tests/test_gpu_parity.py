@@ -160,7 +160,8 @@ def test_pole_rows_and_reference_layout():
 
 
 GOLDEN = ["rh_36x19_csp2", "rh_72x37_nosplit", "mz_60x31_upwind", "jz_72x37_diffusion", "sg_48x25_isp", "mz_48x25_weno",
-          "mz_60x32_diff4", "mz_60x31_rk3_csp2", "sw_72x37_rk4_nosplit"]
+          "mz_60x32_diff4", "mz_60x31_rk3_csp2", "sw_72x37_rk4_nosplit",
+          "jz_72x37_reduce", "mz_60x31_reduce_plain"]
 
 
 @pytest.mark.parametrize("name", GOLDEN)

@@ -108,6 +108,37 @@ def test_namelist_defaults_comments_and_unknown_keys(tmp_path):
     assert rc == 2 and "Cannot match namelist object name days" in out
 
 
+def test_reduced_tendency_and_runge_kutta_keys_parse(tmp_path):
+    """the keys of the reference's own run/namelist.jz_test:12-19 that its params_mod does not define (use_zonal_reduce,
+    reduce_adv_lon, zonal_reduce_factors, use_reduce_tend_smooth) and time_scheme = 'runge_kutta' / time_order
+    (params_mod.F90:40-45): the specified extensions of DESIGN.md section 8"""
+    text = """&dycore_params
+test_case = 'jet_zonal_flow'
+case_name = 'jz_test.360x181.pc.dt240.diffused'
+run_days = 6
+num_lon = 360
+num_lat = 181
+time_step_size = 240
+time_scheme = 'runge_kutta'
+time_order = 4
+qcon_modified = .true.
+split_scheme = 'csp2'
+subcycles = 6
+use_zonal_reduce = .true.
+reduce_adv_lon = .true.
+zonal_reduce_factors = 8, 8, 4, 2, 2
+use_reduce_tend_smooth = .true.
+use_diffusion = .true.
+diffusion_coef = 1.0e5
+/
+"""
+    rc, kv, out = parse(write(tmp_path, text))
+    assert rc == 0, out
+    assert kv["time_scheme"] == "runge_kutta" and kv["time_order"] == "4"
+    assert kv["use_zonal_reduce"] == "1" and kv["reduce_adv_lon"] == "1" and kv["use_reduce_tend_smooth"] == "1"
+    assert kv["reduce_factors"] == "8,8,4,2,2" + ",0" * 15
+
+
 # ------------------------------------------------------------------------------------------------ formats
 @pytest.mark.parametrize("x,s", [(2.812376625197987e19, "0.28123766251980E+20"), (5.083437998896658e12, "0.50834379988967E+13"),
                                  (1.0000123, "0.10000123000000E+01"), (-0.5, "-0.5000000000000E+00"), (0.0, "0.00000000000000E+00"),

@@ -157,6 +157,96 @@ def test_step_matches_numpy(case, adv, diff):
     assert abs(o.diag()[2] - npm.beta) < 1e-12
 
 
+@pytest.mark.parametrize("order,split", [(3, "csp2"), (4, "csp2"), (3, "none"), (4, "none")])
+def test_runge_kutta_step_matches_numpy(order, split):
+    """the specified runge_kutta integrator: oracle against the NumPy second reading, and the
+    property it is built for -- the quadratic invariant is kept to rounding on a flat-bottom case"""
+    nlon, nlat = 72, 37
+    dt = 300.0 if split == "csp2" else 60.0
+    cfg = OracleConfig(num_lon=nlon, num_lat=nlat, time_step_size=dt, subcycles=4, split_scheme=split,
+                       zonal_tend_filter_cutoff_wavenumber=[4] * 3, time_scheme="runge_kutta", time_order=order)
+    o = Oracle(cfg)
+    o.set_initial_condition("steady_geostrophic_flow")
+    u, v, gd = o.state()
+    rng = np.random.default_rng(5)
+    gd = gd * (1 + 1e-3 * np.cos(3 * np.linspace(0, 2 * np.pi, nlon, endpoint=False))[None, :] * np.cos(np.linspace(-1.5, 1.5, nlat))[:, None] ** 4)
+    o.set_state(u, v, gd, o.ghs())
+    ghs = o.ghs()
+    o.run_init()
+    e0 = o.diag()[1]
+    npm = NpModel(nlon, nlat, dt, 4, split=split, cutoff=[4] * 3, time_scheme="runge_kutta", time_order=order)
+    npm.ghs = ghs
+    st = npm.make_state(u, v, gd)
+    for _ in range(3):
+        o.step(1)
+        st = npm.step(st)
+    ou, ov, ogd = o.state()
+    assert rel(ou, st[0]) < 1e-12 and rel(ogd, st[2]) < 1e-12
+    assert np.abs(ov - st[1]).max() < 1e-11 * max(1.0, np.abs(ou).max())
+    assert abs(o.diag()[2] - npm.beta) < 1e-12
+    assert abs(npm.beta - npm.beta_direct) < 1e-6   # the tendency-product form of beta is -2 <K, phi> / (dt <K, K>)
+    assert abs(o.diag()[2] - 1.0) < 1e-3            # beta = 1 + O(dt^2)
+    assert abs(o.diag()[1] / e0 - 1) < 5e-14        # energy kept by the beta fix
+
+
+@pytest.mark.parametrize("smooth,pass_", [(True, "fast"), (False, "fast"), (True, "slow"), (False, "all")])
+def test_moving_reduced_tendency_matches_numpy(smooth, pass_):
+    """the specified moving reduced tendency: on a row with factor r the tendency becomes the
+    average, over the r offsets of the reduced grid, of the reduced-cell means handed back to the fine cells -- written
+    here literally (box means for every offset), against the oracle's triangular-kernel form; then the s1 / s2 rescale"""
+    nlon, nlat = 72, 37
+    factors = [8, 4, 2]
+    u, v, gd, ghs = generic_state(nlon, nlat, seed=11)
+    base = dict(num_lon=nlon, num_lat=nlat, time_step_size=600)
+    o = Oracle(OracleConfig(use_zonal_reduce=True, reduce_adv_lon=True, use_reduce_tend_smooth=smooth,
+                            zonal_reduce_factors=factors, **base))
+    o0 = Oracle(OracleConfig(**base))      # no filter rows, no reduced rows: the raw tendencies
+    for q in (o, o0):
+        q.set_state(u, v, gd, ghs)
+        q.run_init()
+    got, raw = o.space_operators(pass_), o0.space_operators(pass_)
+    U, V, _ = o.iap_state()
+    wts = (U, V, gd + ghs)
+
+    def moving(row, r):
+        out = np.zeros_like(row)
+        for off in range(r):
+            x = np.roll(row, -off)
+            x = np.repeat(x.reshape(-1, r).mean(axis=1), r)
+            out += np.roll(x, off)
+        return out / r
+
+    for f, (g, t, w) in enumerate(zip(got, raw, wts)):
+        exp = t.copy()
+        nrows = t.shape[0]
+        for k, r in enumerate(factors, start=1):
+            rows = (k - 1, nrows - k) if f == 1 else (k, nrows - 1 - k)      # half rows / full rows next to the pole row
+            for j in rows:
+                if np.abs(t[j]).max() == 0.0:
+                    continue
+                s1 = np.sum(t[j] * w[j])
+                if smooth and not abs(s1) > 1e-16:
+                    continue
+                y = moving(t[j], r)
+                exp[j] = y * s1 / np.sum(y * w[j]) if smooth else y
+                assert abs(np.sum(y) - np.sum(t[j])) <= 1e-12 * np.abs(t[j]).sum()   # the reduction conserves the row sum
+        assert np.abs(g - exp).max() <= 1e-12 * max(np.abs(exp).max(), 1e-300)
+    # without reduce_adv_lon the slow pass is left alone
+    o2 = Oracle(OracleConfig(use_zonal_reduce=True, reduce_adv_lon=False, zonal_reduce_factors=factors, **base))
+    o2.set_state(u, v, gd, ghs)
+    o2.run_init()
+    for a, b in zip(o2.space_operators("slow"), o0.space_operators("slow")):
+        assert np.array_equal(a, b)
+
+
+def test_reduced_rows_reject_overlap_with_filter_rows_and_bad_factors():
+    with pytest.raises(Exception):
+        Oracle(OracleConfig(num_lon=72, num_lat=37, time_step_size=600, use_zonal_reduce=True, zonal_reduce_factors=[5]))
+    with pytest.raises(Exception):
+        Oracle(OracleConfig(num_lon=72, num_lat=37, time_step_size=600, use_zonal_reduce=True, zonal_reduce_factors=[4],
+                            zonal_tend_filter_cutoff_wavenumber=[4]))
+
+
 def test_weno_step_matches_numpy():
     """WENO advection (src/weno_mod.F90:69-300) through whole csp2 steps, second reading in tests/np_restatement.py"""
     nlon, nlat = 96, 49
@@ -386,7 +476,8 @@ def test_shallow_water_waves_ic_second_reading():
 
 
 @pytest.mark.parametrize("name", ["rh_36x19_csp2", "rh_72x37_nosplit", "mz_60x31_upwind", "jz_72x37_diffusion",
-                                  "sg_48x25_isp", "mz_48x25_weno", "mz_60x31_rk3_csp2", "sw_72x37_rk4_nosplit"])
+                                  "sg_48x25_isp", "mz_48x25_weno", "mz_60x31_rk3_csp2", "sw_72x37_rk4_nosplit",
+                                  "jz_72x37_reduce", "mz_60x31_reduce_plain"])
 def test_oracle_reproduces_committed_golden(name, golden_dir):
     from golden.make_golden import CASES
     d = np.load(golden_dir / f"case_{name}.npz")
