@@ -174,7 +174,8 @@ struct gmd_model {
   unsigned *d_bar = nullptr;   // grid barrier counters of k_cap
   int cap_ctas = 0;            // CTAs of a k_cap launch (co-resident; a multiple of the cluster size)
   int prio_hi = 0;             // launch priority of k_cap
-  int pdl = 0;                 // GMD_PDL: bit 0: polar rows after their sweep, bit 1: the next sweep after the polar rows
+  int pdl = 0;                 // GMD_PDL: bit 0: polar rows after their sweep, bit 1: the next sweep after the polar rows,
+                               // bit 2: the stage chain of a band without polar rows
 
   // comm: NCCL (optional) and the peer-memory path (gmd_peer_connect)
   void *comm = nullptr;
@@ -1034,7 +1035,13 @@ static int stage(gmd_model *m, int pass, int mode, const State &E, const State *
     dim3 grid((unsigned)m->nbx, (unsigned)nci, 1);
     static const char *const wnames[4] = {"k_stage.S1", "k_stage.S2", "k_stage.S3a", "k_stage.eval"};
     a.tseq = tseq(m, wnames[mode]);
-    if (!m->dry) fn<<<grid, BX, smem_i, m->stream>>>(a);
+    // a band without polar rows runs a plain chain of stage launches: programmatic dependent launch hides the launch
+    // latency between them (GMD_PDL bit 2)
+    a.pdl = ((m->pdl & 4) && m->cfg.nranks > 1 && !m->n_items[li]) ? 1 : 0;
+    if (!m->dry) {
+      if (a.pdl) launch_pdl<StageArgs>(fn, grid, dim3(BX), smem_i, m->stream, a);
+      else fn<<<grid, BX, smem_i, m->stream>>>(a);
+    }
     if ((r = post_launch(m))) return r;
   }
 
@@ -1776,6 +1783,10 @@ int gmd_create(const gmd_config *cfg, gmd_model **out) {
     CKD(cudaMalloc(&m->page, SP_WORDS * sizeof(u64)));
     CKD(cudaMemset(m->page, 0, SP_WORDS * sizeof(u64)));
     m->peer_page[cfg->rank < MAXR ? cfg->rank : 0] = m->page;
+    if (const char *ev = getenv("GMD_PEER_TIMEOUT_S")) {
+      const unsigned long long ns = (unsigned long long)std::max(1.0, atof(ev)) * 1000000000ull;
+      CKD(cudaMemcpyToSymbol(g_spin_timeout_ns, &ns, sizeof ns));
+    }
   }
   int r = build_tables(m);
   if (r) { gmd_destroy(m); return r; }

@@ -221,14 +221,19 @@ __device__ __forceinline__ void st_release_sys(u64 *p, u64 v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 // spin until *p >= want; a peer that never arrives (a bug, a dead rank) must not hang the GPU: give up after
-// ~20 s (once: later waits return at once), flag the page, carry on with whatever is there; gmd_sync turns the
-// flag into GMD_ERR_COMM
+// g_spin_timeout_ns (GMD_PEER_TIMEOUT_S, default 120 s of %globaltimer -- long enough for a neighbour that writes a
+// history file or sits under a profiler), once (later waits return at once), flag the page and carry on; the results
+// from then on are invalid and gmd_sync / gmd_step return GMD_ERR_COMM
+__device__ unsigned long long g_spin_timeout_ns = 120ull * 1000000000ull;
 __device__ __forceinline__ void spin_until(const u64 *p, u64 want, u64 *page) {
   if (ld_acquire_sys(p) >= want) return;
   if (*reinterpret_cast<volatile u64 *>(page + SP_ERR)) return;
-  const long long t0 = clock64();
+  u64 t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
   while (ld_acquire_sys(p) < want) {
-    if (clock64() - t0 > 40000000000LL) {
+    u64 t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    if (t1 - t0 > g_spin_timeout_ns) {
       *reinterpret_cast<volatile u64 *>(page + SP_ERR) = 1;
       return;
     }

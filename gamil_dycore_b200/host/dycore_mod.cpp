@@ -36,14 +36,14 @@ void dycore_init() {
   log_notice("Diag module is initialized.");
   {
     double period = 0.0;
-    if (!TimeManager::parse_period(params.history_periods, period))
+    if (!TimeManager::parse_period(params.history_periods, period, params.time_step_size))
       log_error("Invalid IO period " + params.history_periods + "!");
     timer.add_alert("hist0.output", period);
     log_notice("Create output dataset " + params.case_name + ".h0.");
     log_notice("Create output dataset " + params.case_name + ".debug.");
     log_notice("History module is initialized.");
     // restart_init, src/restart_mod.F90:22-35
-    if (!TimeManager::parse_period(params.restart_period, period))
+    if (!TimeManager::parse_period(params.restart_period, period, params.time_step_size))
       log_error("Invalid IO period " + params.restart_period + "!");
     timer.add_alert("restart.output", period);
     log_notice("Create output dataset " + params.case_name + ".r.");

@@ -99,7 +99,7 @@ int main(int argc, char **argv) {
     TimeManager tm;
     tm.init(p);
     double period = 0;
-    if (!TimeManager::parse_period(p.history_periods, period)) { printf("ERROR: bad period\n"); return 2; }
+    if (!TimeManager::parse_period(p.history_periods, period, p.time_step_size)) { printf("ERROR: bad period\n"); return 2; }
     tm.add_alert("hist0.output", period);
     printf("%s %d %ld %ld\n", tm.curr_time.format(true).c_str(), (int)tm.is_alerted("hist0.output"), tm.steps_until_alert("hist0.output"),
            tm.steps_until_end());

@@ -52,15 +52,23 @@ bool namelist_parse(const std::string &text, NamelistGroups &out, std::string &e
     while (i < n && (std::isalnum((unsigned char)text[i]) || text[i] == '_')) i++;
     if (i == b) { err = std::string("unexpected character '") + text[i] + "' in namelist group " + group; return false; }
     std::string key = lower(text.substr(b, i - b));
-    if (i < n && text[i] == '(') {  // subscripts are accepted and ignored (whole-array assignment only)
+    int sub = 0;   // name(k) = v1, v2, ...: the values start at element k (a single subscript; ranges are refused)
+    if (i < n && text[i] == '(') {
+      const size_t sb = ++i;
       while (i < n && text[i] != ')') i++;
+      const std::string inside = text.substr(sb, i - sb);
       if (i < n) i++;
+      char *endp = nullptr;
+      const long k = std::strtol(inside.c_str(), &endp, 10);
+      while (endp && *endp == ' ') endp++;
+      if (inside.empty() || !endp || *endp != '\0' || k < 1) { err = "unsupported subscript (" + inside + ") on " + key; return false; }
+      sub = (int)k;
     }
     skip_ws();
     if (i >= n || text[i] != '=') { err = "expected '=' after " + key; return false; }
     i++;
-    std::vector<std::string> &vals = out[group][key];
-    vals.clear();
+    std::vector<std::string> &dst = out[group][key];
+    std::vector<std::string> vals;
     while (true) {
       skip_ws();
       if (i >= n) break;
@@ -89,6 +97,12 @@ bool namelist_parse(const std::string &text, NamelistGroups &out, std::string &e
       while (k < n && (text[k] == ' ' || text[k] == '\t')) k++;
       if ((k < n && text[k] == '=') || (i < n && text[i] == '(')) { i = tb; break; }
       vals.push_back(text.substr(tb, te - tb));
+    }
+    if (sub <= 1) {
+      dst = vals;
+    } else {   // elements sub, sub+1, ... are assigned; a gap is padded with empty tokens (= "leave the element as it is")
+      if (dst.size() < (size_t)(sub - 1) + vals.size()) dst.resize((size_t)(sub - 1) + vals.size());
+      for (size_t q = 0; q < vals.size(); q++) dst[(size_t)(sub - 1) + q] = vals[q];
     }
   }
   return true;
@@ -153,6 +167,7 @@ bool params_from_text(const std::string &text, Params &p, std::string &err) {
       int *dst = (k == "start_time") ? p.start_time : p.end_time;
       if (v.size() > 5) { err = "too many values for " + k; return false; }
       for (size_t q = 0; q < v.size(); q++) {
+        if (v[q].empty()) continue;
         if (!to_num(v[q], x)) { err = "bad value for " + k; return false; }
         dst[q] = (int)x;
       }
@@ -166,6 +181,7 @@ bool params_from_text(const std::string &text, Params &p, std::string &err) {
       if (v.size() > 20) { err = "too many values for " + k; return false; }
       size_t q = 0;
       for (const std::string &tok : v) {  // r*c repeat form allowed
+        if (tok.empty()) { q++; continue; }
         size_t star = tok.find('*');
         int rep = 1;
         std::string val = tok;

@@ -94,7 +94,7 @@ struct TimeManager {
     curr_time_format = curr_time.format(false);
   }
   // "<value> <units>" as in history_periods (src/io_mod.F90:202-222)
-  static bool parse_period(const std::string &s, double &seconds) {
+  static bool parse_period(const std::string &s, double &seconds, double step_size = 0.0) {
     double v = 0;
     char unit[32] = "";
     if (sscanf(s.c_str(), "%lf %31s", &v, unit) != 2) return false;
@@ -103,6 +103,7 @@ struct TimeManager {
     else if (u == "hours") seconds = v * 3600.0;
     else if (u == "minutes") seconds = v * 60.0;
     else if (u == "seconds") seconds = v;
+    else if (u == "steps") seconds = v * step_size;   // src/io_mod.F90:209-210
     else return false;
     return true;
   }

@@ -51,6 +51,12 @@ CASES = [
                                  uv_adv_scheme="weno", zonal_tend_filter_cutoff_wavenumber=[4, 4]), 3),
     ("rossby_haurwitz_wave", dict(num_lon=360, num_lat=181, time_step_size=240.0, subcycles=6, split_scheme="csp2",
                                   zonal_tend_filter_cutoff_wavenumber=[4] * 5), 12),
+    # the specified extensions: runge_kutta and the moving reduced tendency across bands
+    ("mountain_zonal_flow", dict(num_lon=96, num_lat=49, time_step_size=600.0, subcycles=4, split_scheme="csp2",
+                                 time_scheme="runge_kutta", time_order=3, zonal_tend_filter_cutoff_wavenumber=[4, 4]), 3),
+    ("jet_zonal_flow", dict(num_lon=144, num_lat=73, time_step_size=450.0, subcycles=6, split_scheme="csp2",
+                            use_zonal_reduce=True, reduce_adv_lon=True, use_reduce_tend_smooth=True,
+                            zonal_reduce_factors=[8, 4, 2, 2], use_diffusion=True, diffusion_coef=1.0e5), 3),
 ]
 
 

@@ -108,6 +108,31 @@ def test_namelist_defaults_comments_and_unknown_keys(tmp_path):
     assert rc == 2 and "Cannot match namelist object name days" in out
 
 
+def test_namelist_subscripts_and_steps_period(tmp_path):
+    """name(k) = ... assigns from element k on, as gfortran does (a round-1 build ignored the subscript); the IO period
+    unit 'steps' of src/io_mod.F90:209-210"""
+    text = """&dycore_params
+ test_case = 'rossby_haurwitz_wave', case_name='x'
+ num_lon = 36, num_lat = 19, time_step_size = 150
+ zonal_tend_filter_cutoff_wavenumber = 4, 4
+ zonal_tend_filter_cutoff_wavenumber(3) = 3, 2
+ zonal_tend_filter_cutoff_wavenumber(7) = 1
+ history_periods = '8 steps'
+/
+"""
+    rc, kv, out = parse(write(tmp_path, text))
+    assert rc == 0, out
+    assert kv["cutoff"] == "4,4,3,2,0,0,1" + ",0" * 13
+    rc, out = selftest("clock", write(tmp_path, text.replace("/\n", " run_hours = 1\n/\n"), "clk"), "20")
+    assert rc == 0, out   # one line per step: the history alert rings every 8 steps = 1200 s
+    lines = out.strip().splitlines()
+    rings = [k for k, l in enumerate(lines[1:], 1) if l.split()[1] == "1"]
+    assert rings and rings[0] == 8
+    bad = text.replace("(3) = 3, 2", "(3:4) = 3, 2")
+    rc, _, out = parse(write(tmp_path, bad, "bad"))
+    assert rc == 2 and "unsupported subscript" in out
+
+
 def test_reduced_tendency_and_runge_kutta_keys_parse(tmp_path):
     """the keys of the reference's own run/namelist.jz_test:12-19 that its params_mod does not define (use_zonal_reduce,
     reduce_adv_lon, zonal_reduce_factors, use_reduce_tend_smooth) and time_scheme = 'runge_kutta' / time_order
