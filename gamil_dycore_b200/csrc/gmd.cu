@@ -6,6 +6,9 @@
 // between two host calls is stream-ordered on one CUDA stream; beta never leaves the device.
 #include "../../include/gmd.h"
 #include "gmd_kernels.cuh"
+#if !GMD_STRICT
+#include "gmd_pc.cuh"
+#endif
 #include "gmd_mesh.h"
 
 #include <dlfcn.h>
@@ -137,6 +140,8 @@ struct gmd_model {
   State cur;
   double *ghs = nullptr;
   Tend tendOld, tendNew, tendNew2, tendA, tendB;  // tendA/B: isp only
+  // (also with the fused predict_correct kernel on one band: its S3a warps write the new tendency while the S1 warps of
+  // other CTAs still read the previous one -- the deferred update -- so the two must be different buffers)
   // the new tendency of predict_correct alternates between tendNew and tendNew2: a neighbour band stores the ghost
   // rows of predict_correct k+1 while this band may still be reading those of k (deferred update)
   int tn_idx = 0;
@@ -176,6 +181,16 @@ struct gmd_model {
   int prio_hi = 0;             // launch priority of k_cap
   int pdl = 0;                 // GMD_PDL: bit 0: polar rows after their sweep, bit 1: the next sweep after the polar rows,
                                // bit 2: the stage chain of a band without polar rows
+  // fused predict_correct (k_pc, gmd_pc.cuh): rows [fz_I0, fz_I1) run the three sweeps as one wavefront kernel on
+  // stream2; the rows next to a pole -- [r0, fz_I0) and [fz_I1, r1), which hold the filter / reduced / pole rows plus
+  // the (2, 4) plain rows the wavefront must keep away from them -- run the k_stage + k_polar chain on the main stream,
+  // each sweep widened towards the fused rows by what the later sweeps of the chain read (nothing is exchanged)
+  bool fused = false;
+  int fz_I0 = 0, fz_I1 = 0, fz_rpc = 0, fz_nchunks = 0, fz_nstrips = 0;
+  int fz_ncb = 0;              // row chunks of a (widened) polar-side launch
+  bool fz_active = false;      // inside the three stage() calls of a fused predict_correct
+  Fold fz_fold;                // the inner-product fold shared by k_pc and the S3a polar-side launches
+  cudaEvent_t fz_ev = nullptr; // completion of the k_pc launch on stream2
 
   // comm: NCCL (optional) and the peer-memory path (gmd_peer_connect)
   void *comm = nullptr;
@@ -543,6 +558,26 @@ static stage_fn pick_stage_lazy_t(int pass, int adv) {
 static stage_fn pick_stage_lazy(int pass, int adv, int lazy) {
   return lazy == 1 ? pick_stage_lazy_t<1>(pass, adv) : pick_stage_lazy_t<2>(pass, adv);
 }
+
+// the fused predict_correct kernel (gmd_pc.cuh; product build, never WENO)
+#if !GMD_STRICT
+template <int LZ, bool PUSH>
+static stage_fn pick_pc_t(int pass, int adv) {
+  if (pass == PASS_FAST) return k_pc<PASS_FAST, ADV_CENTER, LZ, PUSH>;
+  if (pass == PASS_ALL) return adv == ADV_UPWIND ? k_pc<PASS_ALL, ADV_UPWIND, LZ, PUSH> : k_pc<PASS_ALL, ADV_CENTER, LZ, PUSH>;
+  return adv == ADV_UPWIND ? k_pc<PASS_SLOW, ADV_UPWIND, LZ, PUSH> : k_pc<PASS_SLOW, ADV_CENTER, LZ, PUSH>;
+}
+static stage_fn pick_pc(int pass, int adv, int lazy, bool push) {
+  if (adv == ADV_WENO) return nullptr;
+  if (push) return lazy == 0 ? pick_pc_t<0, true>(pass, adv) : (lazy == 1 ? pick_pc_t<1, true>(pass, adv) : pick_pc_t<2, true>(pass, adv));
+  return lazy == 0 ? pick_pc_t<0, false>(pass, adv) : (lazy == 1 ? pick_pc_t<1, false>(pass, adv) : pick_pc_t<2, false>(pass, adv));
+}
+static const size_t PC_SMEM_BYTES = PC_SMEM;
+#else
+static stage_fn pick_pc(int, int, int, bool) { return nullptr; }
+static const size_t PC_SMEM_BYTES = 0;
+static const int WOUT3 = 54, PC_BX = 96;
+#endif
 
 // the fused polar-cap kernel (never WENO: its advection terms come from separate sweeps)
 typedef void (*cap_fn)(const StageArgs, const PolarArgs, const CapArgs);
@@ -951,9 +986,55 @@ static int stage(gmd_model *m, int pass, int mode, const State &E, const State *
     }
   }
   if ((r = allow_smem((const void *)fn))) return r;
+  const int li = (pass == PASS_SLOW) ? 1 : 0;
+  if (m->fz_active) {
+    // fused predict_correct: k_pc (already launched, stream2) covers rows [fz_I0, fz_I1); this call runs the rows next to
+    // the poles, widened towards the fused rows by what the later sweeps of this chain read: S1 (4 north of the southern
+    // range, 2 south of the northern one), S2 (2, 1), S3a none
+    const int xs = (mode == MODE_S1) ? 4 : (mode == MODE_S2 ? 2 : 0), xn = (mode == MODE_S1) ? 2 : (mode == MODE_S2 ? 1 : 0);
+    const bool haveS = m->fz_I0 > r0, haveN = m->fz_I1 < r1;
+    const int ncb = (haveS || haveN) ? m->fz_ncb : 0;
+    const int nst = 2 * m->nbx * ncb + m->fz_nstrips * m->fz_nchunks;
+    if (mode == MODE_S3A) a.fold = m->fz_fold;
+    if (ncb) {
+      StageArgs b = a;
+      b.hpS_U = b.hpS_V = b.hpS_G = b.hpN_U = b.hpN_V = b.hpN_G = nullptr;
+      b.rows_per_cta = m->rows_per_cta_b;
+      b.rb[0] = r0; b.re[0] = haveS ? m->fz_I0 + xs : r0; b.pofs[0] = 0;
+      b.rb[1] = haveN ? m->fz_I1 - xn : r1; b.re[1] = r1; b.pofs[1] = m->nbx * ncb;
+      dim3 gb((unsigned)m->nbx, (unsigned)ncb, 2);
+      static const char *const bnames[4] = {"k_stage.S1.polar_side", "k_stage.S2.polar_side", "k_stage.S3a.polar_side", "k_stage.eval.polar_side"};
+      b.tseq = tseq(m, bnames[mode]);
+      b.pdl = (m->pdl & 2) && (mode == MODE_S2 || mode == MODE_S3A) && m->n_items[li] ? 1 : 0;
+      if (!m->dry) {
+        if (b.pdl) launch_pdl<StageArgs>(fn, gb, dim3(BX), m->stage_smem_b, m->stream, b);
+        else fn<<<gb, BX, m->stage_smem_b, m->stream>>>(b);
+      }
+      if ((r = post_launch(m))) return r;
+    }
+    if (m->n_items[li]) {
+      PolarArgs p;
+      polar_args(m, a, lz != nullptr, li, nst, dt, &p);
+      p.tseq = tseq(m, "k_polar");
+      if (!m->dry) launch_polar(m, mode, m->n_items[li], p, m->stream, ncb && (m->pdl & 1));
+      if ((r = post_launch(m))) return r;
+    }
+    if (mode == MODE_S3A) {
+      if (m->fz_ev) m->last_eI = m->fz_ev;   // whoever reads the new tendency next waits for k_pc
+      m->fz_ev = nullptr;
+      if (!a.fold.ticket) {
+        if ((r = join(m))) return r;
+        RedArgs ra = red_args(m);
+        ra.tseq = tseq(m, "k_reduce_pairs.ip");
+        if (!m->dry) k_reduce_pairs<<<1, 256, 0, m->stream>>>(m->d_partials, nst + m->n_items[li], m->d_ip, ra);
+        if ((r = post_launch(m))) return r;
+        if ((r = allreduce2(m, m->d_ip))) return r;
+      }
+    }
+    return 0;
+  }
   const bool poleS = (r0 == 0), poleN = (r1 == m->geo.nlat);
   const int R0 = r0 - es, R1 = r1 + en;   // rows of this sweep
-  const int li = (pass == PASS_SLOW) ? 1 : 0;
   const bool split = use_split(m);
   // launch geometry
   const int I0 = split ? (poleS ? r0 + m->bs : R0) : R0, I1 = split ? (poleN ? r1 - m->bn : R1) : R1;
@@ -1092,6 +1173,70 @@ static int update(gmd_model *m, const State &O, const Tend &T, double dt, int be
   return post_launch(m);
 }
 
+// The fused sweep of a predict_correct over rows [fz_I0, fz_I1) (k_pc, gmd_pc.cuh): tend(new) of L(L-updated states)
+// into Tn, the inner-product partials, the deferred update materialised into lz->M.  With rows next to a pole on this
+// band the launch goes to stream2 and the polar-side chain (the three stage() calls that follow, m->fz_active) runs
+// beside it on the main stream; otherwise it is the only launch of the predict_correct and stays on the main stream.
+static int launch_pc(gmd_model *m, int pass, const State &E, const LazyIn *lz, double dt, Tend *Tn, bool push) {
+  int r;
+  const int adv = m->cfg.uv_adv_scheme;
+  const int r0 = m->geo.r0, r1 = m->geo.r1;
+  const bool push_ok = push && m->p2p;
+  stage_fn fn = pick_pc(pass, adv, lz ? lz->kind : 0, push_ok);
+  if (!fn) return fail(GMD_ERR_STATE, "internal: no fused predict_correct kernel for this configuration");
+  if ((r = halo_wait(m))) return r;
+  StageArgs a;
+  memset(&a, 0, sizeof a);
+  a.g = m->geo;
+  a.t = m->tab;
+  a.EU = E.U; a.EV = E.V; a.Egd = E.gd; a.ghs = m->ghs;
+  a.TU = Tn->U; a.TV = Tn->V; a.Tgd = Tn->gd;
+  a.dt = dt;
+  a.beta_lon = m->cfg.uv_adv_upwind_lon_beta;
+  a.beta_lat = m->cfg.uv_adv_upwind_lat_beta;
+  a.partials = m->d_partials;
+  if (lz) {
+    a.LU = lz->L->U; a.LV = lz->L->V; a.Lgd = lz->L->gd;
+    a.MU = lz->M->U; a.MV = lz->M->V; a.Mgd = lz->M->gd;
+    a.lip = m->d_ip;
+    a.ldt = lz->ldt;
+    a.lqcon = m->cfg.qcon_modified;
+  }
+  if (push_ok) {
+    double *fg = (pass == PASS_SLOW) ? nullptr : Tn->gd;
+    a.hpS_U = peer_ptr(m, 0, Tn->U); a.hpS_V = peer_ptr(m, 0, Tn->V); a.hpS_G = peer_ptr(m, 0, fg);
+    a.hpN_U = peer_ptr(m, 1, Tn->U); a.hpN_V = peer_ptr(m, 1, Tn->V); a.hpN_G = peer_ptr(m, 1, fg);
+    a.push_s_end = r0 + HALO_N;
+    a.push_n_begin = r1 - HALO_S;
+  }
+  const bool polar_side = (m->fz_I0 > r0) || (m->fz_I1 < r1);
+  a.rows_per_cta = m->fz_rpc;
+  a.rb[0] = m->fz_I0; a.re[0] = m->fz_I1;
+  a.pofs[0] = polar_side ? 2 * m->nbx * m->fz_ncb : 0;
+  // band edges with a neighbour: the deferred update is also materialised on the ghost rows the sweep reads
+  a.medge[0] = ((m->wide && m->cfg.rank > 0 && m->fz_I0 == r0) ? 1 : 0) | ((m->wide && m->cfg.rank + 1 < m->cfg.nranks && m->fz_I1 == r1) ? 2 : 0);
+  a.fold = m->fz_fold;
+  dim3 grid((unsigned)m->fz_nstrips, (unsigned)m->fz_nchunks, 1);
+  a.tseq = tseq(m, "k_pc");
+  if ((r = join(m))) return r;
+  m->fz_ev = nullptr;
+  if (polar_side) {
+    if (!m->dry) {
+      cudaEvent_t e = next_event(m);
+      CK(cudaEventRecord(e, m->stream));
+      CK(cudaStreamWaitEvent(m->stream2, e, 0));
+      fn<<<grid, PC_BX, PC_SMEM_BYTES, m->stream2>>>(a);
+      cudaEvent_t f = next_event(m);
+      CK(cudaEventRecord(f, m->stream2));
+      m->fz_ev = f;
+    }
+    m->ev_polar_side = nullptr;
+  } else if (!m->dry) {
+    fn<<<grid, PC_BX, PC_SMEM_BYTES, m->stream>>>(a);
+  }
+  return post_launch(m);
+}
+
 // A state handed from one predict_correct to the next.  `deferred`: the value is base + beta dts tendNew with beta
 // from the inner products still on the device -- the last update_state of predict_correct (src/dycore_mod.F90:
 // 786-790) has not been run; the next predict_correct folds it into its first operator sweep (k_stage LAZY), which
@@ -1119,7 +1264,7 @@ static int predict_correct(gmd_model *m, double dts, const Carry &in, int pass, 
   const bool wide = m->wide;
   const int hs = (wide && m->cfg.rank > 0) ? 1 : 0, hn = (wide && m->cfg.rank + 1 < m->cfg.nranks) ? 1 : 0;
   Tend *Tn = &m->tendNew;
-  if (m->cfg.nranks > 1) {   // see gmd_model::tn_idx
+  if (m->cfg.nranks > 1 || m->fused) {   // see gmd_model::tn_idx
     if (m->tn_idx) Tn = &m->tendNew2;
     m->tn_idx ^= 1;
   }
@@ -1133,19 +1278,45 @@ static int predict_correct(gmd_model *m, double dts, const Carry &in, int pass, 
   }
   if ((r = new_state(m, &A, slow ? O.gd : nullptr))) return r;
   if ((r = new_state(m, &B, slow ? O.gd : nullptr))) return r;
+  const bool fz = m->fused;
+  if (fz) {
+    // the three sweeps of rows [fz_I0, fz_I1) as one wavefront kernel; the stage() calls below then only run the rows
+    // next to the poles (m->fz_active)
+    const int li = slow ? 1 : 0;
+    const bool polar_side = (m->fz_I0 > m->geo.r0) || (m->fz_I1 < m->geo.r1);
+    const int nst = (polar_side ? 2 * m->nbx * m->fz_ncb : 0) + m->fz_nstrips * m->fz_nchunks;
+    static const int fold_env = getenv("GMD_FOLD") ? atoi(getenv("GMD_FOLD")) : -1;
+    memset(&m->fz_fold, 0, sizeof m->fz_fold);
+    if ((m->cfg.nranks == 1 || m->p2p) && fold_env != 0) {
+      m->fz_fold.ticket = reinterpret_cast<unsigned *>(m->d_ip + 7);
+      m->fz_fold.total = (unsigned)(nst + m->n_items[li]);
+      m->fz_fold.n = nst + m->n_items[li];
+      m->fz_fold.out = m->d_ip;
+      m->fz_fold.r = red_args(m);
+    }
+    LazyIn lz = {in.L, in.dts, &M, in.with_gd ? 1 : 2};
+    if ((r = launch_pc(m, pass, in.deferred ? in.base : O, in.deferred ? &lz : nullptr, dt, Tn, wide && m->fuse_push))) return r;
+    m->fz_active = true;
+  }
+  struct FzGuard {   // an error return below must not leave the model in polar-side-only mode
+    gmd_model *m;
+    ~FzGuard() { m->fz_active = false; }
+  } fz_guard = {m};
+  const int ws = fz ? 0 : 1;   // the fused kernel widens its own sweeps at the band edges
   // tend(old) = L(old); new = old + dt/2 tend(old)
   if (in.deferred) {
     LazyIn lz = {in.L, in.dts, &M, in.with_gd ? 1 : 2};
-    if ((r = stage(m, pass, MODE_S1, in.base, nullptr, dt, &A, &m->tendOld, nullptr, &lz, 2 * hs, 4 * hn))) return r;
+    if ((r = stage(m, pass, MODE_S1, in.base, nullptr, dt, &A, &m->tendOld, nullptr, &lz, 2 * hs * ws, 4 * hn * ws))) return r;
   } else {
-    if ((r = stage(m, pass, MODE_S1, O, &O, dt, &A, &m->tendOld, nullptr, nullptr, 2 * hs, 4 * hn))) return r;
+    if ((r = stage(m, pass, MODE_S1, O, &O, dt, &A, &m->tendOld, nullptr, nullptr, 2 * hs * ws, 4 * hn * ws))) return r;
   }
   if (!wide && (r = exchange_state(m, A, !slow))) return r;
   // tend(old) = L(new); new = old + dt/2 tend(old)
-  if ((r = stage(m, pass, MODE_S2, A, &O, dt, &B, &m->tendOld, nullptr, nullptr, hs, 2 * hn))) return r;
+  if ((r = stage(m, pass, MODE_S2, A, &O, dt, &B, &m->tendOld, nullptr, nullptr, hs * ws, 2 * hn * ws))) return r;
   if (!wide && (r = exchange_state(m, B, !slow))) return r;
   // tend(new) = L(new); ip1 = <tend(old), tend(new)>, ip2 = <tend(new), tend(new)>
-  if ((r = stage(m, pass, MODE_S3A, B, nullptr, 0.0, nullptr, Tn, &m->tendOld, nullptr, 0, 0, wide && m->fuse_push))) return r;
+  if ((r = stage(m, pass, MODE_S3A, B, nullptr, 0.0, nullptr, Tn, &m->tendOld, nullptr, 0, 0, !fz && wide && m->fuse_push))) return r;
+  m->fz_active = false;
   if (wide && m->p2p) m->need_fence = true;
   release_state(m, &B);
   if (wide && !m->fuse_push) {   // NCCL, or a peer run whose band-edge rows are filtered rows
@@ -1915,6 +2086,47 @@ int gmd_create(const gmd_config *cfg, gmd_model **out) {
       m->cap_ctas = lim;
       if (n_march > lim) m->cap = false, m->split = m->split && m->wide;
     }
+    // fused predict_correct (k_pc): product build, predict_correct with centred / upwind advection, one band or wide-halo
+    // bands.  The fused rows keep (2 south, 4 north) plain rows between themselves and every row that takes part in a
+    // full-row operation (filter rows, reduced rows, pole rows): S1 of the wavefront covers that many rows more.
+    m->fused = !GMD_STRICT && cfg->uv_adv_scheme != GMD_ADV_WENO && cfg->time_scheme == GMD_TIME_PREDICT_CORRECT &&
+               (cfg->nranks == 1 || m->wide);
+    if (const char *ev = getenv("GMD_FUSED")) m->fused = m->fused && atoi(ev) != 0;
+    if (m->fused) {
+      auto flagged = [&](int j) {
+        return j <= 0 || j >= nlat - 1 || m->mesh.flag_full[(size_t)j] || m->mesh.flag_half[(size_t)j] ||
+               m->mesh.red_full[(size_t)j] > 1 || m->mesh.red_half[(size_t)j] > 1;
+      };
+      int I0 = m->geo.r0, I1 = m->geo.r1;
+      for (int j = m->geo.r0; j < m->geo.r1; j++)
+        if (flagged(j)) {
+          if (j < nlat / 2) I0 = std::max(I0, j + 3);
+          else I1 = std::min(I1, j - 4);
+        }
+      // a flagged row of the other hemisphere's cap inside [I0, I1) (a band that spans both caps with rows flagged
+      // far from the poles) cannot happen: caps are contiguous from their pole
+      for (int j = std::max(I0 - 2, 0); j < std::min(I1 + 4, nlat) && m->fused; j++)
+        if (flagged(j)) m->fused = false;
+      if (I1 - I0 < 6) m->fused = false;
+      m->fz_I0 = I0;
+      m->fz_I1 = I1;
+    }
+    if (m->fused) {
+      const int adv = cfg->uv_adv_scheme;
+      stage_fn f0 = pick_pc(pass0, adv, 1, false);
+      int ps = 0;
+      CKD(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ps, f0, PC_BX, PC_SMEM_BYTES));
+      ps = std::max(ps, 1);
+      if (const char *ev = getenv("GMD_PC_CTAS_PER_SM")) ps = std::max(1, atoi(ev));
+      m->fz_nstrips = (nlon + WOUT3 - 1) / WOUT3;
+      const int rows = m->fz_I1 - m->fz_I0;
+      const int want = std::max(1, nsm * ps / m->fz_nstrips);
+      m->fz_rpc = std::max(4, (rows + want - 1) / want);
+      if (const char *ev = getenv("GMD_PC_ROWS")) m->fz_rpc = std::max(1, atoi(ev));
+      m->fz_nchunks = (rows + m->fz_rpc - 1) / m->fz_rpc;
+      const int tall = std::max(m->fz_I0 > m->geo.r0 ? m->fz_I0 - m->geo.r0 + 4 : 0, m->fz_I1 < m->geo.r1 ? m->geo.r1 - m->fz_I1 + 2 : 0);
+      m->fz_ncb = (tall + m->rows_per_cta_b - 1) / m->rows_per_cta_b;
+    }
     CKD(cudaStreamCreateWithFlags(&m->stream2, cudaStreamNonBlocking));
     m->evpool.resize(64);
     for (auto &e : m->evpool) CKD(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -1925,6 +2137,7 @@ int gmd_create(const gmd_config *cfg, gmd_model **out) {
     const int rmin = std::max(1, std::min(m->rows_per_cta, m->rows_per_cta_s3a));
     const int cmax = (m->nr + rmin - 1) / rmin + 2;
     m->n_partials = std::max(m->nbx * (2 * cmax + 2 * m->nchunks_b) + m->n_items[0] + m->n_items[1], m->ew_blocks) + 16;
+    if (m->fused) m->n_partials = std::max(m->n_partials, 2 * m->nbx * m->fz_ncb + m->fz_nstrips * m->fz_nchunks + m->n_items[0] + m->n_items[1] + 16);
   }
   CKD(cudaMalloc(&m->d_partials, (size_t)m->n_partials * 2 * sizeof(double)));
   CKD(cudaMalloc(&m->d_ip, 8 * sizeof(double)));
@@ -1945,7 +2158,7 @@ int gmd_create(const gmd_config *cfg, gmd_model **out) {
   if (2 * (size_t)nlon * sizeof(double) > 200 * 1024) { fail(GMD_ERR_ARG, "num_lon too large for the polar-row kernel"); gmd_destroy(m); return GMD_ERR_ARG; }
   // persistent buffers
   if ((r = new_state(m, &m->cur, nullptr)) || (r = acquire(m, KIND_G, &m->ghs)) || (r = new_tend(m, &m->tendOld)) ||
-      (r = new_tend(m, &m->tendNew)) || (cfg->nranks > 1 && (r = new_tend(m, &m->tendNew2)))) {
+      (r = new_tend(m, &m->tendNew)) || ((cfg->nranks > 1 || m->fused) && (r = new_tend(m, &m->tendNew2)))) {
     gmd_destroy(m);
     return r;
   }
