@@ -2108,6 +2108,9 @@ int gmd_create(const gmd_config *cfg, gmd_model **out) {
       for (int j = std::max(I0 - 2, 0); j < std::min(I1 + 4, nlat) && m->fused; j++)
         if (flagged(j)) m->fused = false;
       if (I1 - I0 < 6) m->fused = false;
+      // a band of a multi-band run that holds polar rows keeps the three-sweep path: its step time is the chain
+      // sweep -> polar rows -> sweep ..., and the polar-row CTAs (one SM each) cannot start while k_pc owns the SMs
+      if (cfg->nranks > 1 && (I0 > m->geo.r0 || I1 < m->geo.r1) && !getenv("GMD_FUSED_POLAR_BANDS")) m->fused = false;
       m->fz_I0 = I0;
       m->fz_I1 = I1;
     }

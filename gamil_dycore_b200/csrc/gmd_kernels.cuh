@@ -428,7 +428,8 @@ __device__ __forceinline__ double shfl_dn1(double v) { return __shfl_down_sync(0
 // tendencies of ONE column at row j; all operands are scalars already in registers
 template <int PASS, int ADV>
 __device__ __forceinline__ void tend_col(
-    const double *__restrict__ rc, const bool rowU, const bool rowV, const bool rowG, const double bl, const double bt,
+    const double *__restrict__ rc, const double *__restrict__ rcn /* record of row j+1 */, const bool rowU, const bool rowV,
+    const bool rowG, const double bl, const double bt,
     const double hc0, const double hc1, const double hc2,
     // row j
     const double uw, const double uc, const double ue, const double Uw, const double Uc, const double Ue,
@@ -506,7 +507,7 @@ __device__ __forceinline__ void tend_col(
       dV = -alon - alat;
     }
     if (PASS != PASS_SLOW) {
-      const double f0 = rc[RC_FF], c0 = rc[RC_FC], f1 = rc[RC_N + RC_FF], c1 = rc[RC_N + RC_FC];
+      const double f0 = rc[RC_FF], c0 = rc[RC_FC], f1 = rcn[RC_FF], c1 = rcn[RC_FC];
       const double fu = 0.25 * ((f0 + c0 * uc) * Uc + (f0 + c0 * uw) * Uw + (f1 + c1 * un) * Un +
                                 (f1 + c1 * unw) * Unw);   // :495-503
 #if GMD_STRICT
@@ -921,13 +922,13 @@ __device__ __forceinline__ void stage_body(const StageArgs &a, const int bx, con
       const double cfj = rc[RC_COSF];
       double dUa, dVa, dGa, dUb, dVb, dGb;
       // column a: west = lane-1's b (shuffled / carried), east = own b
-      tend_col<PASS, ADV>(rc, rowU, rowV, rowG, a.beta_lon, a.beta_lat, hc0, hc1, hc2,
+      tend_col<PASS, ADV>(rc, rc + RC_N, rowU, rowV, rowG, a.beta_lon, a.beta_lat, hc0, hc1, hc2,
                           uw_a, u0.x, u0.y, Uw_a, U0.x, U0.y, Vw_a, V0.x, V0.y, sw_a, s0.x, s0.y, v0.x, v0.y,
                           Um.x, Vm.x, Vm.y, vm.x, vm.y, sm_.x,
                           Up.x, Unw_a, up.x, unw_a, Vp.x, vp.x, sp.x,
                           ghdx_a, ghdy_a, wul.x, wut.x, wvl.x, wvt.x, dUa, dVa, dGa);
       // column b: west = own a, east = lane+1's a (shuffled / carried)
-      tend_col<PASS, ADV>(rc, rowU, rowV, rowG, a.beta_lon, a.beta_lat, hc0, hc1, hc2,
+      tend_col<PASS, ADV>(rc, rc + RC_N, rowU, rowV, rowG, a.beta_lon, a.beta_lat, hc0, hc1, hc2,
                           u0.x, u0.y, ue_b, U0.x, U0.y, Ue_b, V0.x, V0.y, Ve_b, s0.x, s0.y, se_b, v0.y, ve_b,
                           Um.y, Vm.y, Vse_b, vm.y, vse_b, sm_.y,
                           Up.y, Up.x, up.y, up.x, Vp.y, vp.y, sp.y,

@@ -53,7 +53,10 @@ __host__ __device__ constexpr int pc_ring_line0(int kind) {
 // the HBM latency (measured: 6 barrier-stall cycles per issued instruction with a one-row register prefetch).
 constexpr int PC_IN_DEPTH = 4, PC_IN_NF = 7;
 enum { IN_GD = 0, IN_U = 1, IN_V = 2, IN_HS = 3, IN_TG = 4, IN_TU = 5, IN_TV = 6 };
-constexpr size_t PC_SMEM = (size_t)(PC_RING_LINES + PC_IN_DEPTH * PC_IN_NF) * 512 + PC_IN_DEPTH * 8;   // 42016 bytes per CTA
+// Row records (128 bytes per latitude row, gmd_kernels.cuh RC_*): a 16-row ring per CTA, filled with S1's packets (the
+// record of row j+1 travels with the packet of iteration j) and read by all three warps -- S3a is 10 rows behind S1.
+constexpr int PC_REC_DEPTH = 16;
+constexpr size_t PC_SMEM = (size_t)(PC_RING_LINES + PC_IN_DEPTH * PC_IN_NF) * 512 + PC_REC_DEPTH * RC_N * 8 + PC_IN_DEPTH * 8;   // 44064 bytes per CTA
 
 // Tick table (rows relative to ja; tick t ends with barrier t):
 //   S1  evaluates row x in tick x + 2            and writes A(x), old(x) into the rings
@@ -86,18 +89,6 @@ __device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
                "r"(bytes), "r"(bar) : "memory");
 }
-// one row of a strip (64 columns from column cs, periodic) of field f into a 512-byte line
-__device__ __forceinline__ void bulk_row(unsigned dst, const double *rowp, int cs, int nlon, unsigned bar) {
-  int rem = 64, col = cs;
-  while (rem > 0) {
-    const int n = min(rem, nlon - col);
-    bulk_g2s(dst, rowp + col, (unsigned)n * 8u, bar);
-    dst += (unsigned)n * 8u;
-    rem -= n;
-    col = 0;
-  }
-}
-
 template <int PASS, int ADV, int ROLE, int LAZY, bool PUSH>
 __device__ __forceinline__ void pc_role(const StageArgs &a, const int strip, const int ja, const int jb, const bool edgeS,
                                         const bool edgeN, D2 *const ring, double &ip1, double &ip2) {
@@ -133,8 +124,6 @@ __device__ __forceinline__ void pc_role(const StageArgs &a, const int strip, con
     *reinterpret_cast<double2 *>(ring + line(kind, x, f) * 32) = make_double2(v.x, v.y);
   };
 
-  for (int t = 0; t < T0; t++) pc_bar();
-
   ptrdiff_t off = (ptrdiff_t)(rja - r0) * nl + (ptrdiff_t)c0;   // element offset of (row j, column c0)
 #define ATK(p, k) ((p) + (off + (ptrdiff_t)(k) * nl))
 #define AT(p, jj) ATK(p, (jj) - j)
@@ -158,7 +147,6 @@ __device__ __forceinline__ void pc_role(const StageArgs &a, const int strip, con
   // ---- ROLE 0: input ring ---------------------------------------------------------------------------------------
   const D2 *const in_ring = ring + PC_RING_LINES * 32;   // (this lane's 16 bytes of) line 0 of the input ring
   const unsigned in_sa = (unsigned)__cvta_generic_to_shared(ring - lane) + (unsigned)PC_RING_LINES * 512u;
-  const unsigned in_bar = in_sa + (unsigned)(PC_IN_DEPTH * PC_IN_NF) * 512u;
   auto ldl = [&](const D2 *q) -> D2 {
     const double2 v = *reinterpret_cast<const double2 *>(q);
     D2 r;
@@ -166,35 +154,75 @@ __device__ __forceinline__ void pc_role(const StageArgs &a, const int strip, con
     r.y = v.y;
     return r;
   };
-  // packet of iteration r (one thread): rows r+2 of gd / Lgd, r+1 of U, V, ghs, LU, LV, 64 columns from this strip's first
-  auto issue_packet = [&](const int r) {
-    const int st = (r - rja) % PC_IN_DEPTH;
-    const unsigned d = in_sa + (unsigned)(st * PC_IN_NF) * 512u, bar = in_bar + 8u * (unsigned)st;
-    int cs = strip * WOUT3 - 4;
+  const unsigned rec_sa = in_sa + (unsigned)(PC_IN_DEPTH * PC_IN_NF) * 512u;
+  const unsigned in_bar = rec_sa + (unsigned)(PC_REC_DEPTH * RC_N) * 8u;
+  const double *const rec = reinterpret_cast<const double *>(ring - lane) + (size_t)(PC_RING_LINES + PC_IN_DEPTH * PC_IN_NF) * 64;
+  // record of row x (x >= rja0 - 1, rja0 = ja - 2: the first row S1 evaluates)
+  auto recp = [&](int x) -> const double * { return rec + ((unsigned)(x - (ja - 3)) % (unsigned)PC_REC_DEPTH) * RC_N; };
+  // packet of iteration r: rows r+2 of gd / Lgd, r+1 of U, V, ghs, LU, LV (64 columns from this strip's first) and the
+  // record of row r+1.  Everything here is warp-uniform (uniform datapath); one elected lane issues the copies.
+  constexpr unsigned pk_nf = 3u + (need_gh ? 1u : 0u) + (LAZY == 1 ? 3u : (LAZY == 2 ? 2u : 0u));
+  const int rja0 = ja - 2, rjb0 = jb + 4;   // the rows S1 evaluates
+  int cs = 0, n1 = 64;
+  if (ROLE <= 1) {
+    cs = strip * WOUT3 - 4;
     cs %= nlon;
     if (cs < 0) cs += nlon;
-    constexpr unsigned nf = 3u + (need_gh ? 1u : 0u) + (LAZY == 1 ? 3u : (LAZY == 2 ? 2u : 0u));
-    mbar_expect_tx(bar, nf * 512u);
-    const ptrdiff_t o1 = (ptrdiff_t)(r + 1 - r0) * nl, o2 = o1 + nl;
-    bulk_row(d + IN_GD * 512u, a.Egd + o2, cs, nlon, bar);
-    bulk_row(d + IN_U * 512u, a.EU + o1, cs, nlon, bar);
-    bulk_row(d + IN_V * 512u, a.EV + o1, cs, nlon, bar);
-    if (need_gh) bulk_row(d + IN_HS * 512u, a.ghs + o1, cs, nlon, bar);
-    if (LAZY) {
-      if (LAZY == 1) bulk_row(d + IN_TG * 512u, a.Lgd + o2, cs, nlon, bar);
-      bulk_row(d + IN_TU * 512u, a.LU + o1, cs, nlon, bar);
-      bulk_row(d + IN_TV * 512u, a.LV + o1, cs, nlon, bar);
+    n1 = min(64, nlon - cs);
+  }
+  auto issue_packet = [&](const int r, const int nrec) {   // nrec: records of rows r+2-nrec .. r+1
+    const int it = r - rja0;
+    const int st = it % PC_IN_DEPTH;
+    const unsigned bar = in_bar + 8u * (unsigned)st;
+    const unsigned d = in_sa + (unsigned)(st * PC_IN_NF) * 512u;
+    const ptrdiff_t o1 = (ptrdiff_t)(r + 1 - r0) * nl + cs, o2 = o1 + nl;
+    const unsigned b1 = (unsigned)n1 * 8u;
+    if (lane == 0) {
+      mbar_expect_tx(bar, pk_nf * 512u + (unsigned)nrec * (unsigned)(RC_N * 8));
+      bulk_g2s(d + IN_GD * 512u, a.Egd + o2, b1, bar);
+      bulk_g2s(d + IN_U * 512u, a.EU + o1, b1, bar);
+      bulk_g2s(d + IN_V * 512u, a.EV + o1, b1, bar);
+      if (need_gh) bulk_g2s(d + IN_HS * 512u, a.ghs + o1, b1, bar);
+      if (LAZY) {
+        if (LAZY == 1) bulk_g2s(d + IN_TG * 512u, a.Lgd + o2, b1, bar);
+        bulk_g2s(d + IN_TU * 512u, a.LU + o1, b1, bar);
+        bulk_g2s(d + IN_TV * 512u, a.LV + o1, b1, bar);
+      }
+      if (n1 < 64) {   // the strip crosses the seam (several times on a grid narrower than a strip)
+        const ptrdiff_t w1 = o1 - cs, w2 = o2 - cs;   // column 0 of the same rows
+        unsigned done = b1;
+        int rem = 64 - n1;
+        while (rem > 0) {
+          const int n = min(rem, nlon);
+          const unsigned bn = (unsigned)n * 8u;
+          bulk_g2s(d + IN_GD * 512u + done, a.Egd + w2, bn, bar);
+          bulk_g2s(d + IN_U * 512u + done, a.EU + w1, bn, bar);
+          bulk_g2s(d + IN_V * 512u + done, a.EV + w1, bn, bar);
+          if (need_gh) bulk_g2s(d + IN_HS * 512u + done, a.ghs + w1, bn, bar);
+          if (LAZY) {
+            if (LAZY == 1) bulk_g2s(d + IN_TG * 512u + done, a.Lgd + w2, bn, bar);
+            bulk_g2s(d + IN_TU * 512u + done, a.LU + w1, bn, bar);
+            bulk_g2s(d + IN_TV * 512u + done, a.LV + w1, bn, bar);
+          }
+          done += bn;
+          rem -= n;
+        }
+      }
+      for (int q = r + 2 - nrec; q <= r + 1; q++)
+        bulk_g2s(rec_sa + ((unsigned)(q - (ja - 3)) % (unsigned)PC_REC_DEPTH) * (unsigned)(RC_N * 8), a.t.rowrec + (ptrdiff_t)q * RC_N,
+                 (unsigned)(RC_N * 8), bar);
     }
   };
+  // (the barriers are initialised by k_pc before the warps part ways)  S1 sends for its first packets itself -- the first
+  // brings the records of rows rja0-1 .. rja0+1 --, from then on S2's warp, the one with the fewest instructions per
+  // row, issues the packet S1 consumes PC_IN_DEPTH - 1 ticks later: in tick t the slot S1 read in tick t-1 is free
   if (ROLE == 0) {
-    if (lane == 0) {
-      for (int q = 0; q < PC_IN_DEPTH; q++) mbar_init(in_bar + 8u * (unsigned)q, 1u);
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      for (int q = 0; q < PC_IN_DEPTH - 1; q++)
-        if (rja + q < rjb) issue_packet(rja + q);
-    }
-    __syncwarp();
+    for (int q = 0; q < PC_IN_DEPTH - 1; q++)
+      if (rja0 + q < rjb0) issue_packet(rja0 + q, q == 0 ? 3 : 1);
+  }
+  for (int t = 0; t < T0; t++) {
+    if (ROLE == 1 && rja0 + t + (PC_IN_DEPTH - 1) < rjb0) issue_packet(rja0 + t + (PC_IN_DEPTH - 1), 1);
+    pc_bar();
   }
   // ---- prologue: rows rja-1, rja, rja+1 of sqrt(gd); rows rja-1, rja of U, V; gd + ghs of row rja -----------------
   D2 sm_, s0, sp, sq, u0, up, vm, v0, vp, Um, U0, Up, Vm, V0, Vp;
@@ -282,9 +310,6 @@ __device__ __forceinline__ void pc_role(const StageArgs &a, const int strip, con
     if (ROLE == 0) {
       const int it = j - rja;
       const int st = it % PC_IN_DEPTH;
-      // the slot read one iteration ago is free once every lane has passed this point: refill it PC_IN_DEPTH - 1 rows ahead
-      __syncwarp();
-      if (lane == 0 && j + (PC_IN_DEPTH - 1) < rjb) issue_packet(j + (PC_IN_DEPTH - 1));
       mbar_wait(in_bar + 8u * (unsigned)st, (unsigned)(it / PC_IN_DEPTH) & 1u);
       const D2 *const pk = in_ring + st * (PC_IN_NF * 32);
       c_gd2 = ldl(pk + IN_GD * 32);
@@ -306,6 +331,10 @@ __device__ __forceinline__ void pc_role(const StageArgs &a, const int strip, con
         }
       }
     } else {
+      if (ROLE == 1) {   // tick t = j - rja + PC_D1: the packet of S1's iteration t + PC_IN_DEPTH - 1
+        const int r = rja0 + (j - rja) + PC_D1 + (PC_IN_DEPTH - 1);
+        if (r < rjb0) issue_packet(r, 1);
+      }
       c_gd2 = rld(RIN, j + 2, 2);
       c_U = rld(RIN, j + 1, 0);
       c_V = rld(RIN, j + 1, 1);
@@ -323,7 +352,9 @@ __device__ __forceinline__ void pc_role(const StageArgs &a, const int strip, con
       qV = rld(RG_P, j, 1);
       qG = rld(RG_P, j, 2);
     }
-    const double *__restrict__ rc = a.t.rowrec + (ptrdiff_t)j * RC_N;
+    const double *__restrict__ rc = recp(j);
+    const double *__restrict__ rcm = recp(j - 1);
+    const double *__restrict__ rcn = recp(j + 1);
     const bool rowU = (j >= 1 && j <= nlat - 2);
     const bool rowV = (j <= nlat - 2);
     const bool rowG = rowU && (PASS != PASS_SLOW);
@@ -361,14 +392,14 @@ __device__ __forceinline__ void pc_role(const StageArgs &a, const int strip, con
       ghdy_a = gp.x - g0.x;
       ghdy_b = gp.y - g0.y;
     }
-    const double hc0 = __ldg(rc + RC_COSH - RC_N), hc1 = __ldg(rc + RC_COSH), hc2 = __ldg(rc + RC_COSH + RC_N);
+    const double hc0 = rcm[RC_COSH], hc1 = rc[RC_COSH], hc2 = rcn[RC_COSH];
     double dUa, dVa, dGa, dUb, dVb, dGb;
-    tend_col<PASS, ADV>(rc, rowU, rowV, rowG, a.beta_lon, a.beta_lat, hc0, hc1, hc2,
+    tend_col<PASS, ADV>(rc, rcn, rowU, rowV, rowG, a.beta_lon, a.beta_lat, hc0, hc1, hc2,
                         uw_a, u0.x, u0.y, Uw_a, U0.x, U0.y, Vw_a, V0.x, V0.y, sw_a, s0.x, s0.y, v0.x, v0.y,
                         Um.x, Vm.x, Vm.y, vm.x, vm.y, sm_.x,
                         Up.x, Unw_a, up.x, unw_a, Vp.x, vp.x, sp.x,
                         ghdx_a, ghdy_a, 0.0, 0.0, 0.0, 0.0, dUa, dVa, dGa);
-    tend_col<PASS, ADV>(rc, rowU, rowV, rowG, a.beta_lon, a.beta_lat, hc0, hc1, hc2,
+    tend_col<PASS, ADV>(rc, rcn, rowU, rowV, rowG, a.beta_lon, a.beta_lat, hc0, hc1, hc2,
                         u0.x, u0.y, ue_b, U0.x, U0.y, Ue_b, V0.x, V0.y, Ve_b, s0.x, s0.y, se_b, v0.y, ve_b,
                         Um.y, Vm.y, Vse_b, vm.y, vse_b, sm_.y,
                         Up.y, Up.x, up.y, up.x, Vp.y, vp.y, sp.y,
@@ -403,7 +434,7 @@ __device__ __forceinline__ void pc_role(const StageArgs &a, const int strip, con
       rst(RG_P, j, 2, t);
     } else {
       if (out) {
-        const double cfj = __ldg(rc + RC_COSF);
+        const double cfj = rc[RC_COSF];
         if (rowU) {
           st2(AT(a.TU, j), dUa, dUb);
           ip1 = ip1 + dUa * qU.x * cfj;
@@ -475,6 +506,14 @@ __global__ void __launch_bounds__(PC_BX, GMD_PC_MINB) k_pc(const StageArgs a) {
   const size_t pslot = (size_t)a.pofs[0] + (size_t)blockIdx.y * gridDim.x + blockIdx.x;
   if (ja < jb) {   // (CTA-uniform)
     D2 *const ring = reinterpret_cast<D2 *>(pc_smem) + lane;
+    if (threadIdx.x == 0) {
+      const unsigned bar0 = (unsigned)__cvta_generic_to_shared(pc_smem) + (unsigned)(PC_RING_LINES + PC_IN_DEPTH * PC_IN_NF) * 512u +
+                            (unsigned)(PC_REC_DEPTH * RC_N) * 8u;
+      for (int q = 0; q < PC_IN_DEPTH; q++) mbar_init(bar0 + 8u * (unsigned)q, 1u);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
     const bool edgeS = (ja == a.rb[0]) && (a.medge[0] & 1), edgeN = (jb == a.re[0]) && (a.medge[0] & 2);
     double ip1 = 0.0, ip2 = 0.0;
     if (warp == 0) pc_role<PASS, ADV, 0, LAZY, PUSH>(a, blockIdx.x, ja, jb, edgeS, edgeN, ring, ip1, ip2);
