@@ -312,26 +312,60 @@ def main():
                    "frac": vbytes / (vms * 1e-3) / 1e9 / peak}
         fam_ms += vms
         fam_bytes += vbytes
-    kms, kbytes = fam["S2"]["ms_per_launch"], fam["S2"]["algorithmic_bytes_per_launch"]
-    achieved = kbytes / (kms * 1e-3) / 1e9
-    traffic = None
-    if world == 1:   # the ncu capture was made on one GPU at this grid; a band of an N-GPU run moves less
-        try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "stage_kernel_traffic.json"))).get(args.workload)
-        except Exception:
-            pass
+    traffic_tab = {}
+    try:
+        traffic_tab = json.load(open(os.path.join(ROOT, "profiles", "stage_kernel_traffic.json")))
+    except Exception:
+        pass
     step_gbps = d.algorithmic_bytes_per_column_step() * value / 1e9 / max(world, 1)
-    roofline = {"bound": "hbm", "kernel": f"k_stage<{pass_name}, S2>", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic,
-                "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch "
-                                  "(profiles/stage_kernel_traffic.json)" if traffic else None,
-                "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
-                "ms_per_launch": kms, "algorithmic_bytes_per_launch": kbytes,
-                "family": {"what": "the three stage-kernel variants of one fast predict_correct, time-weighted: "
-                                   "sum of algorithmic bytes / sum of launch times",
-                           "achieved": fam_bytes / (fam_ms * 1e-3) / 1e9, "frac": fam_bytes / (fam_ms * 1e-3) / 1e9 / peak,
-                           "variants": fam},
-                "step_algorithmic_GBps": step_gbps, "step_frac_per_gpu": step_gbps / peak}
+    family = {"what": "the three stage-kernel variants of one fast predict_correct (the path of the rows next to the poles, "
+                      "of polar bands and of the strict build), each timed alone over the whole band, time-weighted: sum "
+                      "of algorithmic bytes / sum of launch times",
+              "achieved": fam_bytes / (fam_ms * 1e-3) / 1e9, "frac": fam_bytes / (fam_ms * 1e-3) / 1e9 / peak, "variants": fam}
+    fused = None
+    try:
+        d.time_stage_variant(pass_name, 5, 3)
+        fused = d.time_stage_variant(pass_name, 5, 20)
+    except gmd.GmdError:
+        pass
+    if fused is not None:
+        # The dominant kernel of the step is k_pc: one launch = one predict_correct (S1 + S2 + S3a as one wavefront kernel,
+        # the previous predict_correct's update folded in).  `achieved` follows the contract: SURVEY 8d's per-unit figure
+        # (312 B per column and fast predict_correct, 216 B slow) x the columns the launch covers / its duration.  The
+        # kernel itself only has to move 13 of those 39 words (`moved`): the stage states travel through shared memory,
+        # so `frac` can exceed 1 and the kernel is bound by fp64 issue, not by HBM (profiles/r2_n_ncu_k_pc_summary.txt).
+        kms, kbytes = fused
+        per_col = 312.0 if pass_name != "slow" else 216.0
+        model_bytes = kbytes / (13 * 8.0) * per_col
+        achieved = model_bytes / (kms * 1e-3) / 1e9
+        traffic = traffic_tab.get(args.workload + ":k_pc") if world == 1 else None
+        roofline = {"bound": "hbm", "kernel": f"k_pc<{pass_name}, deferred update>", "achieved": achieved, "peak": peak,
+                    "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                    "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch "
+                                      "(profiles/stage_kernel_traffic.json)" if traffic else None,
+                    "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
+                    "ms_per_launch": kms, "algorithmic_bytes_per_launch": model_bytes,
+                    "algorithmic_bytes_what": f"SURVEY 8d: {per_col:.0f} B per column per predict_correct x the columns of the fused rows "
+                                              "(one launch = one predict_correct)",
+                    "moved": {"what": "what the fused kernel has to move: old state 3 + ghs 1 + deferred tendency 3 words in, "
+                                      "materialised state 3 + new tendency 3 out = 13 words per column",
+                              "bytes_per_launch": kbytes, "GBps": kbytes / (kms * 1e-3) / 1e9,
+                              "frac_of_peak": kbytes / (kms * 1e-3) / 1e9 / peak},
+                    "rows_covered": list(d.fused_rows()),
+                    "limiter": "fp64 issue / dependent latency (ncu: issue active 57 %, fp64 pipe 38 %, DRAM 30 % of peak)",
+                    "three_sweep_family": family,
+                    "step_algorithmic_GBps": step_gbps, "step_frac_per_gpu": step_gbps / peak}
+    else:
+        kms, kbytes = fam["S2"]["ms_per_launch"], fam["S2"]["algorithmic_bytes_per_launch"]
+        achieved = kbytes / (kms * 1e-3) / 1e9
+        traffic = traffic_tab.get(args.workload) if world == 1 else None
+        roofline = {"bound": "hbm", "kernel": f"k_stage<{pass_name}, S2>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": traffic,
+                    "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch "
+                                      "(profiles/stage_kernel_traffic.json)" if traffic else None,
+                    "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
+                    "ms_per_launch": kms, "algorithmic_bytes_per_launch": kbytes, "family": family,
+                    "step_algorithmic_GBps": step_gbps, "step_frac_per_gpu": step_gbps / peak}
 
     # ---- end to end through the C ABI with host buffers ----------------------------------------------------
     barrier()

@@ -144,6 +144,12 @@ module gmd_c
       integer(c_int), intent(out) :: row_begin, row_end
     end function
 
+    integer(c_int) function gmd_get_fused_rows(model, row_begin, row_end) bind(c, name='gmd_get_fused_rows')
+      import c_ptr, c_int
+      type(c_ptr), value :: model
+      integer(c_int), intent(out) :: row_begin, row_end
+    end function
+
   end interface
 
 contains

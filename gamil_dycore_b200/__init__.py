@@ -139,6 +139,7 @@ def load(kind: str = "fast") -> C.CDLL:
     lib.gmd_peer_connect.argtypes = [P, C.c_void_p, C.c_int]
     lib.gmd_peer_disconnect.argtypes = [P]
     lib.gmd_get_band.argtypes = [P, I, I]
+    lib.gmd_get_fused_rows.argtypes = [P, I, I]
     lib.gmd_set_state.argtypes = [P, D, D, D, D, C.c_int]
     lib.gmd_run_init.argtypes = [P]
     lib.gmd_step.argtypes = [P, C.c_int]
@@ -276,6 +277,12 @@ class Dycore:
     def band(self):
         a, b = C.c_int(), C.c_int()
         self._chk(self.lib.gmd_get_band(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def fused_rows(self):
+        """rows [a, b) whose predict_correct runs as the fused kernel k_pc; (0, 0) when it is not in use"""
+        a, b = C.c_int(), C.c_int()
+        self._chk(self.lib.gmd_get_fused_rows(self.h, C.byref(a), C.byref(b)))
         return a.value, b.value
 
     def set_state(self, u, v, gd, ghs=None, layout=LAYOUT_COMPACT):

@@ -2325,6 +2325,13 @@ int gmd_get_band(const gmd_model *m, int *b, int *e) {
   return 0;
 }
 
+int gmd_get_fused_rows(const gmd_model *m, int *b, int *e) {
+  if (!m) return fail(GMD_ERR_ARG, "null model");
+  if (b) *b = m->fused ? m->fz_I0 : 0;
+  if (e) *e = m->fused ? m->fz_I1 : 0;
+  return 0;
+}
+
 int gmd_set_stream(gmd_model *m, void *s) {
   if (!m) return fail(GMD_ERR_ARG, "null model");
   int r = set_dev(m);
@@ -2874,7 +2881,7 @@ static int time_stage(gmd_model *m, int pass, int mode, int reps, float *ms_per_
   a.rb[0] = m->geo.r0; a.re[0] = m->geo.r1; a.pofs[0] = 0;
   if ((r = join(m))) return r;
   dim3 grid((unsigned)m->nbx, (unsigned)((m->nr + rpc - 1) / rpc), 1);
-  stage_fn fn = pick_stage(pass, m->cfg.uv_adv_scheme, mode);
+  stage_fn fn = pick_stage(pass, m->cfg.uv_adv_scheme, mode == 5 ? MODE_S1 : mode);
   if (mode == 4) {  // MODE_S1 with the deferred update folded in: E = cur + beta dt tendNew -> A (= M), N = B
     a.LU = m->tendNew.U; a.LV = m->tendNew.V; a.Lgd = m->tendNew.gd;
     a.MU = A.U; a.MV = A.V; a.Mgd = A.gd;
@@ -2882,13 +2889,30 @@ static int time_stage(gmd_model *m, int pass, int mode, int reps, float *ms_per_
     a.lip = m->d_ip; a.ldt = dt; a.lqcon = m->cfg.qcon_modified;
     fn = pick_stage_lazy(pass, m->cfg.uv_adv_scheme == ADV_WENO ? ADV_CENTER : m->cfg.uv_adv_scheme, slow ? 2 : 1);
   }
+  unsigned threads = BX;
+  size_t smem = stage_smem_bytes(rpc);
+  if (mode == 5) {  // the fused predict_correct kernel with the deferred update, over the rows it covers in a step
+    if (!m->fused) return fail(GMD_ERR_STATE, "the fused predict_correct kernel is not in use in this configuration");
+    a.LU = m->tendNew.U; a.LV = m->tendNew.V; a.Lgd = m->tendNew.gd;
+    a.MU = A.U; a.MV = A.V; a.Mgd = A.gd;
+    a.EU = m->cur.U; a.EV = m->cur.V; a.Egd = m->cur.gd;
+    a.TU = m->tendNew2.U; a.TV = m->tendNew2.V; a.Tgd = m->tendNew2.gd;
+    a.lip = m->d_ip; a.ldt = dt; a.lqcon = m->cfg.qcon_modified;
+    a.rows_per_cta = m->fz_rpc;
+    a.rb[0] = m->fz_I0; a.re[0] = m->fz_I1;
+    fn = pick_pc(pass, m->cfg.uv_adv_scheme, 1, false);
+    if (!fn) return fail(GMD_ERR_STATE, "no fused kernel for this configuration");
+    grid = dim3((unsigned)m->fz_nstrips, (unsigned)m->fz_nchunks, 1);
+    threads = PC_BX;
+    smem = PC_SMEM_BYTES;
+  }
   if ((r = allow_smem((const void *)fn))) return r;
   cudaEvent_t e0, e1;
   CK(cudaEventCreate(&e0));
   CK(cudaEventCreate(&e1));
   CK(cudaEventRecord(e0, m->stream));
   for (int k = 0; k < reps; k++) {
-    fn<<<grid, BX, stage_smem_bytes(rpc), m->stream>>>(a);
+    fn<<<grid, threads, smem, m->stream>>>(a);
     m->launches++;
   }
   CK(cudaEventRecord(e1, m->stream));
@@ -2924,13 +2948,16 @@ int gmd_time_stage_kernel(gmd_model *m, int reps, float *ms_per_launch, double *
 int gmd_time_stage_variant(gmd_model *m, int pass, int mode, int reps, float *ms_per_launch, double *alg_bytes) {
   if (!m || !ms_per_launch) return fail(GMD_ERR_ARG, "null argument");
   if (!m->run_inited) return fail(GMD_ERR_STATE, "gmd_run_init has not been called");
-  if (reps < 1 || pass < 0 || pass > 2 || mode < 0 || mode > 4) return fail(GMD_ERR_ARG, "bad argument");
+  if (reps < 1 || pass < 0 || pass > 2 || mode < 0 || mode > 5) return fail(GMD_ERR_ARG, "bad argument");
   int r = set_dev(m);
   if (r) return r;
   if ((r = time_stage(m, pass, mode, reps, ms_per_launch))) return r;
-  // words per column: fast/all S1 7, S2 13, S3a 10; slow S1 5, S2 9, S3a 7; EVAL = reads + 3 (2) writes
-  static const double words[2][5] = {{7, 13, 10, 7, 13}, {5, 9, 7, 5, 9}};
-  if (alg_bytes) *alg_bytes = words[pass == PASS_SLOW ? 1 : 0][mode] * 8.0 * (double)m->nr * (double)m->geo.nlon;
+  // words per column: fast/all S1 7, S2 13, S3a 10; slow S1 5, S2 9, S3a 7; EVAL = reads + 3 (2) writes;
+  // mode 5, the fused kernel: what it actually has to move -- old state 3 + ghs 1 + deferred tendency 3 in, materialised
+  // state 3 + new tendency 3 out (slow pass: no ghs, gd carries no new tendency) -- over the rows it covers
+  static const double words[2][6] = {{7, 13, 10, 7, 13, 13}, {5, 9, 7, 5, 9, 11}};
+  const double rows = (mode == 5) ? (double)(m->fz_I1 - m->fz_I0) : (double)m->nr;
+  if (alg_bytes) *alg_bytes = words[pass == PASS_SLOW ? 1 : 0][mode] * 8.0 * rows * (double)m->geo.nlon;
   return 0;
 }
 

@@ -33,6 +33,9 @@ constexpr int WOUT3 = 54;      // output columns per strip (64 held)
 constexpr int PC_BX = 96;      // three warps: S1, S2, S3a
 constexpr int PC_D1 = 4;       // S2 starts 4 ticks after S1
 constexpr int PC_D2 = 8;       // S3a starts 8 ticks after S1
+#ifndef GMD_PC_UNROLL
+#define GMD_PC_UNROLL 1
+#endif
 #ifndef GMD_PC_MINB
 #define GMD_PC_MINB 5          // resident CTAs per SM the register allocation is capped for (15 warps)
 #endif
@@ -41,6 +44,7 @@ constexpr int PC_D2 = 8;       // S3a starts 8 ticks after S1
 //   4 rows deep (depths checked against the tick table below by tests/test_host.py::test_pc_ring_schedule)
 enum { RG_A = 0, RG_O = 1, RG_B = 2, RG_P = 3 };
 constexpr int PC_DEPTH_AB = 5, PC_DEPTH_OP = 4;
+static_assert((PC_DEPTH_OP & (PC_DEPTH_OP - 1)) == 0, "PC_DEPTH_OP must be a power of two");
 constexpr int PC_RING_LINES = 3 * (2 * PC_DEPTH_AB + 2 * PC_DEPTH_OP);   // 54 lines = 27648 bytes
 __host__ __device__ constexpr int pc_ring_line0(int kind) {
   return kind == RG_A ? 0 : kind == RG_B ? 3 * PC_DEPTH_AB : kind == RG_O ? 6 * PC_DEPTH_AB : 6 * PC_DEPTH_AB + 3 * PC_DEPTH_OP;
@@ -65,7 +69,20 @@ constexpr size_t PC_SMEM = (size_t)(PC_RING_LINES + PC_IN_DEPTH * PC_IN_NF) * 51
 //   S3a evaluates row x in tick x + PC_D2        reading gd_B(x+2) [tick x+7], U,V_B(x+1) [x+6], tend2(x) [x+5];
 //       its prologue (tick PC_D2) reads B rows -1..1 [ticks 4..6]
 // A row is overwritten `depth` ticks after it was written; the longest-lived rows are the prologue rows (4 ticks).
-__device__ __forceinline__ void pc_bar() { asm volatile("bar.sync 1, 96;" ::: "memory"); }
+// The three warps reach the barrier from three different loops, each warp converged.  That is what bar.sync (=
+// barrier.sync.aligned) asks for; compute-sanitizer --tool synccheck nevertheless wants a whole-CTA aligned barrier at
+// ONE instruction, so tools/sanitize_fused.sh checks a build with the unaligned form (-DGMD_PC_UNALIGNED_BAR=1: same
+// results, 6 % slower on B200)
+#ifndef GMD_PC_UNALIGNED_BAR
+#define GMD_PC_UNALIGNED_BAR 0
+#endif
+__device__ __forceinline__ void pc_bar() {
+#if GMD_PC_UNALIGNED_BAR
+  asm volatile("barrier.sync 1, 96;" ::: "memory");
+#else
+  asm volatile("bar.sync 1, 96;" ::: "memory");
+#endif
+}
 
 // ---- mbarrier + bulk copy (sm_90+ PTX) ------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
@@ -108,21 +125,22 @@ __device__ __forceinline__ void pc_role(const StageArgs &a, const int strip, con
   const ptrdiff_t nl = nlon;
   // ring slot of row x (x >= ja - 2)
   const int rbase = ja - 2;
-  auto line = [&](int kind, int x, int f) -> int {
-    const unsigned d = (kind == RG_A || kind == RG_B) ? (unsigned)PC_DEPTH_AB : (unsigned)PC_DEPTH_OP;
-    return pc_ring_line0(kind) + (int)((unsigned)(x - rbase) % d) * 3 + f;
-  };
-  // 16-byte shared-memory accesses, one 512-byte line per (ring, row, field): conflict-free LDS.128 / STS.128
-  auto rld = [&](int kind, int x, int f) -> D2 {
-    const double2 v = *reinterpret_cast<const double2 *>(ring + line(kind, x, f) * 32);
+  // 16-byte shared-memory accesses, one 512-byte line per (ring, row, field): conflict-free LDS.128 / STS.128.  The
+  // ring slot of a row is (row - rbase) mod depth; the row loop carries the slots of rows j, j+1, j+2 along instead of
+  // dividing (slot5 / slot4 below)
+  auto rld = [&](int kind, int sl, int f) -> D2 {
+    const double2 v = *reinterpret_cast<const double2 *>(ring + (pc_ring_line0(kind) + sl * 3 + f) * 32);
     D2 r;
     r.x = v.x;
     r.y = v.y;
     return r;
   };
-  auto rst = [&](int kind, int x, int f, const D2 &v) {
-    *reinterpret_cast<double2 *>(ring + line(kind, x, f) * 32) = make_double2(v.x, v.y);
+  auto rst = [&](int kind, int sl, int f, const D2 &v) {
+    *reinterpret_cast<double2 *>(ring + (pc_ring_line0(kind) + sl * 3 + f) * 32) = make_double2(v.x, v.y);
   };
+  auto slot5 = [&](int x) -> int { return (int)((unsigned)(x - rbase) % (unsigned)PC_DEPTH_AB); };
+  auto slot4 = [&](int x) -> int { return (int)((unsigned)(x - rbase) % (unsigned)PC_DEPTH_OP); };
+  auto next5 = [](int sl) -> int { return sl == PC_DEPTH_AB - 1 ? 0 : sl + 1; };
 
   ptrdiff_t off = (ptrdiff_t)(rja - r0) * nl + (ptrdiff_t)c0;   // element offset of (row j, column c0)
 #define ATK(p, k) ((p) + (off + (ptrdiff_t)(k) * nl))
@@ -268,13 +286,14 @@ __device__ __forceinline__ void pc_role(const StageArgs &a, const int strip, con
         }
       }
     } else {
-      a0 = rld(RIN, j - 1, 2);
-      a1 = rld(RIN, j, 2);
-      a2 = rld(RIN, j + 1, 2);
-      Um = rld(RIN, j - 1, 0);
-      U0 = rld(RIN, j, 0);
-      Vm = rld(RIN, j - 1, 1);
-      V0 = rld(RIN, j, 1);
+      const int sm1 = slot5(j - 1), s00 = next5(sm1), sp1 = next5(s00);
+      a0 = rld(RIN, sm1, 2);
+      a1 = rld(RIN, s00, 2);
+      a2 = rld(RIN, sp1, 2);
+      Um = rld(RIN, sm1, 0);
+      U0 = rld(RIN, s00, 0);
+      Vm = rld(RIN, sm1, 1);
+      V0 = rld(RIN, s00, 1);
     }
     gr0 = a1;
     gr1 = a2;
@@ -305,7 +324,10 @@ __device__ __forceinline__ void pc_role(const StageArgs &a, const int strip, con
   D2 n_hs = zero2;
   if (ROLE != 0 && need_gh) n_hs = ld2(ATK(a.ghs, 1));
 
+  int sj5 = slot5(rja), sj4 = slot4(rja);   // ring slots of row j
+  GMD_UNROLL_PRAGMA(GMD_PC_UNROLL)
   for (int j = rja; j < rjb; j++) {
+    const int sj5n = next5(sj5), sj5nn = next5(sj5n);   // ... of rows j+1, j+2
     D2 c_gd2, c_U, c_V, c_hs = zero2;
     if (ROLE == 0) {
       const int it = j - rja;
@@ -335,22 +357,22 @@ __device__ __forceinline__ void pc_role(const StageArgs &a, const int strip, con
         const int r = rja0 + (j - rja) + PC_D1 + (PC_IN_DEPTH - 1);
         if (r < rjb0) issue_packet(r, 1);
       }
-      c_gd2 = rld(RIN, j + 2, 2);
-      c_U = rld(RIN, j + 1, 0);
-      c_V = rld(RIN, j + 1, 1);
+      c_gd2 = rld(RIN, sj5nn, 2);
+      c_U = rld(RIN, sj5n, 0);
+      c_V = rld(RIN, sj5n, 1);
       c_hs = n_hs;
       if (need_gh && j + 1 < rjb) n_hs = ld2(AT(a.ghs, j + 2));
     }
     // what this row's result is combined with: the old state (ROLE 1), the previous tendency (ROLE 2)
     D2 qU = zero2, qV = zero2, qG = zero2;
     if (ROLE == 1) {
-      qU = rld(RG_O, j, 0);
-      qV = rld(RG_O, j, 1);
-      qG = rld(RG_O, j, 2);
+      qU = rld(RG_O, sj4, 0);
+      qV = rld(RG_O, sj4, 1);
+      qG = rld(RG_O, sj4, 2);
     } else if (ROLE == 2) {
-      qU = rld(RG_P, j, 0);
-      qV = rld(RG_P, j, 1);
-      qG = rld(RG_P, j, 2);
+      qU = rld(RG_P, sj4, 0);
+      qV = rld(RG_P, sj4, 1);
+      qG = rld(RG_P, sj4, 2);
     }
     const double *__restrict__ rc = recp(j);
     const double *__restrict__ rcm = recp(j - 1);
@@ -410,28 +432,28 @@ __device__ __forceinline__ void pc_role(const StageArgs &a, const int strip, con
       if (rowU) { nU.x = U0.x + a.dt * dUa; nU.y = U0.y + a.dt * dUb; }
       if (rowV) { nV.x = V0.x + a.dt * dVa; nV.y = V0.y + a.dt * dVb; }
       if (rowG) { nG.x = gr0.x + a.dt * dGa; nG.y = gr0.y + a.dt * dGb; }
-      rst(RG_A, j, 0, nU);
-      rst(RG_A, j, 1, nV);
-      rst(RG_A, j, 2, nG);
-      rst(RG_O, j, 0, U0);
-      rst(RG_O, j, 1, V0);
-      rst(RG_O, j, 2, gr0);
+      rst(RG_A, sj5, 0, nU);
+      rst(RG_A, sj5, 1, nV);
+      rst(RG_A, sj5, 2, nG);
+      rst(RG_O, sj4, 0, U0);
+      rst(RG_O, sj4, 1, V0);
+      rst(RG_O, sj4, 2, gr0);
     } else if (ROLE == 1) {
       // B(j) = old(j) + dt tend2(j); tend2(j) goes on to S3a
       D2 nU = qU, nV = qV, nG = qG;
       if (rowU) { nU.x = qU.x + a.dt * dUa; nU.y = qU.y + a.dt * dUb; }
       if (rowV) { nV.x = qV.x + a.dt * dVa; nV.y = qV.y + a.dt * dVb; }
       if (rowG) { nG.x = qG.x + a.dt * dGa; nG.y = qG.y + a.dt * dGb; }
-      rst(RG_B, j, 0, nU);
-      rst(RG_B, j, 1, nV);
-      rst(RG_B, j, 2, nG);
+      rst(RG_B, sj5, 0, nU);
+      rst(RG_B, sj5, 1, nV);
+      rst(RG_B, sj5, 2, nG);
       D2 t;
       t.x = dUa; t.y = dUb;
-      rst(RG_P, j, 0, t);
+      rst(RG_P, sj4, 0, t);
       t.x = dVa; t.y = dVb;
-      rst(RG_P, j, 1, t);
+      rst(RG_P, sj4, 1, t);
       t.x = dGa; t.y = dGb;
-      rst(RG_P, j, 2, t);
+      rst(RG_P, sj4, 2, t);
     } else {
       if (out) {
         const double cfj = rc[RC_COSF];
@@ -486,6 +508,8 @@ __device__ __forceinline__ void pc_role(const StageArgs &a, const int strip, con
     vse_b = ve_b;
     se_b = spe_b;
     off += nl;
+    sj5 = sj5n;
+    sj4 = (sj4 + 1) & (PC_DEPTH_OP - 1);
     pc_bar();
   }
 #undef AT

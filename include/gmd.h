@@ -123,6 +123,11 @@ int gmd_peer_connect(gmd_model *m, const void *blobs, int nblobs);
 int gmd_peer_disconnect(gmd_model *m);
 /* full-latitude rows [row_begin, row_end) (0-based) owned by this rank */
 int gmd_get_band(const gmd_model *m, int *row_begin, int *row_end);
+/* rows [row_begin, row_end) of this rank whose predict_correct runs as the fused wavefront kernel k_pc (the rest --
+   filter / reduced / pole rows and the plain rows next to them -- runs the three-sweep k_stage + k_polar chain);
+   row_begin == row_end == 0 when the configuration does not use it (WENO, runge_kutta, the strict build, polar bands of
+   a multi-band run, GMD_FUSED=0).  Informational: results do not depend on it beyond rounding of the inner products. */
+int gmd_get_fused_rows(const gmd_model *m, int *row_begin, int *row_end);
 
 /* The IC plugins / restart_read write state(old)%{u,v,gd} and static%ghs (e.g.
    rossby_haurwitz_wave_test_mod.F90:45-83); this uploads them.  ghs may be NULL (= 0).
@@ -185,7 +190,10 @@ double gmd_algorithmic_bytes_per_column_step(const gmd_model *m);
    launch and the algorithmic bytes one launch moves on this rank */
 int gmd_time_stage_kernel(gmd_model *m, int reps, float *ms_per_launch, double *alg_bytes_per_launch);
 /* the same for any (pass, mode) instantiation: mode 0 = S1 (predict), 1 = S2 (predict + store tendency),
-   2 = S3a (tendency + inner products), 3 = evaluation only */
+   2 = S3a (tendency + inner products), 3 = evaluation only, 4 = S1 with the deferred update folded in,
+   5 = the fused predict_correct kernel k_pc (S1 + S2 + S3a as one wavefront, deferred update folded in) over the rows
+   it covers in a step; GMD_ERR_STATE when the configuration does not use it.  alg_bytes of mode 5: the 13 (slow pass:
+   11) words per column the kernel has to move, not the 36 of the three sweeps it replaces */
 int gmd_time_stage_variant(gmd_model *m, int pass, int mode, int reps, float *ms_per_launch,
                            double *alg_bytes_per_launch);
 /* Device timeline of the following model steps (libgmd_trace.so, the -DGMD_TRACE=1 build of the same sources; the

@@ -503,6 +503,57 @@ def test_error_behaviour():
         d.run_init()
 
 
+FUSED_CASES = {
+    # csp2 with the deferred update: slow / fast passes, LAZY 0 / 1 / 2 of k_pc
+    "rh_csp2_360x181": ("rossby_haurwitz_wave", dict(num_lon=360, num_lat=181, time_step_size=240.0, subcycles=6, split_scheme="csp2",
+                                                     zonal_tend_filter_cutoff_wavenumber=[4] * 5), 6),
+    # unsplit pass (advection + fast terms in one sweep), upwind, a mountain (ghs != 0), a grid narrower than two strips
+    "mz_upwind_unsplit_100x51": ("mountain_zonal_flow", dict(num_lon=100, num_lat=51, time_step_size=300.0, split_scheme="none",
+                                                             uv_adv_scheme="upwind", uv_adv_upwind_lat_beta=0.1,
+                                                             zonal_tend_filter_cutoff_wavenumber=[4, 4, 4]), 8),
+    # several row chunks per strip, a strip that crosses the seam, diffusion between the steps
+    "jz_csp2_diffusion_1440x721": ("jet_zonal_flow", dict(num_lon=1440, num_lat=721, time_step_size=30.0, subcycles=6, split_scheme="csp2",
+                                                          zonal_tend_filter_cutoff_wavenumber=[4] * 20, use_diffusion=True,
+                                                          diffusion_coef=6.0e3), 4),
+    # no filter at all: the fused rows reach to three rows from the poles
+    "sg_csp2_nofilter_72x37": ("steady_geostrophic_flow", dict(num_lon=72, num_lat=37, time_step_size=300.0, subcycles=4, split_scheme="csp2",
+                                                                use_zonal_tend_filter=False), 5),
+}
+
+
+@pytest.mark.parametrize("name", list(FUSED_CASES))
+@pytest.mark.parametrize("graph", [False, True])
+def test_fused_predict_correct_matches_three_sweeps(name, graph, parity_log, monkeypatch):
+    """The fused wavefront kernel k_pc (gamil_dycore_b200/csrc/gmd_pc.cuh) evaluates the same expressions as the three
+    k_stage sweeps it replaces; only the inner products are summed over a different partition of the grid.  Same
+    initial state through both paths (GMD_FUSED=1 / 0): fields within 1e-13 of the field maximum, invariants within
+    1e-14; the run with k_pc must really have used it."""
+    ic, kw, nsteps = FUSED_CASES[name]
+    u, v, gd, ghs = gmd.initial_condition(ic, kw["num_lon"], kw["num_lat"])
+    res = {}
+    for fused in (1, 0):
+        monkeypatch.setenv("GMD_FUSED", str(fused))
+        d = gmd.Dycore(gmd.Config(**kw))
+        a, b = d.fused_rows()
+        assert (b - a > 0) == bool(fused), (a, b)
+        d.set_graph_mode(graph)
+        d.set_state(u, v, gd, ghs)
+        d.run_init()
+        d.step(nsteps)
+        res[fused] = (d.state(), d.diag(), (a, b))
+        d.close()
+    errs = [float(np.abs(p - q).max() / max(np.abs(q).max(), 1e-300)) for p, q in zip(res[1][0], res[0][0])]
+    m1, e1, _ = res[1][1]
+    m0, e0, _ = res[0][1]
+    parity_log.add(f"fused_vs_three_sweeps:{name}:{'graph' if graph else 'direct'}", steps=nsteps, fused_rows=list(res[1][2]),
+                   max_abs_over_field_max_u_v_gd=errs, mass_rel=abs(m1 / m0 - 1), energy_rel=abs(e1 / e0 - 1))
+    # v of the jet and of the steady flow is rounding noise beside the wind: measure it against u
+    uscale = float(np.abs(res[0][0][0]).max())
+    errs[1] = float(np.abs(res[1][0][1] - res[0][0][1]).max() / max(np.abs(res[0][0][1]).max(), uscale))
+    assert max(errs) <= 1e-13, errs
+    assert abs(m1 / m0 - 1) <= 1e-14 and abs(e1 / e0 - 1) <= 1e-14
+
+
 @pytest.mark.parametrize("mode,nranks", [("peer", 2), ("peer", 3), ("nccl", 2)])
 def test_band_decomposition_matches_oracle_and_one_band(mode, nranks, parity_log, tmp_path):
     """N>1 path: latitude bands, halo rows over peer memory (the product path) or NCCL, == oracle (beside the noise

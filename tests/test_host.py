@@ -403,3 +403,75 @@ def test_connect_wiring_and_nccl_fallback_over_gloo_world_size_2(fail_rank):
             assert mode == "peer" and len(calls) == 2
         else:
             assert mode == "nccl" and calls[2] == "disconnect" and calls[3] == ("comm_init", 128) and strict is True
+
+
+def test_pc_ring_schedule():
+    """The fused predict_correct kernel (gamil_dycore_b200/csrc/gmd_pc.cuh) passes rows between its three warps through
+    shared-memory rings, in lockstep ticks.  Replay its schedule with the depths and lags the header defines: every
+    read must see the row written in an EARLIER tick (a barrier in between), and nothing may be overwritten in the tick
+    it is read or before."""
+    import re
+    src = open(os.path.join(ROOT, "gamil_dycore_b200", "csrc", "gmd_pc.cuh")).read()
+
+    def const(name):
+        m = re.search(r"constexpr int [^;]*\b" + name + r" = (\d+)", src)
+        assert m, name
+        return int(m.group(1))
+    D1, D2, DAB, DOP, IND, REC = (const(n) for n in ("PC_D1", "PC_D2", "PC_DEPTH_AB", "PC_DEPTH_OP", "PC_IN_DEPTH", "PC_REC_DEPTH"))
+    depth = {"A": DAB, "B": DAB, "O": DOP, "P": DOP}
+    for n in range(1, 70):                      # rows of a chunk
+        ja, jb = 0, n
+        rja0, rjb0 = ja - 2, jb + 4
+        ring = {k: {} for k in "AOBP"}          # slot -> (row, tick written)
+        inr, rec = {}, {}                       # input ring: slot -> (packet, tick issued); records: slot -> (row, tick)
+        def issue(it, t):
+            if rja0 + it >= rjb0:
+                return
+            inr[it % IND] = (it, t)
+            for y in ([rja0 - 1, rja0, rja0 + 1] if it == 0 else [rja0 + it + 1]):
+                rec[(y - (ja - 3)) % REC] = (y, t)
+        for q in range(IND - 1):
+            issue(q, -1)
+        reads = []
+        def rd(k, x, t):
+            e = ring[k].get((x - (ja - 2)) % depth[k])
+            assert e is not None and e[0] == x and e[1] < t, (n, t, k, x, e)
+            reads.append((t, k, (x - (ja - 2)) % depth[k]))
+        def rdrec(x, t):
+            for y in (x - 1, x, x + 1):
+                e = rec.get((y - (ja - 3)) % REC)
+                assert e is not None and e[0] == y and e[1] < t, (n, t, "rec", y, e)
+        for t in range(n + D2):
+            writes, issues = [], []
+            x = rja0 + t                        # S1
+            if x < rjb0:
+                e = inr.get(t % IND)
+                assert e is not None and e[0] == t and e[1] < t, (n, t, "packet", e)
+                rdrec(x, t)
+                writes += [("A", x), ("O", x)]
+            if t < D1 or ja - 1 + (t - D1) < jb + 2:   # S2's warp is in its idle prefix or its row loop: it issues
+                issues.append(t + IND - 1)
+            if t >= D1:                         # S2
+                x = ja - 1 + (t - D1)
+                if x < jb + 2:
+                    if t == D1:
+                        for y in (x - 1, x, x + 1):
+                            rd("A", y, t)
+                    rd("A", x + 2, t), rd("A", x + 1, t), rd("O", x, t)
+                    rdrec(x, t)
+                    writes += [("B", x), ("P", x)]
+            if t >= D2:                         # S3a
+                x = ja + (t - D2)
+                if x < jb:
+                    if t == D2:
+                        for y in (x - 1, x, x + 1):
+                            rd("B", y, t)
+                    rd("B", x + 2, t), rd("B", x + 1, t), rd("P", x, t)
+                    rdrec(x, t)
+            # a packet issued in tick t lands in the slot S1 read in tick t-1; S1 reads slot t % IND in tick t
+            for it in issues:
+                assert it % IND != t % IND
+                issue(it, t)
+            for k, x in writes:
+                assert (t, k, (x - (ja - 2)) % depth[k]) not in reads, (n, t, k, x)   # no write into a slot read this tick
+                ring[k][(x - (ja - 2)) % depth[k]] = (x, t)
