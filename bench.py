@@ -323,11 +323,15 @@ def main():
                       "of algorithmic bytes / sum of launch times",
               "achieved": fam_bytes / (fam_ms * 1e-3) / 1e9, "frac": fam_bytes / (fam_ms * 1e-3) / 1e9 / peak, "variants": fam}
     fused = None
-    try:
+    fr = d.fused_rows()
+    use_fused = fr[1] > fr[0]
+    if world > 1:   # the timing call is collective (its warm-up runs the inner-product all-reduce): all ranks or none
+        t = torch.tensor([1.0 if use_fused else 0.0], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        use_fused = bool(t.item() > 0.5)
+    if use_fused:
         d.time_stage_variant(pass_name, 5, 3)
         fused = d.time_stage_variant(pass_name, 5, 20)
-    except gmd.GmdError:
-        pass
     if fused is not None:
         # The dominant kernel of the step is k_pc: one launch = one predict_correct (S1 + S2 + S3a as one wavefront kernel,
         # the previous predict_correct's update folded in).  `achieved` follows the contract: SURVEY 8d's per-unit figure

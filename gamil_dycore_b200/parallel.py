@@ -26,16 +26,22 @@ def band(rank: int, nranks: int, num_lat: int, polar_band_rows: int = 0):
 
 
 def polar_band_rows_for(nranks: int, num_lon: int, num_lat: int, filtered: bool = True) -> int:
-    """rows for the two polar bands that balance them against the others: the polar-row kernel (filter rows and pole
-    caps) costs the first and the last rank about 6 us per operator sweep that the other ranks do not pay, a sweep
-    costs about 0.06 us per row of 3600 columns (measured on 4 B200 at 3600x1801: 450/450 rows 1.74 ms per step,
-    400/500 1.57 ms, 350/550 1.69 ms); never less than half an even share.  0 (even bands) below 3 ranks."""
+    """rows for the two polar bands that balance them against the others (0 = even bands, below 3 ranks).
+
+    A polar band runs the chain sweep -> polar rows -> sweep ... on the rows next to its pole (three links per
+    predict_correct, about 51 us + 0.17 us per band row at 3600 columns: the links do not shrink with the band), the other
+    bands run one fused kernel per predict_correct (about 14 us + 0.17 us per row).  Measured on B200 at 3600x1801, ms per
+    model step: 8 bands, polar bands of 150 / 100 / 66 / 48 / 32 rows: 0.963 / 0.915 / 0.828 / 0.835 / 0.824; 4 bands with
+    400-row polar bands 1.33 (profiles/r2_p_*).  The balance point of the two costs, not below 48 rows (the filter rows,
+    the plain rows around them and the wide halo must fit) and not above an even share."""
     if nranks < 3 or not filtered:
         return 0
     even = num_lat // nranks
-    row_us = 0.06 * num_lon / 3600.0
-    shift = 6.0 / (row_us * (1.0 + 2.0 / (nranks - 2)))
-    return max(even // 2, int(even - shift), 32)
+    w = num_lon / 3600.0
+    a, b, c0, c1 = 0.172 * w, 0.174 * w, 51.0, 14.0
+    mid = nranks - 2
+    rp = (b * num_lat / mid + c1 - c0) / (a + 2.0 * b / mid)
+    return int(min(even, max(48.0, rp)))
 
 
 def halo_rows(rank: int, nranks: int, num_lat: int):
