@@ -2091,7 +2091,9 @@ int gmd_create(const gmd_config *cfg, gmd_model **out) {
     // full-row operation (filter rows, reduced rows, pole rows): S1 of the wavefront covers that many rows more.
     m->fused = !GMD_STRICT && cfg->uv_adv_scheme != GMD_ADV_WENO && cfg->time_scheme == GMD_TIME_PREDICT_CORRECT &&
                (cfg->nranks == 1 || m->wide);
-    if (const char *ev = getenv("GMD_FUSED")) m->fused = m->fused && atoi(ev) != 0;
+    // GMD_FUSED=1 / 0 forces the fused kernel on (where it applies) / off; unset: on where it pays (below)
+    const char *fused_env = getenv("GMD_FUSED");
+    if (fused_env && atoi(fused_env) == 0) m->fused = false;
     if (m->fused) {
       auto flagged = [&](int j) {
         return j <= 0 || j >= nlat - 1 || m->mesh.flag_full[(size_t)j] || m->mesh.flag_half[(size_t)j] ||
@@ -2110,12 +2112,14 @@ int gmd_create(const gmd_config *cfg, gmd_model **out) {
       if (I1 - I0 < 6) m->fused = false;
       // a band of a multi-band run that holds polar rows keeps the three-sweep path: its step time is the chain
       // sweep -> polar rows -> sweep ..., and the polar-row CTAs (one SM each) cannot start while k_pc owns the SMs
-      // (measured at 0.1 degree: two 900-row bands 2.39 -> 2.22 ms per step with k_pc, four bands with 400-row polar
-      // bands 1.34 -> 1.49 ms)
-      if (cfg->nranks > 1 && (I0 > m->geo.r0 || I1 < m->geo.r1)) {
-        bool on = m->nr >= 600;
-        if (const char *ev = getenv("GMD_FUSED_POLAR_BANDS")) on = atoi(ev) != 0;
-        if (!on) m->fused = false;
+      // Where it pays.  A band without polar rows: always (one launch per predict_correct instead of three).  A band
+      // with polar rows: the polar-row CTAs (one SM each) cannot start while k_pc owns the SMs, so the chain sweep -> polar
+      // rows -> sweep ... of the rows next to the poles finishes AFTER k_pc instead of beside the interior sweeps; that
+      // costs 20-50 us per predict_correct and is only won back on a big band.  Measured on B200, ms per step, three
+      // sweeps -> fused: 3600x1801 4.18 -> 3.44, 7200x3601 16.0 -> 12.9, two 900-row bands of 3600 2.39 -> 2.22, but
+      // 1440x721 0.71 -> 0.90 and 400-row polar bands of 3600 (4 bands) 1.34 -> 1.49.
+      if ((I0 > m->geo.r0 || I1 < m->geo.r1) && !(fused_env && atoi(fused_env) != 0)) {
+        if ((double)(I1 - I0) * (double)nlon < 2.0e6) m->fused = false;
       }
       m->fz_I0 = I0;
       m->fz_I1 = I1;

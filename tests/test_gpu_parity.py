@@ -165,12 +165,19 @@ GOLDEN = ["rh_36x19_csp2", "rh_72x37_nosplit", "mz_60x31_upwind", "jz_72x37_diff
 
 
 @pytest.mark.parametrize("name", GOLDEN)
-@pytest.mark.parametrize("graph", [False, True])
-def test_golden_cases(golden_dir, name, graph, parity_log):
-    """committed oracle fixtures (tests/golden/make_golden.py): state after nsteps and the diag series"""
+@pytest.mark.parametrize("graph", [False, True, "fused"])
+def test_golden_cases(golden_dir, name, graph, parity_log, monkeypatch):
+    """committed oracle fixtures (tests/golden/make_golden.py): state after nsteps and the diag series.
+    "fused": the same through the fused predict_correct kernel k_pc (GMD_FUSED=1: grids this small would not pick it by
+    themselves), for the fixtures whose scheme it covers (predict_correct with centred / upwind advection)."""
     g = np.load(golden_dir / f"case_{name}.npz", allow_pickle=True)
     kw = ast.literal_eval(str(g["config"]))
+    mode = "fused" if graph == "fused" else ("graph" if graph else "direct")
+    monkeypatch.setenv("GMD_FUSED", "1" if mode == "fused" else "0")
     d = gmd.Dycore(gmd.Config(**kw))
+    if mode == "fused" and d.fused_rows() == (0, 0):
+        pytest.skip("this fixture's scheme does not use the fused kernel")
+    graph = mode != "direct"
     d.set_graph_mode(graph)
     d.set_state(g["u0"], g["v0"], g["gd0"], g["ghs"])
     d.run_init()
@@ -197,7 +204,7 @@ def test_golden_cases(golden_dir, name, graph, parity_log):
                                    for a, k in zip(o.state(), ("u1", "v1", "gd1"))])
     errs = [rel(u, g["u1"]), rel(v, g["v1"]) if np.abs(g["v1"]).max() > 0 else float(np.abs(v).max()), rel(gd, g["gd1"])]
     berr = np.abs(series[1:, 2] - g["beta"][1:]).max()
-    parity_log.add(f"golden:{name}:{'graph' if graph else 'direct'}", rel_l2_u_v_gd=errs, noise_floor_u_v_gd=floor,
+    parity_log.add(f"golden:{name}:{mode}", rel_l2_u_v_gd=errs, noise_floor_u_v_gd=floor,
                    tol="max(1e-12, 30 x floor)", beta_err=berr, beta_floor=bfloor,
                    mass_rel=np.abs(series[:, 0] / g["mass"] - 1).max(), energy_rel=np.abs(series[:, 1] / g["energy"] - 1).max())
     assert np.abs(series[:, 0] / g["mass"] - 1).max() <= 1e-13
@@ -263,14 +270,24 @@ def noise_floor(kw, test_case, nsteps):
     return [rel(a, b) for a, b in zip(o2.state(), o1.state())], o1
 
 
-def test_rossby_haurwitz_one_day_parity_C1(parity_log):
+_C1_ORACLE = {}
+
+
+@pytest.mark.parametrize("path", ["three_sweeps", "fused"])
+def test_rossby_haurwitz_one_day_parity_C1(path, parity_log, monkeypatch):
     """BASELINE config C1: RH wave 360x181, dt=240, csp2 x6, centred, filter 4 on 5 rows, one model day.
-    north_star: prognostic fields within 1e-12 rel-L2, mass/energy series within 1e-13 relative."""
+    north_star: prognostic fields within 1e-12 rel-L2, mass/energy series within 1e-13 relative.
+    Through both device paths of predict_correct: the three k_stage sweeps (what a grid this small picks) and the fused
+    kernel k_pc (what the 0.1 degree benchmark runs)."""
     kw = dict(num_lon=360, num_lat=181, time_step_size=240.0, subcycles=6, split_scheme="csp2",
               zonal_tend_filter_cutoff_wavenumber=[4] * 5)
     nsteps = 360
-    floor, o = noise_floor(kw, "rossby_haurwitz_wave", nsteps)
+    if "ref" not in _C1_ORACLE:
+        _C1_ORACLE["ref"] = noise_floor(kw, "rossby_haurwitz_wave", nsteps)
+    floor, o = _C1_ORACLE["ref"]
+    monkeypatch.setenv("GMD_FUSED", "1" if path == "fused" else "0")
     d = gmd.Dycore(gmd.Config(**kw))
+    assert (d.fused_rows() != (0, 0)) == (path == "fused")
     o0 = Oracle(OracleConfig(**kw))
     o0.set_initial_condition("rossby_haurwitz_wave")
     u, v, gd = o0.state()
@@ -281,7 +298,7 @@ def test_rossby_haurwitz_one_day_parity_C1(parity_log):
     errs = [rel(a, b) for a, b in zip(d.state(), o.state())]
     m, e, b = d.diag_series(nsteps + 1)
     mo, eo, _ = o.diag()
-    parity_log.add("C1:rossby_haurwitz_360x181_one_day", steps=nsteps, rel_l2_u_v_gd=errs, noise_floor_u_v_gd=floor,
+    parity_log.add(f"C1:rossby_haurwitz_360x181_one_day:{path}", steps=nsteps, rel_l2_u_v_gd=errs, noise_floor_u_v_gd=floor,
                    tol="max(1e-12, 20 x floor)", mass_drift=np.abs(m / m0 - 1).max(), energy_drift=np.abs(e / e0 - 1).max(),
                    mass_rel_vs_oracle=abs(m[-1] / mo - 1), energy_rel_vs_oracle=abs(e[-1] / eo - 1))
     for err, fl in zip(errs, floor):

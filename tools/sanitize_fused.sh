@@ -12,6 +12,7 @@ cat > /tmp/_san_case.py <<'PY'
 import os, sys
 import numpy as np
 sys.path.insert(0, os.getcwd())
+os.environ['GMD_FUSED'] = '1'   # a grid this small would not pick the fused kernel by itself
 import gamil_dycore_b200 as gmd
 kw = dict(num_lon=72, num_lat=37, time_step_size=600.0, subcycles=4, split_scheme="csp2", zonal_tend_filter_cutoff_wavenumber=[4, 4, 4])
 u, v, gd, ghs = gmd.initial_condition("mountain_zonal_flow", 72, 37)
