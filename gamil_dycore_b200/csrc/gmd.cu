@@ -889,13 +889,38 @@ static void launch_pdl(void (*fn)(const A), dim3 grid, dim3 block, size_t smem, 
   lc.numAttrs = 1;
   cudaLaunchKernelEx(&lc, fn, args);
 }
+// element groups per thread (1 or 2) when every item of the launch is one k_polar_lean handles, else 0
+static int polar_lean_groups(const gmd_model *m, const PolarArgs &p, int nitems) {
+  const char *ev = getenv("GMD_POLAR_LEAN");   // (read per launch: the tests switch it between two models of one process)
+  const bool off = ev && atoi(ev) == 0;
+  const int n = m->geo.nlon;
+  if (off || GMD_STRICT || (n & 3)) return 0;
+  const int G = (n / 4 + PT - 1) / PT;
+  if (G > 2) return 0;
+  for (int q = 0; q < nitems; q++) {
+    const unsigned pk = p.items[q];
+    const int K = (int)((pk >> 16) & 0x1ffu), kind = (int)((pk >> 28) & 7u);   // K = cutoff + 1
+    if (kind == IT_POLE_S || kind == IT_POLE_N) continue;
+    if ((pk & ITEM_REDUCE) || K < 1 || K > KF || 2 * K >= n) return 0;
+  }
+  return G;
+}
+template <int G>
+static void (*pick_polar_lean(int mode))(const PolarArgs) {
+  return (mode == MODE_S1) ? k_polar_lean<MODE_S1, G> : (mode == MODE_S2) ? k_polar_lean<MODE_S2, G>
+       : (mode == MODE_S3A) ? k_polar_lean<MODE_S3A, G> : k_polar_lean<MODE_EVAL, G>;
+}
 static void launch_polar(gmd_model *m, int mode, int nitems, PolarArgs &p, cudaStream_t st, bool pdl = false) {
   p.basis = m->d_basis;
   p.rot = m->d_rot;
   p.pdl = pdl ? 1 : 0;
-  const size_t sh = polar_smem(m, &p.use_q);
+  size_t sh = polar_smem(m, &p.use_q);
   void (*fn)(const PolarArgs) = (mode == MODE_S1) ? k_polar<MODE_S1> : (mode == MODE_S2) ? k_polar<MODE_S2>
                               : (mode == MODE_S3A) ? k_polar<MODE_S3A> : k_polar<MODE_EVAL>;
+  if (const int G = polar_lean_groups(m, p, nitems)) {   // rows in registers: no dynamic shared memory
+    fn = (G == 1) ? pick_polar_lean<1>(mode) : pick_polar_lean<2>(mode);
+    sh = 0;
+  }
   if (pdl) launch_pdl<PolarArgs>(fn, dim3((unsigned)nitems), dim3(PT), sh, st, p);
   else fn<<<nitems, PT, sh, st>>>(p);
 }
@@ -1988,9 +2013,8 @@ int gmd_create(const gmd_config *cfg, gmd_model **out) {
       if (e1 - e0 < HALO_N) m->wide = false;
     }
     if (getenv("GMD_NO_WIDE")) m->wide = false;
-    // single band: the split buys nothing (the one-wave interior launch owns every register file, so the polar-row
-    // CTAs cannot co-run; measured 4.80 vs 4.75 ms per step); with several bands the two polar ranks split off the
-    // rows next to their pole, so that the polar-row kernel that follows them overlaps the rest of the sweep
+    // the bands that hold polar rows split off the rows next to their pole, so that the polar-row kernel that follows
+    // them overlaps the rest of the sweep
     // fused polar cap: every item must be one the thread-owned projector handles (cutoff < KF, nlon % 4 == 0, at most
     // PQ element groups per thread)
     m->cap = (m->n_items[0] + m->n_items[1] > 0) && (nlon % 4 == 0) && ((nlon / 4 + PT - 1) / PT <= PQ) &&
@@ -2002,11 +2026,12 @@ int gmd_create(const gmd_config *cfg, gmd_model **out) {
         if (kind != IT_POLE_S && kind != IT_POLE_N && !(Kk >= 1 && Kk <= KF && 2 * Kk < nlon)) m->cap = false;
         if (pk & ITEM_REDUCE) m->cap = false;
       }
-    // without the fused cap a single band gains nothing from the split (the one-wave interior launch owns every
-    // register file, so the 512-thread polar-row CTAs cannot co-run; measured 4.80 vs 4.75 ms per step); the cap CTAs
-    // are ordinary stage CTAs and do overlap the interior sweep
-    static const bool cap_n1 = getenv("GMD_CAP_N1") != nullptr;
-    m->split = (m->wide || (m->cap && cfg->nranks == 1 && cap_n1)) && (m->bs + m->bn > 0);
+    // the three-sweep path of a single band splits as well: the rows next to the poles first, the polar rows behind them,
+    // the other rows beside both on stream2 (measured on B200, ms per step without / with: 360x181 0.416 / 0.321,
+    // 1440x721 0.710 / 0.685, 3600x1801 4.18 / 4.11 -- round 1 saw no gain because every launch then paid a full gap)
+    // (same schemes as the wide-halo bands: with WENO the advection sweeps between two stages read every row)
+    const bool split_n1 = cfg->nranks == 1 && cfg->uv_adv_scheme != GMD_ADV_WENO && cfg->time_scheme == GMD_TIME_PREDICT_CORRECT;
+    m->split = (m->wide || split_n1) && (m->bs + m->bn > 0);
     if (const char *ev = getenv("GMD_NO_SPLIT")) m->split = (atoi(ev) == 0) && (cfg->nranks == 1 || m->wide);
     if (m->bs + m->bn >= m->nr) m->split = false;
     // measured on two 226-row polar bands (profiles/r2_i_*): 1 -> 0.915 ms per step, 0 -> 0.962, 3 -> 1.015

@@ -1529,6 +1529,253 @@ __global__ void __launch_bounds__(PT) k_polar(const __grid_constant__ PolarArgs 
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// k_polar_lean<MODE, G>: the fast projector of k_polar with everything but the reductions in REGISTERS.
+// k_polar is one kernel for every kind of item (any cutoff, any row length, reduced rows); that generality costs
+// instructions -- 1860 per warp and item at 3600 columns, 17 % of them fp64 (profiles/r1_k_ncu_polar_summary.txt) -- and the
+// kernel sits on the critical chain sweep -> polar rows -> sweep of every band that holds polar rows.  When every item
+// of a launch is one the thread-owned projector handles (filter rows with cutoff < KF on a row of n % 4 == 0 elements,
+// G = ceil(n / 4 / PT) <= 2 element groups per thread; pole caps) the host launches this variant instead: the G x 4
+// elements a thread owns, their weights and base values stay in registers from the first load to the last store (no
+// row in shared memory, no index arithmetic beyond b + q n/4), the loops over groups and quarters are unrolled at
+// compile time.  Same element-to-thread mapping, same operation order, same reduction trees as k_polar: the results are
+// bit-identical (tests/test_gpu_parity.py::test_polar_lean_is_bit_identical).
+// ---------------------------------------------------------------------------------------------------------
+template <int MODE, int G>
+__global__ void __launch_bounds__(PT) k_polar_lean(const __grid_constant__ PolarArgs a) {
+  __shared__ double red[64];
+  __shared__ double coef[2 * KF + 2];
+  __shared__ double part[512];
+  __shared__ double bc[2];
+  constexpr int NW = PT / 32;
+  constexpr int NV = 2 + 2 * KF;
+  static_assert(NV * NW <= 512 && (NV * NW) % 32 == 0, "second reduction stage runs on whole warps");
+  const unsigned pk = a.items[blockIdx.x];
+  const int j = (int)(pk & 0xffffu), cutoff = (int)((pk >> 16) & 0x1ffu) - 1, kind = (int)((pk >> 28) & 7u);
+  const int rescale = a.rescale;
+  const int n = a.g.nlon, r0 = a.g.r0;
+  const int tid = threadIdx.x;
+  trace_in(a.tseq);
+  const ptrdiff_t off = (ptrdiff_t)(j - r0) * (ptrdiff_t)n;
+  double ip1 = 0.0, ip2 = 0.0;
+  if (a.pdl) {
+    pdl_trigger();
+    pdl_wait();
+  }
+  if (kind == IT_POLE_S || kind == IT_POLE_N) {
+    // src/dycore_mod.F90:572-596 (as k_polar)
+    const double *__restrict__ g0 = a.Egd + off;
+    const double *__restrict__ g1 = (kind == IT_POLE_S) ? a.Egd + off + n : a.Egd + off - n;
+    const double *__restrict__ vv = (kind == IT_POLE_S) ? a.EV + off : a.EV + off - n;
+    const double *__restrict__ Q = (MODE == MODE_S3A) ? a.Pgd : a.Ogd;
+    double acc = 0.0;
+    for (int i0 = tid; i0 < n; i0 += PT * 8) {
+      double av[8], bv[8], cv[8];
+#pragma unroll
+      for (int e = 0; e < 8; e++) {
+        const int i = i0 + e * PT;
+        const bool ok = i < n;
+        av[e] = ok ? __ldg(g0 + i) : 0.0;
+        bv[e] = ok ? __ldg(g1 + i) : 0.0;
+        cv[e] = ok ? __ldg(vv + i) : 0.0;
+      }
+#pragma unroll
+      for (int e = 0; e < 8; e++) {
+        const int i = i0 + e * PT;
+        if (i < n) {
+          const double f = (sqrt(av[e]) + sqrt(bv[e])) * cv[e];
+          acc = (kind == IT_POLE_S) ? acc + f : acc - f;
+        }
+      }
+    }
+    const double r = block_sum<PT>(acc, red);
+    if (tid == 0) bc[0] = -(r * 2.0 / n / a.radius / a.dlat);
+    __syncthreads();
+    const double dG = bc[0];
+    const double cw = a.t.cosf[j];
+    for (int i = tid; i < n; i += PT) {
+      double o = 0.0;
+      if (MODE != MODE_EVAL) o = __ldg(Q + off + i);
+      if (MODE == MODE_S1 || MODE == MODE_S2) a.Ngd[off + i] = o + a.dt * dG;
+      if (MODE != MODE_S1) a.Tgd[off + i] = dG;
+      if (MODE == MODE_S3A) {
+        ip1 = ip1 + dG * o * cw;
+        ip2 = ip2 + dG * dG * cw;
+      }
+    }
+  } else {
+    double *T = (kind == IT_DU) ? a.TU : (kind == IT_DV) ? a.TV : a.Tgd;
+    const double *__restrict__ W = (kind == IT_DU) ? a.EU : (kind == IT_DV) ? a.EV : a.Egd;
+    const double *__restrict__ O = (kind == IT_DU) ? a.OU : (kind == IT_DV) ? a.OV : a.Ogd;
+    double *N = (kind == IT_DU) ? a.NU : (kind == IT_DV) ? a.NV : a.Ngd;
+    const double *__restrict__ P = (kind == IT_DU) ? a.PU : (kind == IT_DV) ? a.PV : a.Pgd;
+    const double *__restrict__ Q = (MODE == MODE_S1 || MODE == MODE_S2) ? O : (MODE == MODE_S3A) ? P : nullptr;
+    const int K = cutoff + 1;
+    const int n4 = n >> 2;
+    // ---- every global load of the row first: element (g, q) is b + q n4, b = tid + g PT -----------------------
+    double xv[G][4], wv[G][4], qv[G][4];
+    bool okg[G];
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+      const int b = tid + g * PT;
+      okg[g] = b < n4;
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const ptrdiff_t i = off + b + q * n4;
+        xv[g][q] = okg[g] ? T[i] : 0.0;
+        double ww = (okg[g] && rescale) ? __ldg(W + i) : 0.0;
+        if (kind == IT_DGD) ww += (okg[g] && rescale) ? __ldg(a.ghs + i) : 0.0;
+        wv[g][q] = ww;
+        qv[g][q] = (okg[g] && MODE != MODE_EVAL) ? __ldg(Q + i) : 0.0;
+      }
+    }
+    double bcv[KF], bsv[KF];
+#pragma unroll
+    for (int k = 0; k < KF; k++) {
+      bcv[k] = bsv[k] = 0.0;
+      if (k < K && tid < n4) {
+        bcv[k] = __ldg(a.basis + (size_t)(2 * k + 1) * n + tid);
+        bsv[k] = __ldg(a.basis + (size_t)(2 * k + 2) * n + tid);
+      }
+    }
+    // ---- s1 and the 2K+1 dot products in one pass over the thread's own elements --------------------------------
+    double v[NV];
+#pragma unroll
+    for (int m = 0; m < NV; m++) v[m] = 0.0;
+    {
+      double s1p = 0.0;
+#pragma unroll
+      for (int g = 0; g < G; g++)
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+          if (okg[g]) s1p = s1p + xv[g][q] * wv[g][q];
+      v[0] = s1p;
+    }
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+      if (okg[g]) {
+        const double x0 = xv[g][0], x1 = xv[g][1], x2 = xv[g][2], x3 = xv[g][3];
+        const double e0 = x0 + x2, e1 = x1 + x3, d0 = x0 - x2, d1 = x1 - x3;
+        const double a0 = e0 + e1, a2 = e0 - e1;
+        v[1] += a0;
+#pragma unroll
+        for (int k = 0; k < KF; k++) {
+          if (k < K) {
+            const double ec = __ldg(a.rot + (g * KF + k) * 2), es = __ldg(a.rot + (g * KF + k) * 2 + 1);
+            const double cr = bcv[k] * ec - bsv[k] * es;   // cos, sin of wavenumber k+1 at element b
+            const double sr = bsv[k] * ec + bcv[k] * es;
+            switch ((k + 1) & 3) {                         // quarter turns of the other three elements
+              case 1: v[2 + 2 * k] += cr * d0 - sr * d1; v[3 + 2 * k] += sr * d0 + cr * d1; break;
+              case 2: v[2 + 2 * k] += cr * a2;           v[3 + 2 * k] += sr * a2;           break;
+              case 3: v[2 + 2 * k] += cr * d0 + sr * d1; v[3 + 2 * k] += sr * d0 - cr * d1; break;
+              default: v[2 + 2 * k] += cr * a0;          v[3 + 2 * k] += sr * a0;           break;
+            }
+          }
+        }
+      }
+    }
+    const int warp = tid >> 5, lane = tid & 31;
+    warp_sum_n<NV>(v);
+    if (lane == 0) {
+#pragma unroll
+      for (int m = 0; m < NV; m++) part[m * NW + warp] = v[m];
+    }
+    __syncthreads();
+    if (tid < NV * NW) {  // NW-lane segments, fixed tree
+      double p = part[tid];
+#pragma unroll
+      for (int o = NW / 2; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+      if ((tid & (NW - 1)) == 0) {
+        const int m = tid / NW;
+        if (m == 0) bc[0] = p;
+        else coef[m - 1] = p * ((m == 1) ? 1.0 / n : 2.0 / n);  // rfftf1.f:87-107 normalisation
+      }
+    }
+    __syncthreads();
+    const double s1 = bc[0];
+    bool do_filter = true;
+    double s2 = 1.0;
+    if (rescale) do_filter = fabs(s1) > 1.0e-16;  // filter_inner_product_threshold, src/filter_mod.F90:31
+    if (do_filter) {
+      // ---- reconstruction from entries 0 .. 2K-1 (sin(K x) is dropped: quirk B3), in place in the registers -----
+      const double c0 = coef[0];
+      double cc[KF], cs[KF];
+#pragma unroll
+      for (int k = 0; k < KF; k++) {
+        cc[k] = (k < K) ? coef[1 + 2 * k] : 0.0;
+        cs[k] = (k < K - 1) ? coef[2 + 2 * k] : 0.0;
+      }
+      double s2p = 0.0;
+#pragma unroll
+      for (int g = 0; g < G; g++) {
+        if (okg[g]) {
+          double S0 = c0, Pa = 0.0, Ra = 0.0, P2 = 0.0;
+#pragma unroll
+          for (int k = 0; k < KF; k++) {
+            if (k < K) {
+              const double ec = __ldg(a.rot + (g * KF + k) * 2), es = __ldg(a.rot + (g * KF + k) * 2 + 1);
+              const double cr = bcv[k] * ec - bsv[k] * es;
+              const double sr = bsv[k] * ec + bcv[k] * es;
+              const double Pk = cc[k] * cr + cs[k] * sr;   // value at b; a quarter turn further: Rk, -Pk, -Rk
+              const double Rk = cs[k] * cr - cc[k] * sr;
+              switch ((k + 1) & 3) {
+                case 1: Pa += Pk; Ra += Rk; break;
+                case 2: P2 += Pk; break;
+                case 3: Pa += Pk; Ra -= Rk; break;
+                default: S0 += Pk; break;
+              }
+            }
+          }
+          const double y0 = (S0 + P2) + Pa, y2 = (S0 + P2) - Pa, y1 = (S0 - P2) + Ra, y3 = (S0 - P2) - Ra;
+          xv[g][0] = y0;
+          xv[g][1] = y1;
+          xv[g][2] = y2;
+          xv[g][3] = y3;
+          s2p = s2p + y0 * wv[g][0] + y1 * wv[g][1] + y2 * wv[g][2] + y3 * wv[g][3];
+        }
+      }
+      if (rescale) {
+        const double r = block_sum<PT>(s2p, red);
+        if (tid == 0) bc[1] = r;
+        __syncthreads();
+        s2 = bc[1];
+      }
+    }
+    const double cw = (kind == IT_DV) ? a.t.cosh[j] : a.t.cosf[j];
+    const bool scale = do_filter && rescale && (s2 != 0.0);   // s2 == 0: see k_polar
+    const double ratio = scale ? s1 / s2 : 1.0;
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+      if (okg[g]) {
+        const int b = tid + g * PT;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const ptrdiff_t i = off + b + q * n4;
+          const double o = qv[g][q];
+          const double d = xv[g][q] * ratio;
+          if (MODE == MODE_S1 || MODE == MODE_S2) N[i] = o + a.dt * d;
+          if (MODE != MODE_S1) T[i] = d;
+          if (MODE == MODE_S3A) {
+            ip1 = ip1 + d * o * cw;
+            ip2 = ip2 + d * d * cw;
+          }
+        }
+      }
+    }
+  }
+  if (MODE == MODE_S3A) {
+    block_sum2<PT>(ip1, ip2, red);
+    if (tid == 0) {
+      a.partials[2 * blockIdx.x] = ip1;
+      a.partials[2 * blockIdx.x + 1] = ip2;
+    }
+    if (a.fold.ticket)
+      fold_tail<PT>(a.fold.ticket, a.fold.total, a.fold_partials, a.fold.n, a.fold.out, a.fold.r.page, a.fold.r.rank,
+                    a.fold.r.nranks, a.fold.r.k, a.tseq);
+  }
+  trace_out(a.tseq);
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Fused polar cap (k_cap): the sweep over the rows next to a pole AND the polar rows of the same sweep -- filter +
 // rescale + update of the flagged rows, pole caps -- in ONE launch.  On a short latitude band the chain
 //   cap sweep -> polar rows -> cap sweep of the next operator evaluation -> ...

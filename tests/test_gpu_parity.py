@@ -520,6 +520,36 @@ def test_error_behaviour():
         d.run_init()
 
 
+@pytest.mark.parametrize("name", ["rh_360x181_G1", "sg_3600x1801_G2", "jz_1440x721_diffusion_G1"])
+def test_polar_lean_is_bit_identical(name, monkeypatch):
+    """k_polar_lean (the polar rows with the row elements in registers) keeps k_polar's element-to-thread mapping,
+    operation order and reduction trees: the same run through either kernel gives the same bits."""
+    cases = {
+        "rh_360x181_G1": ("rossby_haurwitz_wave", dict(num_lon=360, num_lat=181, time_step_size=240.0, subcycles=6, split_scheme="csp2",
+                                                       zonal_tend_filter_cutoff_wavenumber=[4] * 5), 8),
+        "sg_3600x1801_G2": ("steady_geostrophic_flow", dict(num_lon=3600, num_lat=1801, time_step_size=10.0, subcycles=10,
+                                                           split_scheme="csp2", zonal_tend_filter_cutoff_wavenumber=[4] * 20), 2),
+        "jz_1440x721_diffusion_G1": ("jet_zonal_flow", dict(num_lon=1440, num_lat=721, time_step_size=30.0, subcycles=6, split_scheme="csp2",
+                                                            zonal_tend_filter_cutoff_wavenumber=[5, 5, 4, 4, 3, 3, 2, 2, 1, 1],
+                                                            use_diffusion=True, diffusion_coef=6.0e3), 3),
+    }
+    ic, kw, nsteps = cases[name]
+    u, v, gd, ghs = gmd.initial_condition(ic, kw["num_lon"], kw["num_lat"])
+    res = {}
+    for lean in (1, 0):
+        monkeypatch.setenv("GMD_POLAR_LEAN", str(lean))
+        d = gmd.Dycore(gmd.Config(**kw))
+        d.set_graph_mode(False)
+        d.set_state(u, v, gd, ghs)
+        d.run_init()
+        d.step(nsteps)
+        res[lean] = (d.state(), d.diag())
+        d.close()
+    for p, q in zip(res[1][0], res[0][0]):
+        assert np.array_equal(p, q)
+    assert res[1][1] == res[0][1]
+
+
 FUSED_CASES = {
     # csp2 with the deferred update: slow / fast passes, LAZY 0 / 1 / 2 of k_pc
     "rh_csp2_360x181": ("rossby_haurwitz_wave", dict(num_lon=360, num_lat=181, time_step_size=240.0, subcycles=6, split_scheme="csp2",
