@@ -26,6 +26,12 @@ for lib in libs:
             d.time_stage_variant(p, mode, 3)
             ms, nb = d.time_stage_variant(p, mode, 20)
             out[f"{p}.{nm}"] = (round(ms * 1e3, 1), round(nb / ms / 1e6))
+        try:   # the fused predict_correct kernel (13 / 11 words per column), where the configuration uses it
+            d.time_stage_variant(p, 5, 3)
+            ms, nb = d.time_stage_variant(p, 5, 20)
+            out[f"{p}.k_pc"] = (round(ms * 1e3, 1), round(nb / ms / 1e6))
+        except gmd.GmdError:
+            pass
     d.step(3)
     d.step(10)
     print(os.path.basename(lib), json.dumps(out), "step_ms", round(d.last_step_ms() / 10, 3), flush=True)
