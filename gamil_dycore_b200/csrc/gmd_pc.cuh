@@ -7,11 +7,13 @@
 //
 // k_stage runs these as three sweeps over the band (7..13 + 13 + 10 words per column).  Every sweep is a south -> north
 // march whose stencil reaches one row south and two rows north, so the three marches can run as a WAVEFRONT a few rows
-// apart: a CTA is three warps working on the SAME 64-column strip -- warp 0 evaluates S1 at row j+8.., warp 1 S2 four
-// rows behind it, warp 2 S3a another four rows behind -- and the rows of A, `old`, B and tend2 travel from warp to warp
-// through a small shared-memory ring (6 rows deep), never through global memory.  Per column the kernel reads
-// old (3) + ghs (1) [+ the deferred update's tendency (3)] and writes tend3 (3) [+ the materialised old state (3)]:
-// 13 words instead of 36 for a fast predict_correct with the deferred update.
+// apart: a CTA is three warps working on the SAME 64-column strip -- warp 0 evaluates S1, warp 1 S2 four rows behind
+// it, warp 2 S3a another four rows behind -- and the rows of A, `old`, B and tend2 travel from warp to warp through
+// small shared-memory rings (5 / 4 rows deep), never through global memory.  What S1 consumes from global memory --
+// the old state, ghs, the deferred update's tendency, the per-row coefficient records -- arrives as packets of
+// cp.async.bulk copies counted on mbarriers, three rows ahead, issued by one lane of the S2 warp.  Per column the
+// kernel reads old (3) + ghs (1) [+ the deferred update's tendency (3)] and writes tend3 (3) [+ the materialised old
+// state (3)]: 13 words instead of 36 for a fast predict_correct with the deferred update.
 //
 // Each warp keeps the row window of ITS stage in registers exactly as k_stage does (tend_col is shared); the warps
 // of a CTA advance in lockstep, one row per tick, with one named barrier per tick.  Three chained stencils need
@@ -22,7 +24,8 @@
 //
 // Rows that depend on a full-row operation -- zonal filter rows, reduced rows, pole caps -- cannot be part of the
 // wavefront: the host keeps the fused rows at least (2 south, 4 north) rows away from them and runs the remaining
-// rows next to the poles through k_stage + k_polar as before, concurrently (gmd.cu: pc_fused).
+// rows next to the poles through k_stage + k_polar as before, concurrently (gmd.cu: launch_pc and the m->fz_active
+// branch of stage()).
 //
 // Product build only (the strict build keeps the three-sweep path, whose operand order follows the reference).
 #pragma once
