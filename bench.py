@@ -337,7 +337,7 @@ def main():
         # the previous predict_correct's update folded in).  `achieved` follows the contract: SURVEY 8d's per-unit figure
         # (312 B per column and fast predict_correct, 216 B slow) x the columns the launch covers / its duration.  The
         # kernel itself only has to move 13 of those 39 words (`moved`): the stage states travel through shared memory,
-        # so `frac` can exceed 1 and the kernel is bound by fp64 issue, not by HBM (profiles/r2_n_ncu_k_pc_summary.txt).
+        # so `frac` can exceed 1 and the kernel is bound by fp64 issue, not by HBM (profiles/r2_r_ncu_k_pc_summary.txt).
         kms, kbytes = fused
         per_col = 312.0 if pass_name != "slow" else 216.0
         model_bytes = kbytes / (13 * 8.0) * per_col
