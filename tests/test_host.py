@@ -419,6 +419,10 @@ def test_pc_ring_schedule():
         return int(m.group(1))
     D1, D2, DAB, DOP, IND, REC = (const(n) for n in ("PC_D1", "PC_D2", "PC_DEPTH_AB", "PC_DEPTH_OP", "PC_IN_DEPTH", "PC_REC_DEPTH"))
     depth = {"A": DAB, "B": DAB, "O": DOP, "P": DOP}
+    # five CTAs per SM (GMD_PC_MINB): rings + input ring (7 lines per packet) + row records + barriers, 1 KB reserved per
+    # CTA by the hardware, ~0.5 KB static (reduction scratch of the fold) -- within B200's 228 KB per SM
+    smem = (3 * (2 * DAB + 2 * DOP) + IND * 7) * 512 + REC * 16 * 8 + IND * 8
+    assert 5 * (smem + 1024 + 512) <= 228 * 1024, smem
     for n in range(1, 70):                      # rows of a chunk
         ja, jb = 0, n
         rja0, rjb0 = ja - 2, jb + 4
