@@ -377,6 +377,38 @@ def test_steady_geostrophic_flow_is_stationary():
     assert np.abs(v).max() < 5e-2 and np.abs(u - u0).max() < 0.2
 
 
+def test_rossby_haurwitz_wave_moves_at_the_published_phase_speed():
+    """A known answer that does not come from restating the code: the wavenumber-4 Rossby-Haurwitz wave of the
+    reference's test case (rossby_haurwitz_wave_test_mod.F90, Williamson et al. 1992 test case 6: R = 4, omega = K =
+    7.848e-6 1/s) moves eastward without change of shape at nu = (R (3 + R) omega - 2 Omega) / ((1 + R) (2 + R)) in the
+    nondivergent limit, 12.2 degrees per day; published shallow-water runs of the case sit within a few per cent of it.
+    The oracle's full step (operators, polar filter, predictor-corrector with beta, csp2) must reproduce that: phase of
+    zonal wavenumber 4 of the geopotential at mid latitudes after one model day."""
+    cfg = OracleConfig(num_lon=180, num_lat=91, time_step_size=240.0, subcycles=6, split_scheme="csp2",
+                       zonal_tend_filter_cutoff_wavenumber=[4] * 5)
+    o = Oracle(cfg)
+    o.set_initial_condition("rossby_haurwitz_wave")
+    gd0 = o.state()[2].copy()
+    o.run_init()
+    nsteps = 360   # one day
+    o.step(nsteps)
+    gd1 = o.state()[2]
+    R, om, Om = 4.0, 7.848e-6, 7.292e-5
+    nu = (R * (3.0 + R) * om - 2.0 * Om) / ((1.0 + R) * (2.0 + R))
+    expect = math.degrees(nu * nsteps * cfg.time_step_size)          # degrees of longitude per day
+    rows = range(55, 71)                                             # 20N .. 50N, where the wave is strongest
+    shift = []
+    for j in rows:
+        c0, c1 = np.fft.rfft(gd0[j])[4], np.fft.rfft(gd1[j])[4]
+        dphi = -np.angle(c1 / c0)                                    # pattern f(lambda - s): phase of mode 4 falls by 4 s
+        shift.append(math.degrees(dphi) / 4.0)
+        assert abs(abs(c1) / abs(c0) - 1.0) < 0.05                   # the wave keeps its amplitude
+    got = float(np.mean(shift))
+    assert 11.0 < expect < 13.0
+    assert abs(got / expect - 1.0) < 0.12, (got, expect)
+    assert np.std(shift) < 0.5                                       # the same speed at every latitude: shape preserved
+
+
 def test_pole_rows():
     """u = U = 0 on the pole rows for ever; dgd on a pole row is one zonal constant (cap formula)."""
     cfg = OracleConfig(num_lon=72, num_lat=37, time_step_size=600, subcycles=4,
