@@ -64,6 +64,123 @@ def test_config_defaults_match_params_mod():
     assert list(c.cutoff) == [0] * 20 and (c.rank, c.nranks, c.device) == (0, 1, -1)
 
 
+def _c_prototypes(hdr):
+    """name -> (return type, [argument types]) of every gmd_* prototype of a header, comments stripped"""
+    code = re.sub(r"^\s*#.*$", "", re.sub(r"/\*.*?\*/", "", hdr, flags=re.S), flags=re.M)
+    out = {}
+    for ret, name, args in re.findall(r"([A-Za-z_][\w\s\*]*?)\b(gmd_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", code):
+        args = [a.strip() for a in args.split(",")]
+        args = [] if args == ["void"] else [re.sub(r"\s*\b\w+$", "", a).replace("const ", "").replace(" ", "") for a in args]
+        out[name] = (ret.replace("const ", "").replace(" ", ""), args)
+    return out
+
+
+def _fortran_interfaces(src):
+    """name -> (return kind, [argument kinds]) of every bind(c) interface of fortran/gmd_c.F90, kinds in C spelling"""
+    src = re.sub(r"!.*", "", src)
+    out = {}
+    pat = re.compile(r"^\s*(subroutine|integer\(c_int\) function|type\(c_ptr\) function)\s+(\w+)\s*\(([^)]*)\)\s*"
+                     r"bind\(c, name='(\w+)'\)(.*?)^\s*end (?:subroutine|function)", re.S | re.M)
+    for kind, fname, args, cname, body in pat.findall(src):
+        assert fname == cname
+        args = [a.strip() for a in args.split(",") if a.strip()]
+        decl = {}
+        for line in body.splitlines():
+            m = re.match(r"\s*(type\(c_ptr\)|type\(gmd_config\)|integer\(c_int\)|real\(c_double\)|character\(kind=c_char\))"
+                         r"((?:,\s*\w+(?:\(\w+\))?)*)\s*::\s*(.*)", line)
+            if not m:
+                continue
+            base, attrs, names = m.groups()
+            by_value = "value" in attrs
+            for n in re.findall(r"(\w+)(?:\([^)]*\))?", names):
+                if base == "type(c_ptr)":
+                    decl[n] = "ptr" if by_value else "ptr*"
+                elif base == "type(gmd_config)":
+                    decl[n] = "gmd_config*"
+                elif base == "integer(c_int)":
+                    decl[n] = "int" if by_value else "int*"
+                elif base == "real(c_double)":
+                    decl[n] = "double" if by_value else "double*"
+                else:
+                    decl[n] = "ptr"            # character buffers travel as void*
+        out[cname] = ({"subroutine": "void", "integer(c_int) function": "int", "type(c_ptr) function": "ptr"}[kind],
+                      [decl[a] for a in args])
+    return out
+
+
+def test_fortran_shim_matches_the_c_header():
+    """fortran/gmd_c.F90 cannot be compiled in this image (no Fortran compiler), so its ISO_C_BINDING interfaces are
+    checked textually against include/gmd.h: struct gmd_config field by field (order, type, extent -- bind(c) derived
+    types follow the C layout rules), every enum constant it mirrors, and every bound procedure's return and argument
+    kinds; and the replacement dycore_mod (fortran/dycore_mod.F90) only calls what gmd_c declares."""
+    hdr = open(os.path.join(ROOT, "include", "gmd.h")).read()
+    f90 = open(os.path.join(ROOT, "fortran", "gmd_c.F90")).read()
+    code = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    # struct
+    body = re.search(r"typedef struct gmd_config \{(.*?)\} gmd_config;", code, re.S).group(1)
+    c_fields = [(t, n, int(d) if d else 1) for t, n, d in re.findall(r"\b(int|double)\s+(\w+)(?:\[(\d+)\])?\s*;", body)]
+    fbody = re.search(r"type, bind\(c\) :: gmd_config(.*?)end type gmd_config", f90, re.S).group(1)
+    f_fields = [({"integer(c_int)": "int", "real(c_double)": "double"}[t], n, int(d) if d else 1)
+                for t, n, d in re.findall(r"^\s*(integer\(c_int\)|real\(c_double\))\s+(\w+)(?:\((\d+)\))?\s*$", fbody, re.M)]
+    assert len(c_fields) >= 24 and f_fields == c_fields
+    # the ctypes mirror of the Python interface is the third copy of the same struct
+    py = [(("int" if f[1] in (ctypes.c_int, ctypes.c_int * 20) else "double"), 20 if f[1] is ctypes.c_int * 20 else 1)
+          for f in gmd._Cfg._fields_]
+    assert py == [(t, d) for t, _, d in c_fields]
+    assert ctypes.sizeof(gmd._Cfg) == sum((4 if t == "int" else 8) * d for t, _, d in c_fields) + _c_padding(c_fields)
+    # enum constants
+    c_enum = {}
+    for grp in re.findall(r"enum \{(.*?)\}", code, re.S):
+        for n, v in re.findall(r"(GMD_\w+)\s*=\s*(\d+)", grp):
+            c_enum[n] = int(v)
+    f_par = {n: int(v) for line in re.findall(r"integer\(c_int\), parameter ::(.*)", f90)
+             for n, v in re.findall(r"(GMD_\w+)\s*=\s*(\d+)", line)}
+    assert len(f_par) >= 13 and all(c_enum[n] == v for n, v in f_par.items())
+    # procedures
+    protos = _c_prototypes(hdr)
+    ifaces = _fortran_interfaces(f90)
+    assert len(ifaces) >= 17
+    norm = lambda t: {"gmd_model*": "ptr", "constgmd_model*": "ptr", "void*": "ptr", "char*": "ptr",
+                      "gmd_model**": "ptr*"}.get(t, t)
+    for name, (fret, fargs) in ifaces.items():
+        cret, cargs = protos[name]
+        cargs = [norm(a) for a in cargs]
+        # host arrays are handed over as c_loc(...) pointers (type(c_ptr), value) or as assumed-size / scalar dummies
+        # passed by reference: both are a C double* / int*
+        fargs_n = [("double*" if (a == "ptr" and c == "double*") else a) for a, c in zip(fargs, cargs)]
+        assert norm(cret) == fret, name
+        assert len(fargs) == len(cargs) and fargs_n == cargs, (name, fargs, cargs)
+    # the replacement dycore_mod
+    dm = re.sub(r"!.*", "", open(os.path.join(ROOT, "fortran", "dycore_mod.F90")).read())
+    called = set(re.findall(r"\b(gmd_[a-z_]+)\s*\(", dm))
+    assert called and called <= set(ifaces) | {"gmd_error_message"}, called - set(ifaces)
+    for sub in ("dycore_init", "dycore_restart", "dycore_run", "dycore_final"):      # src/dycore_mod.F90:22-25
+        assert re.search(r"subroutine %s\b" % sub, dm), sub
+
+
+def _c_padding(fields):
+    """bytes of alignment padding of a C struct of int / double members (natural alignment, x86-64 / aarch64)"""
+    off = pad = 0
+    for t, _, d in fields:
+        a = 4 if t == "int" else 8
+        if off % a:
+            pad += a - off % a
+            off += a - off % a
+        off += a * d
+    if off % 8:
+        pad += 8 - off % 8
+    return pad
+
+
+@pytest.mark.parametrize("header", ["gmd.h", "gmd_host.h"])
+def test_headers_are_plain_c(header, tmp_path):
+    """the boundary is a C ABI: both headers compile as C99 on their own (no C++, CUDA or torch types)"""
+    src = write(tmp_path, '#include "%s"\nint main(void) { return 0; }\n' % header, "t.c")
+    res = subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-fsyntax-only",
+                          "-I", os.path.join(ROOT, "include"), src], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+
+
 # ------------------------------------------------------------------------------------------------ namelist
 def parse(path):
     rc, out = selftest("parse", path)
