@@ -377,6 +377,57 @@ def test_steady_geostrophic_flow_is_stationary():
     assert np.abs(v).max() < 5e-2 and np.abs(u - u0).max() < 0.2
 
 
+def test_steady_geostrophic_error_converges_at_second_order():
+    """A known answer that does not come from restating the code: Williamson et al. 1992 test case 2
+    (steady_geostrophic_flow_test_mod.F90:14-16) is an exact steady solution of the continuous equations, so the
+    departure from the initial condition after a fixed time is the truncation error of the whole step -- C-grid
+    operators, IAP transform, polar filter, predictor-corrector, csp2 -- and must fall by 4 per halving of the mesh and
+    the time step (second-order centred differences and a second-order integrator)."""
+    errs = []
+    for nlon, nlat, dt in [(36, 19, 1200.0), (72, 37, 600.0), (144, 73, 300.0)]:
+        o = Oracle(OracleConfig(num_lon=nlon, num_lat=nlat, time_step_size=dt, subcycles=6, split_scheme="csp2",
+                                zonal_tend_filter_cutoff_wavenumber=[4] * 5))
+        o.set_initial_condition("steady_geostrophic_flow")
+        u0, v0, gd0 = [x.copy() for x in o.state()]
+        o.run_init()
+        o.step(int(6 * 3600 / dt))
+        u, v, gd = o.state()
+        errs.append((np.sqrt(np.mean((gd - gd0) ** 2) / np.mean(gd0 ** 2)), np.abs(u - u0).max(), np.abs(v).max()))
+    for coarse, fine in zip(errs, errs[1:]):
+        for a, b in zip(coarse, fine):
+            assert 3.7 < a / b < 4.3, errs
+    assert errs[-1][0] < 1.2e-4
+
+
+def test_balanced_jet_without_the_bump_stays_put():
+    """The zonal jet of Galewsky et al. 2004 (jet_zonal_flow_test_mod.F90:16-66) is in geostrophic balance with the
+    height field the IC plugin integrates with QUADPACK; without the height bump the continuous solution is steady.
+    The oracle must hold it -- v stays near zero, u and gd near the initial state -- and the residual must shrink with
+    the mesh (the jet is 1/7 of a radian wide: 72x37 barely resolves it).  Checks the plugin's quadrature against the
+    discrete operators, which no restatement of either alone does."""
+    res = []
+    for nlon, nlat, dt in [(72, 37, 600.0), (144, 73, 300.0)]:
+        o = Oracle(OracleConfig(num_lon=nlon, num_lat=nlat, time_step_size=dt, subcycles=6, split_scheme="csp2",
+                                zonal_tend_filter_cutoff_wavenumber=[4] * 5))
+        o.set_initial_condition("jet_zonal_flow")
+        u0, v0, gd0 = [x.copy() for x in o.state()]
+        bump = gd0 - gd0.min(axis=1, keepdims=True)
+        # 120 m cos(lat) at 45N, centred on (lon, lat) = (90E, 45N); nothing of it on the far side of the globe
+        assert abs(bump.max() / 9.80616 - 120.0 * math.cos(math.pi / 4)) < 0.5 and bump.max(axis=0).min() == 0.0
+        j, i = np.unravel_index(bump.argmax(), bump.shape)
+        assert (i, j) == (nlon // 2, 3 * (nlat - 1) // 4)
+        gdz = np.repeat(gd0.min(axis=1, keepdims=True), nlon, axis=1)
+        assert np.abs(u0).max() == pytest.approx(80.0, abs=0.5) and not v0.any()
+        o.set_state(u0, v0, gdz, None)
+        o.run_init()
+        o.step(int(24 * 3600 / dt))                                   # one day
+        u, v, gd = o.state()
+        res.append((np.abs(u - u0).max(), np.abs(v).max(), np.abs(gd - gdz).max() / 9.80616))
+        assert np.ptp(u - u.mean(axis=1, keepdims=True)) < 1e-9      # and stays zonally symmetric
+    assert res[1][0] < 0.15 and res[1][1] < 0.4 and res[1][2] < 40.0, res       # m/s, m/s, m (of 80 m/s, 10 km)
+    assert all(b < 0.7 * a for a, b in zip(res[0], res[1])), res
+
+
 def test_rossby_haurwitz_wave_moves_at_the_published_phase_speed():
     """A known answer that does not come from restating the code: the wavenumber-4 Rossby-Haurwitz wave of the
     reference's test case (rossby_haurwitz_wave_test_mod.F90, Williamson et al. 1992 test case 6: R = 4, omega = K =
