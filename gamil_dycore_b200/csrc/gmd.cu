@@ -134,6 +134,8 @@ struct gmd_model {
   std::vector<double *> free_[3];
   double *slab = nullptr;
   int slab_cap = 0, slab_next = 0;
+  bool ew_rows = false;    // row-pair form of the diffusion / derive sweeps
+  unsigned ew2_bx = 1;     // its CTAs per row
   std::map<double *, int> refc;  // base pointer (row r0) -> refcount
   std::map<double *, int> kind_of;
 
@@ -825,7 +827,10 @@ static int derive_uv(gmd_model *m, const State &s) {
   if ((r = join(m))) return r;
   if ((r = halo_wait(m))) return r;
   const int ja = std::max(m->geo.r0 - 1, 0), jb = std::min(m->geo.r1 + 1, m->geo.nlat);
-  if (!m->dry) k_derive<<<m->ew_blocks, 256, 0, m->stream>>>(m->geo, ja, jb, s.U, s.V, s.gd, m->w_u, m->w_v, nullptr);
+  if (!m->dry) {
+    if (m->ew_rows) k_derive2<<<dim3(m->ew2_bx, (unsigned)(jb - ja)), EW2, 0, m->stream>>>(m->geo, ja, s.U, s.V, s.gd, m->w_u, m->w_v, nullptr);
+    else k_derive<<<m->ew_blocks, 256, 0, m->stream>>>(m->geo, ja, jb, s.U, s.V, s.gd, m->w_u, m->w_v, nullptr);
+  }
   return post_launch(m);
 }
 
@@ -1601,7 +1606,10 @@ static int diffusion(gmd_model *m, double dt, const State &in, State *out) {
   double *ou = m->d_ud, *ov = m->d_vd, *og = m->d_gdd;
   for (int order = 1; order <= norder; order++) {
     if ((r = halo_wait(m))) return r;
-    if (!m->dry) k_laplace<<<m->ew_blocks, 256, 0, m->stream>>>(m->geo, m->tab, qu, qv, qg, ou, ov, og);
+    if (!m->dry) {
+      if (m->ew_rows) k_laplace2<<<dim3(m->ew2_bx, (unsigned)m->nr), EW2, 0, m->stream>>>(m->geo, m->tab, qu, qv, qg, ou, ov, og);
+      else k_laplace<<<m->ew_blocks, 256, 0, m->stream>>>(m->geo, m->tab, qu, qv, qg, ou, ov, og);
+    }
     if ((r = post_launch(m))) return r;
     if (south || north) {
       if (!m->dry) k_lap_pole<<<2, PT_EW, 0, m->stream>>>(m->geo, m->tab, qg, og, south ? 1 : 0, north ? 1 : 0);
@@ -1620,7 +1628,10 @@ static int diffusion(gmd_model *m, double dt, const State &in, State *out) {
   State N;
   if ((r = new_state(m, &N, nullptr))) return r;
   if ((r = halo_wait(m))) return r;
-  if (!m->dry) k_diff_update<<<m->ew_blocks, 256, 0, m->stream>>>(m->geo, m->w_u, m->w_v, in.gd, ou, ov, og, sdc, N.U, N.V, N.gd);
+  if (!m->dry) {
+    if (m->ew_rows) k_diff_update2<<<dim3(m->ew2_bx, (unsigned)m->nr), EW2, 0, m->stream>>>(m->geo, m->w_u, m->w_v, in.gd, ou, ov, og, sdc, N.U, N.V, N.gd);
+    else k_diff_update<<<m->ew_blocks, 256, 0, m->stream>>>(m->geo, m->w_u, m->w_v, in.gd, ou, ov, og, sdc, N.U, N.V, N.gd);
+  }
   if ((r = post_launch(m))) return r;
   if ((r = exchange_state(m, N, true))) return r;
   *out = N;
@@ -2171,6 +2182,11 @@ int gmd_create(const gmd_config *cfg, gmd_model **out) {
   }
   const size_t total = (size_t)m->nr * nlon;
   m->ew_blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)nsm * 8);
+  // ordinary_diffusion and the derived u, v: the row-pair kernels (k_derive2 / k_laplace2 / k_diff_update2, one row per
+  // blockIdx.y) on a single band; GMD_EW_ROWS=0/1 forces the element-indexed / the row-pair form
+  m->ew2_bx = (unsigned)((nlon / 2 + EW2 - 1) / EW2);
+  m->ew_rows = (cfg->nranks == 1) && (m->nr + 2 <= 65535);
+  if (const char *ev = getenv("GMD_EW_ROWS")) m->ew_rows = (atoi(ev) != 0) && (m->nr + 2 <= 65535);
   {
     const int rmin = std::max(1, std::min(m->rows_per_cta, m->rows_per_cta_s3a));
     const int cmax = (m->nr + rmin - 1) / rmin + 2;

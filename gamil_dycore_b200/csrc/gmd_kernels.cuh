@@ -2541,6 +2541,129 @@ __global__ void __launch_bounds__(256) k_diff_update(Geo g, const double *u, con
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Row-pair forms of k_derive / k_laplace / k_diff_update: one latitude row per blockIdx.y, one column pair per thread
+// (16-byte accesses, the row's metric terms read once per thread, no index division -- the element-indexed kernels
+// above spend ~600 / 280 / 185 instructions per column, mostly on k / nlon and the per-element table reads:
+// profiles/r2_s_ncu_diffusion_summary.txt).  Every value is formed by the same expression as above, so the results are
+// those of the element-indexed kernels.  Plain (coherent) loads: ghost rows of a band are written by the neighbour
+// rank between launches.  num_lon is even (gmd_create), field rows are 16-byte aligned.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int EW2 = 128;
+__device__ __forceinline__ D2 ldp2(const double *p) {
+  const double2 v = *reinterpret_cast<const double2 *>(p);
+  D2 r;
+  r.x = v.x;
+  r.y = v.y;
+  return r;
+}
+
+__global__ void __launch_bounds__(EW2) k_derive2(Geo g, int ja, const double *U, const double *V, const double *gd,
+                                                 double *u, double *v, double *s_out) {
+  const int nlon = g.nlon;
+  const int i = 2 * (blockIdx.x * EW2 + threadIdx.x);
+  if (i >= nlon) return;
+  const int j = ja + (int)blockIdx.y;
+  const int ie = (i + 2 == nlon) ? 0 : i + 2;
+  const ptrdiff_t row = (ptrdiff_t)(j - g.r0) * nlon, o = row + i;
+  const D2 q = ldp2(gd + o);
+  const double s0 = sqrt(q.x), s1 = sqrt(q.y), s2 = sqrt(gd[row + ie]);
+  if (u) {
+    const D2 a = ldp2(U + o);
+    st2(u + o, a.x * 2.0 / (s0 + s1), a.y * 2.0 / (s1 + s2));
+  }
+  if (v && j <= g.nlat - 2) {
+    const D2 a = ldp2(V + o), qn = ldp2(gd + o + nlon);
+    st2(v + o, a.x * 2.0 / (s0 + sqrt(qn.x)), a.y * 2.0 / (s1 + sqrt(qn.y)));
+  }
+  if (s_out) st2(s_out + o, s0, s1);
+}
+
+// (east - 2 q + west) / dl2 + ((north - q) c1 - (q - south) c0) / dt2 * c   (src/diffusion_mod.F90:109-114,135-138,148-157)
+__device__ __forceinline__ double lap5(double q, double qe, double qw, double qn, double qs, double dl2, double dt2,
+                                       double c1, double c0, double c) {
+  return (qe - 2 * q + qw) / dl2 + ((qn - q) * c1 - (q - qs) * c0) / dt2 * c;
+}
+
+__global__ void __launch_bounds__(EW2) k_laplace2(Geo g, Tab t, const double *u, const double *v, const double *gd,
+                                                  double *ud, double *vd, double *gdd) {
+  const int nlon = g.nlon, nlat = g.nlat;
+  const int i = 2 * (blockIdx.x * EW2 + threadIdx.x);
+  if (i >= nlon) return;
+  const int lj = (int)blockIdx.y, j = g.r0 + lj;
+  const int iw = (i == 0) ? nlon - 1 : i - 1, ie = (i + 2 == nlon) ? 0 : i + 2;
+  const ptrdiff_t row = (ptrdiff_t)lj * nlon, k = row + i;
+  if (j >= 1 && j <= nlat - 2) {
+    const double dl2 = t.fdlon[j] * t.fdlon[j], dt2 = t.fdlat[j] * t.fdlat[j];
+    const double hc1 = t.cosh[j], hc0 = t.cosh[j - 1], fc = t.cosf[j];
+    {
+      const D2 q = ldp2(gd + k), qn = ldp2(gd + k + nlon), qs = ldp2(gd + k - nlon);
+      const double qw = gd[row + iw], qe = gd[row + ie];
+      st2(gdd + k, lap5(q.x, q.y, qw, qn.x, qs.x, dl2, dt2, hc1, hc0, fc),
+          lap5(q.y, qe, q.x, qn.y, qs.y, dl2, dt2, hc1, hc0, fc));
+    }
+    {
+      const D2 q = ldp2(u + k), qn = ldp2(u + k + nlon), qs = ldp2(u + k - nlon);
+      const double qw = u[row + iw], qe = u[row + ie];
+      st2(ud + k, lap5(q.x, q.y, qw, qn.x, qs.x, dl2, dt2, hc1, hc0, fc),
+          lap5(q.y, qe, q.x, qn.y, qs.y, dl2, dt2, hc1, hc0, fc));
+    }
+  } else {
+    st2(ud + k, 0.0, 0.0);  // pole rows of ud are never written in the reference (stay 0)
+  }
+  if (j <= nlat - 2) {
+    const D2 q = ldp2(v + k);
+    const double qw = v[row + iw], qe = v[row + ie];
+    const double hl2 = t.hdlon[j] * t.hdlon[j], ht2 = t.hdlat[j] * t.hdlat[j];
+    double r0 = (q.y - 2 * q.x + qw) / hl2, r1 = (qe - 2 * q.y + q.x) / hl2;                      // :145-147
+    if (j >= 1 && j <= nlat - 3) {
+      const D2 qn = ldp2(v + k + nlon), qs = ldp2(v + k - nlon);
+      const double c1 = t.cosf[j + 1], c0 = t.cosf[j], c = t.cosh[j];
+      r0 = r0 + ((qn.x - q.x) * c1 - (q.x - qs.x) * c0) / ht2 * c;                                 // :148-157
+      r1 = r1 + ((qn.y - q.y) * c1 - (q.y - qs.y) * c0) / ht2 * c;
+    } else if (j == 0) {
+      const D2 qn = ldp2(v + k + nlon);
+      const double c1 = t.cosf[j + 1], c = t.cosh[j];
+      r0 = r0 + (qn.x - q.x) * c1 / ht2 * c;                                                       // :158-163
+      r1 = r1 + (qn.y - q.y) * c1 / ht2 * c;
+    } else {
+      const D2 qs = ldp2(v + k - nlon);
+      const double c0 = t.cosf[j], c = t.cosh[j];
+      r0 = r0 - (q.x - qs.x) * c0 / ht2 * c;                                                       // :164-170
+      r1 = r1 - (q.y - qs.y) * c0 / ht2 * c;
+    }
+    st2(vd + k, r0, r1);
+  }
+}
+
+__global__ void __launch_bounds__(EW2) k_diff_update2(Geo g, const double *u, const double *v, const double *gd,
+                                                      const double *ud, const double *vd, const double *gdd,
+                                                      double sdc, double *NU, double *NV, double *Ngd) {
+  const int nlon = g.nlon, nlat = g.nlat;
+  const int i = 2 * (blockIdx.x * EW2 + threadIdx.x);
+  if (i >= nlon) return;
+  const int lj = (int)blockIdx.y, j = g.r0 + lj;
+  const int ie = (i + 2 == nlon) ? 0 : i + 2;
+  const ptrdiff_t row = (ptrdiff_t)lj * nlon, k = row + i;
+  const D2 q = ldp2(gd + k), qd = ldp2(gdd + k);
+  const double g0 = q.x + sdc * qd.x, g1 = q.y + sdc * qd.y;
+  const double ge = gd[row + ie] + sdc * gdd[row + ie];
+  const double s0 = sqrt(g0), s1 = sqrt(g1), se = sqrt(ge);
+  st2(Ngd + k, g0, g1);
+  {
+    const D2 a = ldp2(u + k), ad = ldp2(ud + k);
+    const double un0 = a.x + sdc * ad.x, un1 = a.y + sdc * ad.y;
+    st2(NU + k, 0.5 * (s0 + s1) * un0, 0.5 * (s1 + se) * un1);
+  }
+  if (j <= nlat - 2) {
+    const D2 qn = ldp2(gd + k + nlon), qnd = ldp2(gdd + k + nlon);
+    const double gn0 = qn.x + sdc * qnd.x, gn1 = qn.y + sdc * qnd.y;
+    const D2 a = ldp2(v + k), ad = ldp2(vd + k);
+    const double vn0 = a.x + sdc * ad.x, vn1 = a.y + sdc * ad.y;
+    st2(NV + k, 0.5 * (s0 + sqrt(gn0)) * vn0, 0.5 * (s1 + sqrt(gn1)) * vn1);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // WENO advection (src/weno_mod.F90:69-300), order 2 -- unfused sweeps on derived u, v (a "next" row of the
 // scope table: correct first, fused later).  All arrays are band fields.
 // ---------------------------------------------------------------------------------------------------------
