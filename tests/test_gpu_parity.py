@@ -550,6 +550,40 @@ def test_polar_lean_is_bit_identical(name, monkeypatch):
     assert res[1][1] == res[0][1]
 
 
+@pytest.mark.parametrize("name", ["jz_1440x721_order2", "mz_100x50_order4_unsplit", "mz_96x49_weno"])
+def test_row_pair_diffusion_sweeps_are_bit_identical(name, monkeypatch):
+    """k_derive2 / k_laplace2 / k_diff_update2 (one row per blockIdx.y, one column pair per thread; the default on a
+    single band) form every value by the expression of the element-indexed k_derive / k_laplace / k_diff_update
+    (GMD_EW_ROWS=0): same bits.  Also run by tools/check_ew_rows.py with timings (profiles/r2_s_ew_rows_check.json)."""
+    cases = {
+        "jz_1440x721_order2": ("jet_zonal_flow", dict(num_lon=1440, num_lat=721, time_step_size=30.0, subcycles=6, split_scheme="csp2",
+                                                      zonal_tend_filter_cutoff_wavenumber=[4] * 20, use_diffusion=True,
+                                                      diffusion_coef=6.0e3), 4),
+        # a row of 50 column pairs (one partly filled CTA), an even number of latitudes, two Laplacian passes
+        "mz_100x50_order4_unsplit": ("mountain_zonal_flow", dict(num_lon=100, num_lat=50, time_step_size=600.0, split_scheme="none",
+                                                                use_diffusion=True, diffusion_order=4, diffusion_coef=1.0e14,
+                                                                zonal_tend_filter_cutoff_wavenumber=[4, 4]), 3),
+        # WENO advection reads the derived u, v (k_derive2)
+        "mz_96x49_weno": ("mountain_zonal_flow", dict(num_lon=96, num_lat=49, time_step_size=600.0, subcycles=4, split_scheme="csp2",
+                                                      uv_adv_scheme="weno", zonal_tend_filter_cutoff_wavenumber=[4, 4]), 3),
+    }
+    ic, kw, nsteps = cases[name]
+    u, v, gd, ghs = gmd.initial_condition(ic, kw["num_lon"], kw["num_lat"])
+    res = {}
+    for rows in (1, 0):
+        monkeypatch.setenv("GMD_EW_ROWS", str(rows))
+        d = gmd.Dycore(gmd.Config(**kw))
+        d.set_state(u, v, gd, ghs)
+        d.run_init()
+        d.step(nsteps)
+        res[rows] = (d.state(), d.diag())
+        d.close()
+    assert np.isfinite(res[1][0][2]).all()
+    for p, q in zip(res[1][0], res[0][0]):
+        assert np.array_equal(p, q)
+    assert res[1][1] == res[0][1]
+
+
 FUSED_CASES = {
     # csp2 with the deferred update: slow / fast passes, LAZY 0 / 1 / 2 of k_pc
     "rh_csp2_360x181": ("rossby_haurwitz_wave", dict(num_lon=360, num_lat=181, time_step_size=240.0, subcycles=6, split_scheme="csp2",
