@@ -10,7 +10,9 @@
  *  and cannot be compiled in this image (Fortran only; no gfortran, no netCDF).
  * The oracle is pinned instead by (1) an independent NumPy restatement in tests/np_restatement.py,
  * (2) the invariants the scheme guarantees (mass/energy conservation, operator antisymmetry,
- * steady-state stationarity) and (3) a binary128 build of this same source (-DORC_QUAD).
+ * steady-state stationarity), (3) a binary128 build of this same source (-DORC_QUAD) and (4) known answers of
+ * the continuous problem: second-order convergence to the steady geostrophic solution, the analytic
+ * Rossby-Haurwitz phase speed, the balanced jet without its bump (tests/test_oracle.py).
  *
  * Array exchange format ("compact"): C-contiguous, longitude fastest, no halos, 0-based.
  *   full-lat fields  u, gd, ghs, du, dgd, div : [num_lat][num_lon]
