@@ -460,6 +460,35 @@ def test_rossby_haurwitz_wave_moves_at_the_published_phase_speed():
     assert np.std(shift) < 0.5                                       # the same speed at every latitude: shape preserved
 
 
+def test_shamir_paldor_rossby_wave_moves_at_its_analytic_phase_speed():
+    """A known answer from the linearised equations: the (n, k) = (5, 10) Rossby wave of Shamir & Paldor (2016) on a
+    5 km layer (shallow_water_waves_test_mod.F90) is an eigensolution of the linear shallow-water equations on the sphere
+    that travels westward at the root C of its cubic dispersion relation (:130-171), 3.0 degrees of longitude per day,
+    keeping its shape.  The initial amplitude is 4 m2/s2 on 5e4, so the oracle's full nonlinear step must move the
+    pattern at that speed: projection of zonal wavenumber 10 of gd, u and v on the initial pattern after one day."""
+    lib = orc.load("strict")
+    C = lib.orc_swe_phase_speed(0)
+    cfg = OracleConfig(num_lon=180, num_lat=91, time_step_size=300.0, subcycles=6, split_scheme="csp2",
+                       zonal_tend_filter_cutoff_wavenumber=[12] * 5)     # the filter keeps wavenumber 10
+    o = Oracle(cfg)
+    o.set_initial_condition("shallow_water_waves")
+    f0 = [x.copy() for x in o.state()]
+    o.run_init()
+    nsteps = 288
+    o.step(nsteps)
+    expect = math.degrees(C * nsteps * cfg.time_step_size)
+    assert -3.1 < expect < -2.9
+    k = 10
+    for a0, a1, w in zip(f0, o.state(), (o.table(0), o.table(1), o.table(0))):      # u, v, gd
+        c0, c1 = np.fft.rfft(a0, axis=1)[:, k], np.fft.rfft(a1, axis=1)[:, k]
+        w = w[:len(c0)]
+        z, nrm = np.sum(w * np.conj(c0) * c1), np.sum(w * np.abs(c0) ** 2)
+        shift = math.degrees(-np.angle(z) / k)        # pattern f(lambda - s): the phase of mode k falls by k s
+        assert abs(shift / expect - 1.0) < 0.06, (shift, expect)
+        assert abs(z) / nrm > 0.97                     # the same pattern, not just the same wavenumber
+        assert abs(math.sqrt(np.sum(w * np.abs(c1) ** 2) / nrm) - 1.0) < 0.03
+
+
 def test_pole_rows():
     """u = U = 0 on the pole rows for ever; dgd on a pole row is one zonal constant (cap formula)."""
     cfg = OracleConfig(num_lon=72, num_lat=37, time_step_size=600, subcycles=4,
