@@ -505,6 +505,60 @@ def test_pole_rows():
     assert np.all(u[0] == 0) and np.all(u[-1] == 0) and np.all(iu[0] == 0) and np.all(iu[-1] == 0)
 
 
+def test_reference_behaviour_for_nonzero_u_on_a_pole_row():
+    """What gmd_set_state refuses (include/gmd.h: u on the two pole rows must be 0;
+    tests/test_gpu_parity.py::test_pole_rows_and_reference_layout checks the refusal), shown on the reference's side: the
+    reference would take such a state, the pole-row u enters the first operator evaluation through the four-point
+    Coriolis / advection averages of the rows next to the pole (src/dycore_mod.F90:477-505) -- the answer changes -- and
+    the first update_state then overwrites the pole rows: the tendency loops never write du there (rows 2..nlat-1,
+    :197-364), so U(pole) = 0 + dt * 0.  No IC plugin of the reference produces it (the Shamir-Paldor amplitudes give
+    ~1e-146 there, taken as 0), so the product treats it as a caller error instead of carrying a one-step transient."""
+    kw = dict(num_lon=72, num_lat=37, time_step_size=600.0, subcycles=4, split_scheme="csp2",
+              zonal_tend_filter_cutoff_wavenumber=[4, 4, 4])
+    o = Oracle(OracleConfig(**kw))
+    o.set_initial_condition("mountain_zonal_flow")
+    u, v, gd = o.state()
+    ghs = o.ghs()
+    assert not u[0].any() and not u[-1].any()
+    o.run_init()
+    o.step(1)
+    rng = np.random.default_rng(0)
+    u2 = u.copy()
+    u2[0], u2[-1] = 10.0 * rng.standard_normal(72), 10.0 * rng.standard_normal(72)
+    o2 = Oracle(OracleConfig(**kw))
+    o2.set_state(u2, v, gd, ghs)                  # accepted
+    o2.run_init()
+    o2.step(1)
+    a, b = o.state(), o2.state()
+    assert not b[0][0].any() and not b[0][-1].any()                   # gone after one step ...
+    assert np.abs(b[1] - a[1]).max() > 1e-3 and np.isfinite(b[2]).all()   # ... but it has moved the rows next to the poles
+
+
+def test_reference_behaviour_when_the_filter_rescaling_denominator_is_zero():
+    """The other documented deviation, shown on the reference's side: the
+    SMOOTHING block rescales a filtered tendency row by s1 / s2 (src/dycore_mod.F90:212-219) with s2 the inner product
+    AFTER the filter.  A row whose tendency is a pure two-grid wave (here: a +-8 m2/s2 zigzag in gd and a +-0.5 m/s zigzag
+    in u on the second row from the south pole of a fluid at rest: pressure-gradient and mass-divergence tendencies
+    that alternate exactly) is filtered to exact zeros, s2 = 0 while s1 is not, and the reference divides: NaN rows, then
+    the fatal 'Total mass is NaN!' of diag_run (src/diag_mod.F90:79-87).  The product leaves such a row unscaled when
+    its s2 is exactly 0 instead of aborting."""
+    nlon, nlat = 64, 33
+    o = Oracle(OracleConfig(num_lon=nlon, num_lat=nlat, time_step_size=300.0, split_scheme="none",
+                            zonal_tend_filter_cutoff_wavenumber=[4, 4, 4]))
+    assert o.filter_rows()[0][2] == 1
+    u, v, gd = np.zeros((nlat, nlon)), np.zeros((nlat - 1, nlon)), np.full((nlat, nlon), 5.0e4)
+    zigzag = np.where(np.arange(nlon) % 2 == 0, 1.0, -1.0)
+    gd[2] += 8.0 * zigzag
+    u[2] = 0.5 * zigzag
+    o.set_state(u, v, gd, None)
+    o.run_init()
+    du, dv, dgd = o.space_operators("all")
+    assert np.isnan(du[2]).all() and np.isnan(dgd[2]).all()
+    assert np.isfinite(np.delete(du, 2, axis=0)).all() and np.isfinite(np.delete(dgd, 2, axis=0)).all() and np.isfinite(dv).all()
+    with pytest.raises(orc.OracleError, match="Total mass is NaN"):
+        o.step(1)
+
+
 def test_fast_math_build_is_at_the_noise_floor():
     """The reference is built with -Ofast; our strict and -ffast-math builds of the same source bracket
     what any build of it can reproduce.  One model step must agree to ~1e-11 on a well conditioned case."""
