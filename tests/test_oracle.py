@@ -508,11 +508,12 @@ def test_pole_rows():
 def test_reference_behaviour_for_nonzero_u_on_a_pole_row():
     """What gmd_set_state refuses (include/gmd.h: u on the two pole rows must be 0;
     tests/test_gpu_parity.py::test_pole_rows_and_reference_layout checks the refusal), shown on the reference's side: the
-    reference would take such a state, the pole-row u enters the first operator evaluation through the four-point
-    Coriolis / advection averages of the rows next to the pole (src/dycore_mod.F90:477-505) -- the answer changes -- and
-    the first update_state then overwrites the pole rows: the tendency loops never write du there (rows 2..nlat-1,
-    :197-364), so U(pole) = 0 + dt * 0.  No IC plugin of the reference produces it (the Shamir-Paldor amplitudes give
-    ~1e-146 there, taken as 0), so the product treats it as a caller error instead of carrying a one-step transient."""
+    reference would take such a state.  iap_transform makes U(pole) from it, and because the tendency loops never write
+    du on a pole row (rows 2..nlat-1, src/dycore_mod.F90:197-364) update_state carries that U(pole) unchanged for ever
+    (:626-630) while u(pole) of every later state is never written (the no_pole loop :639-643) and reads 0: an
+    inconsistent pair whose frozen U keeps entering the four-point Coriolis / advection averages of the rows next to the
+    pole (:477-505).  No IC plugin of the reference produces it (the Shamir-Paldor amplitudes give ~1e-146 there, taken
+    as 0), so the product treats it as a caller error instead of carrying a frozen pole wind."""
     kw = dict(num_lon=72, num_lat=37, time_step_size=600.0, subcycles=4, split_scheme="csp2",
               zonal_tend_filter_cutoff_wavenumber=[4, 4, 4])
     o = Oracle(OracleConfig(**kw))
@@ -521,17 +522,20 @@ def test_reference_behaviour_for_nonzero_u_on_a_pole_row():
     ghs = o.ghs()
     assert not u[0].any() and not u[-1].any()
     o.run_init()
-    o.step(1)
+    o.step(3)
     rng = np.random.default_rng(0)
     u2 = u.copy()
     u2[0], u2[-1] = 10.0 * rng.standard_normal(72), 10.0 * rng.standard_normal(72)
     o2 = Oracle(OracleConfig(**kw))
     o2.set_state(u2, v, gd, ghs)                  # accepted
     o2.run_init()
-    o2.step(1)
-    a, b = o.state(), o2.state()
-    assert not b[0][0].any() and not b[0][-1].any()                   # gone after one step ...
-    assert np.abs(b[1] - a[1]).max() > 1e-3 and np.isfinite(b[2]).all()   # ... but it has moved the rows next to the poles
+    U0 = o2.iap_state()[0].copy()
+    assert np.abs(U0[0]).max() > 1e3
+    o2.step(3)
+    a, b, U = o.state(), o2.state(), o2.iap_state()[0]
+    assert not b[0][0].any() and not b[0][-1].any()                            # u(pole) reads 0 from the first step on ...
+    assert np.array_equal(U[0], U0[0]) and np.array_equal(U[-1], U0[-1])       # ... U(pole) is frozen at what it was given
+    assert np.abs(b[1] - a[1]).max() > 1e-3 and np.isfinite(b[2]).all()        # and keeps moving the rows next to the poles
 
 
 def test_reference_behaviour_when_the_filter_rescaling_denominator_is_zero():
