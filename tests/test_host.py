@@ -34,7 +34,7 @@ def write(tmp_path, text, name="namelist"):
 
 
 # ------------------------------------------------------------------------------------------------ C ABI
-@pytest.mark.parametrize("kind", ["fast", "strict"])
+@pytest.mark.parametrize("kind", ["fast", "strict", "trace"])
 def test_library_exports_every_declared_symbol(kind):
     hdr = open(os.path.join(ROOT, "include", "gmd.h")).read()
     names = sorted(set(re.findall(r"\b(gmd_[a-z0-9_]+)\s*\(", hdr)))
@@ -43,6 +43,20 @@ def test_library_exports_every_declared_symbol(kind):
     for n in names:
         assert hasattr(lib, n), n
     assert lib.gmd_version() == 100
+
+
+def test_host_library_exports_every_declared_symbol():
+    hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "gmd_host.h")).read(), flags=re.S)
+    names = sorted(set(re.findall(r"\b(gmd_host_[a-z0-9_]+)\s*\(", hdr)))
+    assert names == ["gmd_host_initial_condition", "gmd_host_last_error"]
+    lib = ctypes.CDLL(os.path.join(ROOT, "gamil_dycore_b200", "libgmd_host.so"))
+    for n in names:
+        assert hasattr(lib, n), n
+    # error behaviour of the plugin selector (src/dycore_test.F90:29-42: unknown test case -> log_error)
+    lib.gmd_host_last_error.restype = ctypes.c_char_p
+    z = (ctypes.c_double * 16)()
+    assert lib.gmd_host_initial_condition(b"no_such_case", 4, 5, z, z, z, z) == 2
+    assert b"no_such_case" in lib.gmd_host_last_error()
 
 
 def test_no_cpu_fallback():
