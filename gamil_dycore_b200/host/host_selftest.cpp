@@ -4,11 +4,15 @@
 //   ic <namelist> <out.bin>          run the IC plugin, dump u, v, gd, ghs as raw doubles
 //   history <namelist> <nsteps>      write one h0 frame of the IC fields as if after nsteps steps; prints the path
 //   clock <namelist> <nsteps>        print the log-line time stamps and alert decisions of the first nsteps steps
+//   tables <namelist> <out.bin>      the product's per-latitude coefficient tables and filter / reduced row maps
+//                                    (csrc/gmd_mesh.h, what gmd_create builds): 10 tables of raw doubles in the order of
+//                                    gmd_get_table, then flag_full, cut_full, flag_half, cut_half, red_full, red_half as int32
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
 
+#include "../csrc/gmd_mesh.h"
 #include "history.h"
 #include "restart.h"
 #include "log.h"
@@ -94,6 +98,25 @@ int main(int argc, char **argv) {
     const bool same = f.u == g.u && f.v == g.v && f.gd == g.gd && f.ghs == g.ghs && t.sec == tm.curr_time.sec;
     printf("%s\n%s\n%s\n", path.c_str(), when.c_str(), same ? "identical" : "DIFFERENT");
     return same ? 0 : 4;
+  }
+  if (cmd == "tables" && argc >= 4) {
+    gmd::HostMesh M;
+    M.init(p.num_lon, p.num_lat, /*reset_poles=*/true);
+    M.filter_init(p.use_zonal_tend_filter, p.zonal_tend_filter_cutoff_wavenumber);
+    if (int bad = M.reduce_init(p.use_zonal_reduce, p.zonal_reduce_factors)) { printf("ERROR: zonal_reduce_factors(%d)\n", bad); return 2; }
+    FILE *o = fopen(argv[3], "wb");
+    if (!o) return 3;
+    const std::vector<double> *tab[10] = {&M.full_cos, &M.half_cos, &M.full_f, &M.full_c, &M.full_dlon,
+                                          &M.half_dlon, &M.full_dlat, &M.half_dlat, &M.full_lat, &M.half_lat};
+    for (int w = 0; w < 10; w++) {
+      const bool half = (w == 1 || w == 5 || w == 7 || w == 9);
+      fwrite(tab[w]->data() + gmd::TPAD, 8, (size_t)(p.num_lat - (half ? 1 : 0)), o);
+    }
+    for (const std::vector<int> *v : {&M.flag_full, &M.cut_full, &M.flag_half, &M.cut_half, &M.red_full, &M.red_half})
+      fwrite(v->data(), 4, (size_t)p.num_lat, o);
+    fclose(o);
+    printf("%d %d %d\n", p.num_lon, p.num_lat, M.cutoff_max);
+    return 0;
   }
   if (cmd == "clock" && argc >= 4) {
     TimeManager tm;

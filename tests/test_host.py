@@ -295,6 +295,46 @@ diffusion_coef = 1.0e5
     assert kv["reduce_factors"] == "8,8,4,2,2" + ",0" * 15
 
 
+# ------------------------------------------------------------------------------------------------ mesh tables
+@pytest.mark.parametrize("nlon,nlat,cut,use_filter", [
+    (72, 37, [5, 4, 3], True), (360, 181, [4] * 5, True), (180, 90, [4, 4, 4], True), (3600, 1801, [4] * 20, True),
+    (7200, 3601, [4] * 20, True), (96, 49, [3, 0, 5], False),
+])
+def test_product_mesh_tables_are_the_oracles_bit_for_bit(tmp_path, nlon, nlat, cut, use_filter):
+    """csrc/gmd_mesh.h (what gmd_create builds on the host and copies to the device: mesh_init, data_init,
+    reset_cos_lat_at_poles, filter_init -- src/mesh_mod.F90:44-114, data_mod.F90:26-47, dycore_mod.F90:159-173,
+    filter_mod.F90:35-103) against the oracle's tables and filter row map, bit for bit, without a GPU (the same check
+    through gmd_get_table is tests/test_gpu_parity.py::test_tables_and_filter_rows_bit_identical)."""
+    nml = write(tmp_path, f"""&dycore_params
+ test_case = 'rossby_haurwitz_wave', num_lon = {nlon}, num_lat = {nlat}, time_step_size = 60
+ use_zonal_tend_filter = {'.true.' if use_filter else '.false.'}
+ zonal_tend_filter_cutoff_wavenumber = {', '.join(map(str, cut))}
+/
+""")
+    out = str(tmp_path / "tables.bin")
+    rc, txt = selftest("tables", nml, out)
+    assert rc == 0, txt
+    assert txt.split() == [str(nlon), str(nlat), str(max(cut))]
+    raw = open(out, "rb").read()
+    o = Oracle(OracleConfig(num_lon=nlon, num_lat=nlat, time_step_size=60.0, use_zonal_tend_filter=use_filter,
+                            zonal_tend_filter_cutoff_wavenumber=cut))
+    o.set_initial_condition("steady_geostrophic_flow")
+    o.run_init()                                   # reset_cos_lat_at_poles happens at the head of dycore_run
+    off = 0
+    for which in range(10):
+        n = nlat - 1 if which in (1, 5, 7, 9) else nlat
+        got = np.frombuffer(raw, dtype=np.float64, count=n, offset=off)
+        off += 8 * n
+        assert np.array_equal(got, o.table(which)), which
+    maps = [np.frombuffer(raw, dtype=np.int32, count=nlat, offset=off + 4 * nlat * k) for k in range(6)]
+    assert len(raw) == off + 6 * 4 * nlat
+    ff, fc, hf, hc = o.filter_rows()
+    assert np.array_equal(maps[0], ff) and np.array_equal(maps[1], fc)
+    assert np.array_equal(maps[2][:nlat - 1], hf) and np.array_equal(maps[3][:nlat - 1], hc)
+    assert not maps[4].any() and not maps[5].any()        # no reduced rows configured
+    assert ff.sum() == (2 * sum(1 for c in cut if c) if use_filter else 0)
+
+
 # ------------------------------------------------------------------------------------------------ formats
 @pytest.mark.parametrize("x,s", [(2.812376625197987e19, "0.28123766251980E+20"), (5.083437998896658e12, "0.50834379988967E+13"),
                                  (1.0000123, "0.10000123000000E+01"), (-0.5, "-0.5000000000000E+00"), (0.0, "0.00000000000000E+00"),
